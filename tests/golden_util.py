@@ -1,0 +1,30 @@
+"""Loader for tests/golden/*.npz (made by oracle/make_golden.py from the unmodified reference)."""
+import glob
+import json
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def case_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    shape = tuple(int(v) for v in z["shape"])
+    cube = np.zeros(shape, dtype=np.float32)
+    cube[:, z["kept_bands"], :] = z["cube_kept"]
+    case = dict(name=name, cube=cube, flags=json.loads(str(z["flags"])), libname=str(z["libname"]),
+                active=[int(z["active"][0]), int(z["active"][1])], product=z["product"],
+                header=json.loads(str(z["header"])), stdout_avg=z["stdout_avg"],
+                stdout_std=z["stdout_std"])
+    if "bgmeta" in z.files:
+        case["bgmeta"] = z["bgmeta"]
+        case["bgmeta_header"] = json.loads(str(z["bgmeta_header"]))
+    flags = case["flags"]
+    case["model"] = flags[flags.index("-M") + 1] if "-M" in flags else "looshrinkage"
+    case["reflectance"] = "-R" in flags
+    return case
