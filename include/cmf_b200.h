@@ -1,0 +1,131 @@
+/* cmf_b200.h -- C ABI of the B200-native columnwise matched filter (libcmf_b200.so).
+ *
+ * The reference (dsmbgu8/srcfinder, cmf/robust_mf.py) exposes no FFI: its boundary is the CLI
+ * (robust_mf.py:142-166), the ENVI products it writes (:210-279, :383-403) and the importable
+ * looshrinkage(I_zm, alphas, nll, n, I_reg) (:92-136).  This header is the boundary a maintainer
+ * binds instead of the body of the column loop (:297-397); INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions: every function returns 0 on success or a negative CMF_E_* code and never throws;
+ * cmf_last_error() gives the message.  The caller owns host buffers, the context owns device
+ * buffers.  One context per (GPU, stream); a context is not thread-safe, independent contexts are.
+ * All entry points are asynchronous on the context's stream unless stated; cmf_sync() waits.
+ * There is no CPU fallback: without a CUDA device cmf_create() fails with CMF_E_CUDA.
+ */
+#ifndef CMF_B200_H
+#define CMF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cmf_ctx cmf_ctx;
+
+enum {
+    CMF_OK = 0,
+    CMF_E_ARG = -1,      /* bad argument / unsupported configuration */
+    CMF_E_CUDA = -2,     /* CUDA runtime error (message has the detail) */
+    CMF_E_STATE = -3,    /* call sequence error (e.g. run before set_problem / upload) */
+    CMF_E_NOMEM = -4
+};
+
+enum { CMF_MODEL_LOOSHRINKAGE = 0, CMF_MODEL_EMPIRICAL = 1 };      /* -M, robust_mf.py:159-160 */
+enum { CMF_INTERLEAVE_BIL = 0 };                                  /* the reference requires BIL, :208 */
+
+/* Per-column status bits returned by CMF_OUT_STATUS. */
+enum {
+    CMF_COL_OK = 0,
+    CMF_COL_EMPTY = 1,        /* no valid pixel; column skipped (:303-304) */
+    CMF_COL_DEGENERATE = 2,   /* a single valid pixel: NaN scores, alpha index 0 (reference behaviour) */
+    CMF_COL_SINGULAR = 4,     /* C not invertible: scores := 0 ("singular matrix", :371-374) */
+    CMF_COL_NOCONVERGE = 8,   /* eigen-solver hit its sweep cap */
+    CMF_COL_ALLINF = 16       /* every nll inf: alpha := 0, index -1 (:123-127) */
+};
+
+/* What cmf_download()/cmf_device_ptr() can return.  Shapes use L lines, S samples, D active bands,
+ * A alphas, DP = D rounded up to a multiple of 8. */
+enum {
+    CMF_OUT_MF = 0,           /* double [L][S]   matched-filter score (ppm*m), nodata where masked (:266,:383-386) */
+    CMF_OUT_MASK = 1,         /* uint8  [L][S]   1 = pixel used (finite and >= 0 in every active band, :282) */
+    CMF_OUT_COLSTATS = 2,     /* double [3][S]   npix, mean, std(ddof=0) of the written scores (:388-391) */
+    CMF_OUT_ALPHA_INDEX = 3,  /* int32  [S]      argmin index, -1 all-inf, -2 not applicable (:121-127) */
+    CMF_OUT_NLL = 4,          /* double [S][A]   leave-one-out negative log likelihood (:117) */
+    CMF_OUT_MU = 5,           /* double [S][DP]  column mean over valid pixels (:347) */
+    CMF_OUT_WEIGHTS = 6,      /* double [S][DP]  Cinv t / (t Cinv t) * scale (:380-384) */
+    CMF_OUT_STATUS = 7,       /* int32  [S]      CMF_COL_* bits */
+    CMF_OUT_NVALID = 8,       /* int32  [S]      valid pixels per column (nuse, :302) */
+    CMF_OUT_EIGVALS = 9,      /* double [S][DP]  eigenvalues of the column correlation matrix */
+    CMF_OUT_SWEEPS = 10       /* int32  [S]      Jacobi sweeps used */
+};
+
+typedef struct cmf_problem {
+    int32_t lines, bands, samples;   /* cube shape (L, B, S), ENVI BIL: element (l,b,s) at (l*B+b)*S+s */
+    int32_t interleave;              /* CMF_INTERLEAVE_BIL */
+    int32_t band_lo, band_hi;        /* 1-based inclusive active window, e.g. 351..422 (:186-194) */
+    int32_t reflectance;             /* -R: target = abscf - mu, no ppm scaling (:379,:383) */
+    int32_t model;                   /* CMF_MODEL_* */
+    int32_t num_alphas;              /* 201 in the reference (:241-243); ignored for EMPIRICAL */
+    int32_t reserved;
+    double nodata;                   /* 'data ignore value', must be <= 0 (:232-234) */
+    const double* alphas;            /* [num_alphas] host */
+    const double* abscf;             /* [band_hi-band_lo+1] host: library column 3 over the window (:237-238) */
+} cmf_problem;
+
+/* ---- lifetime ---- */
+int cmf_create(cmf_ctx** out, int device);
+void cmf_destroy(cmf_ctx* ctx);
+const char* cmf_last_error(const cmf_ctx* ctx);   /* ctx may be NULL: error of the last failed cmf_create */
+const char* cmf_version(void);
+
+/* Use an existing CUDA stream (cudaStream_t as void*) instead of the context's own. */
+int cmf_set_stream(cmf_ctx* ctx, void* cuda_stream);
+
+/* ---- problem + input ---- */
+int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p);
+/* Host cube (L,B,S) float32 BIL -> device: only the active band window is transferred
+ * (one strided H2D copy; pinned memory makes it asynchronous).  Replaces the memmap gather at :298. */
+int cmf_upload_bil(cmf_ctx* ctx, const float* host_cube);
+/* Input already on the device: pointer to element (line 0, band band_lo, sample 0); consecutive lines are
+ * line_pitch floats apart, consecutive bands band_pitch floats apart (a full BIL cube: B*S and S). */
+int cmf_bind_device_slab(cmf_ctx* ctx, const float* dev_slab, int64_t line_pitch, int32_t band_pitch);
+
+/* ---- compute: the whole column loop (:297-392) for every column, no host round trip ---- */
+enum { CMF_RUN_TIMING = 1 };      /* bracket every kernel with CUDA events (see cmf_kernel_times) */
+int cmf_run(cmf_ctx* ctx, uint32_t flags);
+int cmf_sync(cmf_ctx* ctx);
+
+/* Upload + run + download of scores / column statistics / alpha indices in one call; overlaps the
+ * H2D copy with the first pass block by block.  Any output pointer may be NULL.  Synchronous. */
+int cmf_run_host(cmf_ctx* ctx, const float* host_cube, double* mf_out, double* colstats_out,
+                 int32_t* alpha_index_out, uint32_t flags);
+
+/* ---- results ---- */
+int cmf_download(cmf_ctx* ctx, int what, void* host_dst, size_t bytes);   /* synchronous */
+void* cmf_device_ptr(cmf_ctx* ctx, int what);                            /* NULL if not available */
+size_t cmf_output_bytes(const cmf_ctx* ctx, int what);
+
+/* ---- instrumentation ---- */
+int cmf_kernel_count(void);
+const char* cmf_kernel_name(int i);
+/* milliseconds of each kernel in the last cmf_run(CMF_RUN_TIMING); returns the number written */
+int cmf_kernel_times(cmf_ctx* ctx, float* ms, int n);
+/* launches issued by the last cmf_run()/cmf_run_host() */
+int cmf_launch_count(const cmf_ctx* ctx);
+
+/* ---- pinned host memory helpers (for asynchronous uploads) ---- */
+void* cmf_host_alloc(size_t bytes);
+void cmf_host_free(void* p);
+int cmf_host_register(void* p, size_t bytes);
+int cmf_host_unregister(void* p);
+
+/* ---- micro-benchmarks used for the roofline denominators (profiles/): returns achieved rate ---- */
+/* kind: 0 DMMA.8x8x4 TFLOP/s, 1 DFMA TFLOP/s, 2 HBM read GB/s (8-byte loads), 3 HBM read GB/s (16-byte),
+ *       4 HBM copy GB/s, 5 bulk-async-copy read GB/s */
+double cmf_microbench(int device, int kind, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMF_B200_H */

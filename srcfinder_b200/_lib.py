@@ -1,0 +1,78 @@
+"""ctypes binding of libcmf_b200.so (include/cmf_b200.h).  No fallback: if the library is missing or
+no CUDA device is present the caller gets an exception."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcmf_b200.so")
+
+# every symbol include/cmf_b200.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = [
+    "cmf_create", "cmf_destroy", "cmf_last_error", "cmf_version", "cmf_set_stream", "cmf_set_problem",
+    "cmf_upload_bil", "cmf_bind_device_slab", "cmf_run", "cmf_sync", "cmf_run_host", "cmf_download",
+    "cmf_device_ptr", "cmf_output_bytes", "cmf_kernel_count", "cmf_kernel_name", "cmf_kernel_times",
+    "cmf_launch_count", "cmf_host_alloc", "cmf_host_free", "cmf_host_register", "cmf_host_unregister",
+    "cmf_microbench",
+]
+
+OUT_MF, OUT_MASK, OUT_COLSTATS, OUT_ALPHA_INDEX, OUT_NLL, OUT_MU, OUT_WEIGHTS, OUT_STATUS, OUT_NVALID, \
+    OUT_EIGVALS, OUT_SWEEPS = range(11)
+RUN_TIMING = 1
+MODEL_LOOSHRINKAGE, MODEL_EMPIRICAL = 0, 1
+COL_EMPTY, COL_DEGENERATE, COL_SINGULAR, COL_NOCONVERGE, COL_ALLINF = 1, 2, 4, 8, 16
+
+
+class Problem(C.Structure):
+    _fields_ = [
+        ("lines", C.c_int32), ("bands", C.c_int32), ("samples", C.c_int32), ("interleave", C.c_int32),
+        ("band_lo", C.c_int32), ("band_hi", C.c_int32), ("reflectance", C.c_int32), ("model", C.c_int32),
+        ("num_alphas", C.c_int32), ("reserved", C.c_int32), ("nodata", C.c_double),
+        ("alphas", C.POINTER(C.c_double)), ("abscf", C.POINTER(C.c_double)),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library and declare every prototype.  Raises OSError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OSError("libcmf_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(srcfinder_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, u32, i64, sz = C.c_void_p, C.c_int32, C.c_uint32, C.c_int64, C.c_size_t
+    sig = {
+        "cmf_create": (C.c_int, [C.POINTER(vp), C.c_int]),
+        "cmf_destroy": (None, [vp]),
+        "cmf_last_error": (C.c_char_p, [vp]),
+        "cmf_version": (C.c_char_p, []),
+        "cmf_set_stream": (C.c_int, [vp, vp]),
+        "cmf_set_problem": (C.c_int, [vp, C.POINTER(Problem)]),
+        "cmf_upload_bil": (C.c_int, [vp, vp]),
+        "cmf_bind_device_slab": (C.c_int, [vp, vp, i64, i32]),
+        "cmf_run": (C.c_int, [vp, u32]),
+        "cmf_sync": (C.c_int, [vp]),
+        "cmf_run_host": (C.c_int, [vp, vp, vp, vp, vp, u32]),
+        "cmf_download": (C.c_int, [vp, C.c_int, vp, sz]),
+        "cmf_device_ptr": (vp, [vp, C.c_int]),
+        "cmf_output_bytes": (sz, [vp, C.c_int]),
+        "cmf_kernel_count": (C.c_int, []),
+        "cmf_kernel_name": (C.c_char_p, [C.c_int]),
+        "cmf_kernel_times": (C.c_int, [vp, C.POINTER(C.c_float), C.c_int]),
+        "cmf_launch_count": (C.c_int, [vp]),
+        "cmf_host_alloc": (vp, [sz]),
+        "cmf_host_free": (None, [vp]),
+        "cmf_host_register": (C.c_int, [vp, sz]),
+        "cmf_host_unregister": (C.c_int, [vp]),
+        "cmf_microbench": (C.c_double, [C.c_int, C.c_int, C.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib

@@ -1,0 +1,191 @@
+"""Host-side driver of the CUDA columnwise matched filter: one object per (GPU, problem shape).
+
+Mirrors the inputs of the reference's column loop (cmf/robust_mf.py:297-397): a float32 BIL cube, the
+1-based active band window, the unit-absorption coefficients over that window, the model name and the
+alpha grid.  All arithmetic happens in libcmf_b200.so; this module only moves pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+PPM_SCALING = 100000.0
+
+
+def alpha_grid(aminexp=-10.0, amaxexp=0.0, astep=0.05):
+    """The reference's 201 shrinkage candidates (cmf/robust_mf.py:241-243)."""
+    return 10.0 ** np.arange(aminexp, amaxexp + astep, astep)
+
+
+class CmfError(RuntimeError):
+    pass
+
+
+class ColumnwiseMF(object):
+    """GPU columnwise matched filter for cubes of one shape."""
+
+    def __init__(self, lines, bands, samples, active, abscf, model="looshrinkage", reflectance=False,
+                 alphas=None, nodata=-9999.0, device=0, stream=None):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        rc = self._lib.cmf_create(C.byref(self._ctx), int(device))
+        if rc != 0:
+            raise CmfError("cmf_create failed (%d): %s" % (rc, self._lib.cmf_last_error(None).decode()))
+        self.L, self.B, self.S = int(lines), int(bands), int(samples)
+        self.active = [int(active[0]), int(active[1])]
+        self.D = self.active[1] - self.active[0] + 1
+        self.DP = (self.D + 7) // 8 * 8
+        self.model = model
+        self.reflectance = bool(reflectance)
+        self.nodata = float(nodata)
+        self.device = int(device)
+        if model not in ("looshrinkage", "empirical"):
+            raise CmfError("unknown model %r" % (model,))
+        self.alphas = np.ascontiguousarray(alpha_grid() if alphas is None else alphas, dtype=np.float64)
+        self.A = len(self.alphas) if model == "looshrinkage" else 1
+        ab = np.ascontiguousarray(abscf, dtype=np.float64)
+        if ab.shape != (self.D,):
+            raise CmfError("abscf must have %d entries (active window), got %r" % (self.D, ab.shape))
+        p = _lib.Problem()
+        p.lines, p.bands, p.samples, p.interleave = self.L, self.B, self.S, 0
+        p.band_lo, p.band_hi = self.active
+        p.reflectance = int(self.reflectance)
+        p.model = _lib.MODEL_LOOSHRINKAGE if model == "looshrinkage" else _lib.MODEL_EMPIRICAL
+        p.num_alphas = len(self.alphas)
+        p.nodata = self.nodata
+        p.alphas = self.alphas.ctypes.data_as(C.POINTER(C.c_double))
+        p.abscf = ab.ctypes.data_as(C.POINTER(C.c_double))
+        if stream is not None:
+            self._check(self._lib.cmf_set_stream(self._ctx, C.c_void_p(int(stream))))
+        self._check(self._lib.cmf_set_problem(self._ctx, C.byref(p)))
+        self._keep = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise CmfError("libcmf_b200 error %d: %s" % (rc, self._lib.cmf_last_error(self._ctx).decode()))
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.cmf_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ input
+    def upload(self, cube_lbs):
+        """Host (L, B, S) float32 BIL cube -> device (only the active window is copied)."""
+        cube = np.ascontiguousarray(cube_lbs, dtype=np.float32)
+        if cube.shape != (self.L, self.B, self.S):
+            raise CmfError("cube shape %r != %r" % (cube.shape, (self.L, self.B, self.S)))
+        self._keep = cube
+        self._check(self._lib.cmf_upload_bil(self._ctx, C.c_void_p(cube.ctypes.data)))
+
+    def bind_device(self, dev_ptr, line_pitch=None, band_pitch=None):
+        """Device-resident slab: pointer to (line 0, band active[0], sample 0)."""
+        lp = self.D * self.S if line_pitch is None else int(line_pitch)
+        bp = self.S if band_pitch is None else int(band_pitch)
+        self._check(self._lib.cmf_bind_device_slab(self._ctx, C.c_void_p(int(dev_ptr)), lp, bp))
+
+    # ------------------------------------------------------------------ compute
+    def run(self, timing=False, sync=True):
+        self._check(self._lib.cmf_run(self._ctx, _lib.RUN_TIMING if timing else 0))
+        if sync:
+            self.sync()
+
+    def sync(self):
+        self._check(self._lib.cmf_sync(self._ctx))
+
+    def run_host(self, host_ptr, mf_out=None, colstats_out=None, alpha_out=None):
+        """End-to-end call on a host cube pointer (int address): H2D + all kernels + D2H, synchronous."""
+        def addr(a):
+            return C.c_void_p(None if a is None else int(a))
+        self._check(self._lib.cmf_run_host(self._ctx, C.c_void_p(int(host_ptr)), addr(mf_out),
+                                           addr(colstats_out), addr(alpha_out), 0))
+
+    def kernel_times(self):
+        n = self._lib.cmf_kernel_count()
+        buf = (C.c_float * n)()
+        got = self._lib.cmf_kernel_times(self._ctx, buf, n)
+        if got < 0:
+            self._check(got)
+        return {self._lib.cmf_kernel_name(i).decode(): float(buf[i]) for i in range(got)}
+
+    def launch_count(self):
+        return int(self._lib.cmf_launch_count(self._ctx))
+
+    def device_ptr(self, what):
+        return self._lib.cmf_device_ptr(self._ctx, int(what))
+
+    # ------------------------------------------------------------------ results
+    def _get(self, what, dtype, shape):
+        out = np.empty(shape, dtype=dtype)
+        self._check(self._lib.cmf_download(self._ctx, int(what), C.c_void_p(out.ctypes.data), out.nbytes))
+        return out
+
+    def mf(self):
+        return self._get(_lib.OUT_MF, np.float64, (self.L, self.S))
+
+    def mask(self):
+        return self._get(_lib.OUT_MASK, np.uint8, (self.L, self.S)).astype(bool)
+
+    def colstats(self):
+        """(3, S): npix, mean, std of the written scores; nodata for skipped columns."""
+        return self._get(_lib.OUT_COLSTATS, np.float64, (3, self.S))
+
+    def alpha_index(self):
+        return self._get(_lib.OUT_ALPHA_INDEX, np.int32, (self.S,))
+
+    def nll(self):
+        return self._get(_lib.OUT_NLL, np.float64, (self.S, self.A))
+
+    def mu(self):
+        return self._get(_lib.OUT_MU, np.float64, (self.S, self.DP))[:, :self.D]
+
+    def weights(self):
+        return self._get(_lib.OUT_WEIGHTS, np.float64, (self.S, self.DP))[:, :self.D]
+
+    def status(self):
+        return self._get(_lib.OUT_STATUS, np.int32, (self.S,))
+
+    def nvalid(self):
+        return self._get(_lib.OUT_NVALID, np.int32, (self.S,))
+
+    def eigvals(self):
+        return self._get(_lib.OUT_EIGVALS, np.float64, (self.S, self.DP))[:, :self.D]
+
+    def sweeps(self):
+        return self._get(_lib.OUT_SWEEPS, np.int32, (self.S,))
+
+    def results(self):
+        cs = self.colstats()
+        return dict(mf=self.mf(), mask=self.mask(), colnum=cs[0], colavg=cs[1], colstd=cs[2],
+                    alpha_index=self.alpha_index(), mu=self.mu(), weights=self.weights(),
+                    status=self.status())
+
+
+def cmf_cube(cube_lbs, abscf, active, model="looshrinkage", reflectance=False, alphas=None,
+             nodata=-9999.0, device=0):
+    """One-shot convenience: same inputs/outputs as the oracle's ``cmf_cube`` (for parity tests)."""
+    L, B, S = cube_lbs.shape
+    with ColumnwiseMF(L, B, S, active, abscf, model=model, reflectance=reflectance, alphas=alphas,
+                      nodata=nodata, device=device) as eng:
+        eng.upload(cube_lbs)
+        eng.run()
+        res = eng.results()
+        if model == "looshrinkage":
+            res["nll"] = eng.nll()
+        return res

@@ -1,0 +1,458 @@
+// Host side of the C ABI (include/cmf_b200.h): context, device buffers, the kernel sequence.
+// No arithmetic happens here and nothing falls back to the CPU.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/cmf_b200.h"
+#include "cmf_internal.h"
+
+using namespace cmf;
+
+namespace {
+
+enum { K_REPACK = 0, K_MEAN, K_GRAM, K_EIGEN, K_LOO, K_FINALIZE, K_SCORE, K_COLSTATS, K_COUNT };
+const char* kKernelNames[K_COUNT] = {"repack", "mean", "gram", "eigen", "loo", "finalize", "score",
+                                     "colstats"};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct cmf_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    bool have_problem = false;
+    Dims d{};
+    int B = 0, band_lo = 0, band_hi = 0, reflectance = 0, model = 0;
+    double nodata = -9999.0, scale = 1.0e5;
+
+    // input
+    const float* slab = nullptr;     // view used by the kernels (element: line 0, band_lo, sample 0)
+    float* slab_own = nullptr;       // allocated by cmf_upload_bil / cmf_run_host
+    bool have_input = false;
+
+    // work + output buffers
+    std::vector<void*> allocs;
+    float* xt = nullptr;
+    uint8_t* mask = nullptr;
+    double *colsum_part = nullptr, *mu = nullptr, *gram_part = nullptr, *P = nullptr, *Pf = nullptr,
+           *Wf = nullptr, *lam = nullptr, *logdet = nullptr, *beta = nullptr, *fpart = nullptr,
+           *nll = nullptr, *w = nullptr, *wT = nullptr, *c0 = nullptr, *mf = nullptr, *stat_part = nullptr,
+           *colstats = nullptr, *alphas_d = nullptr, *abscf_d = nullptr;
+    int *colcnt_part = nullptr, *n = nullptr, *status = nullptr, *sweeps = nullptr, *mindex = nullptr;
+    int nsplit = 1, lps = 8, nchunk_gram = 1, nchunk_loo = 1, nlanes = 1;
+
+    cudaEvent_t ev[K_COUNT + 1] = {};
+    std::vector<cudaEvent_t> blk_ev;
+    bool timed = false;
+    int launches = 0;
+};
+
+namespace {
+
+int fail(cmf_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(ctx, CMF_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+void free_buffers(cmf_ctx* c) {
+    for (void* p : c->allocs) cudaFree(p);
+    c->allocs.clear();
+    if (c->slab_own) { cudaFree(c->slab_own); c->slab_own = nullptr; }
+    c->have_input = false;
+    c->slab = nullptr;
+}
+
+template <typename T>
+cudaError_t dalloc(cmf_ctx* c, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) { c->allocs.push_back(q); *p = reinterpret_cast<T*>(q); }
+    return e;
+}
+
+// Launch the eight kernels on the context stream.  When `blocks_ready` is given, the repack pass runs
+// block by block, each block waiting on the event that marks its upload as complete.
+int enqueue(cmf_ctx* ctx, bool timing, const std::vector<cudaEvent_t>* blocks_ready, int lines_per_block) {
+    const Dims& d = ctx->d;
+    cudaStream_t st = ctx->stream;
+    ctx->launches = 0;
+    auto mark = [&](int i) { if (timing) cudaEventRecord(ctx->ev[i], st); };
+    mark(0);
+    if (blocks_ready) {
+        int line = 0;
+        for (size_t b = 0; b < blocks_ready->size(); ++b) {
+            const int lim = std::min(d.L, line + lines_per_block);
+            cudaStreamWaitEvent(st, (*blocks_ready)[b], 0);
+            launch_repack(d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, line,
+                          lim, st);
+            ++ctx->launches;
+            line = lim;
+        }
+    } else {
+        launch_repack(d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, 0, d.L,
+                      st);
+        ++ctx->launches;
+    }
+    mark(1);
+    launch_mean(d, ctx->colsum_part, ctx->colcnt_part, ctx->nsplit, ctx->mu, ctx->n, st);
+    mark(2);
+    launch_gram(d, ctx->xt, ctx->mu, ctx->nchunk_gram, ctx->gram_part, st);
+    mark(3);
+    launch_eigen(d, ctx->gram_part, ctx->nchunk_gram, ctx->n, ctx->alphas_d, ctx->model, ctx->P, ctx->Pf,
+                 ctx->Wf, ctx->lam, ctx->logdet, ctx->beta, ctx->status, ctx->sweeps, st);
+    mark(4);
+    ctx->launches += 3;
+    if (ctx->model == CMF_MODEL_LOOSHRINKAGE) {
+        launch_loo(d, ctx->xt, ctx->mu, ctx->Pf, ctx->Wf, ctx->beta, ctx->nchunk_loo, ctx->fpart, st);
+        ++ctx->launches;
+    }
+    mark(5);
+    launch_finalize(d, ctx->fpart, ctx->nchunk_loo, ctx->logdet, ctx->n, ctx->alphas_d, ctx->P, ctx->lam,
+                    ctx->mu, ctx->abscf_d, ctx->model, ctx->reflectance, ctx->scale, ctx->nll, ctx->mindex,
+                    ctx->w, ctx->wT, ctx->c0, ctx->status, st);
+    mark(6);
+    launch_score(d, ctx->slab, ctx->mask, ctx->wT, ctx->c0, ctx->status, ctx->nodata, ctx->mf, ctx->stat_part,
+                 ctx->nlanes, st);
+    mark(7);
+    launch_colstats(d, ctx->stat_part, ctx->nlanes, ctx->n, ctx->nodata, ctx->colstats, st);
+    mark(8);
+    ctx->launches += 3;
+    ctx->timed = timing;
+    CK(cudaGetLastError());
+    return CMF_OK;
+}
+
+int ensure_own_slab(cmf_ctx* ctx) {
+    const Dims& d = ctx->d;
+    if (!ctx->slab_own) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, (size_t)d.L * d.D * d.S * sizeof(float));
+        if (e != cudaSuccess) return fail(ctx, CMF_E_NOMEM, std::string("slab alloc: ") + cudaGetErrorString(e));
+        ctx->slab_own = reinterpret_cast<float*>(q);
+    }
+    ctx->slab = ctx->slab_own;
+    ctx->d.line_pitch = (long long)d.D * d.S;
+    ctx->d.band_pitch = d.S;
+    ctx->d.vec2 = (d.S % 2 == 0) ? 1 : 0;
+    return CMF_OK;
+}
+
+struct OutDesc { void* ptr; size_t bytes; };
+
+OutDesc out_desc(const cmf_ctx* c, int what) {
+    const Dims& d = c->d;
+    const size_t LS = (size_t)d.L * d.S;
+    switch (what) {
+        case CMF_OUT_MF: return {c->mf, LS * sizeof(double)};
+        case CMF_OUT_MASK: return {c->mask, LS};
+        case CMF_OUT_COLSTATS: return {c->colstats, (size_t)3 * d.S * sizeof(double)};
+        case CMF_OUT_ALPHA_INDEX: return {c->mindex, (size_t)d.S * sizeof(int)};
+        case CMF_OUT_NLL: return {c->nll, (size_t)d.S * d.A * sizeof(double)};
+        case CMF_OUT_MU: return {c->mu, (size_t)d.S * d.DP * sizeof(double)};
+        case CMF_OUT_WEIGHTS: return {c->w, (size_t)d.S * d.DP * sizeof(double)};
+        case CMF_OUT_STATUS: return {c->status, (size_t)d.S * sizeof(int)};
+        case CMF_OUT_NVALID: return {c->n, (size_t)d.S * sizeof(int)};
+        case CMF_OUT_EIGVALS: return {c->lam, (size_t)d.S * d.DP * sizeof(double)};
+        case CMF_OUT_SWEEPS: return {c->sweeps, (size_t)d.S * sizeof(int)};
+        default: return {nullptr, 0};
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cmf_version(void) { return "cmf_b200 0.1 (sm_100a)"; }
+
+int cmf_create(cmf_ctx** out, int device) {
+    cmf_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, CMF_E_ARG, "cmf_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, CMF_E_CUDA,
+                    std::string("cmf_create: no CUDA device (") + cudaGetErrorString(e) +
+                        "); this library has no CPU path");
+    if (device < 0 || device >= ndev) return fail(nullptr, CMF_E_ARG, "cmf_create: bad device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CMF_E_CUDA, cudaGetErrorString(e));
+    ctx = new cmf_ctx();
+    ctx->device = device;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    for (int i = 0; i <= K_COUNT; ++i) CK(cudaEventCreate(&ctx->ev[i]));
+    *out = ctx;
+    return CMF_OK;
+}
+
+void cmf_destroy(cmf_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_buffers(ctx);
+    for (int i = 0; i <= K_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (cudaEvent_t e : ctx->blk_ev) cudaEventDestroy(e);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+const char* cmf_last_error(const cmf_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int cmf_set_stream(cmf_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return CMF_E_ARG;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+    return CMF_OK;
+}
+
+int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
+    if (!ctx || !p) return CMF_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (p->interleave != CMF_INTERLEAVE_BIL) return fail(ctx, CMF_E_ARG, "only BIL input is supported (robust_mf.py:208)");
+    if (p->lines <= 0 || p->bands <= 0 || p->samples <= 0) return fail(ctx, CMF_E_ARG, "bad cube shape");
+    if (p->band_lo < 1 || p->band_hi > p->bands || p->band_hi < p->band_lo)
+        return fail(ctx, CMF_E_ARG, "active band window outside the cube");
+    if (p->nodata > 0) return fail(ctx, CMF_E_ARG, "nodata value > 0, values will not be masked (robust_mf.py:233-234)");
+    if (!p->abscf) return fail(ctx, CMF_E_ARG, "abscf is NULL");
+    const int D = p->band_hi - p->band_lo + 1;
+    const int NT = (D + 7) / 8;
+    if (NT > kMaxNT)
+        return fail(ctx, CMF_E_ARG, "active window wider than 96 bands is not supported by this build");
+    const bool loo = p->model == CMF_MODEL_LOOSHRINKAGE;
+    if (!loo && p->model != CMF_MODEL_EMPIRICAL) return fail(ctx, CMF_E_ARG, "unknown model");
+    if (loo && (p->num_alphas < 1 || p->num_alphas > 4096 || !p->alphas))
+        return fail(ctx, CMF_E_ARG, "looshrinkage needs 1..4096 alphas");
+
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_buffers(ctx);
+    Dims& d = ctx->d;
+    d.L = p->lines; d.S = p->samples; d.D = D; d.NT = NT; d.DP = 8 * NT;
+    d.A = loo ? p->num_alphas : 1;
+    d.NT2 = (d.A + 7) / 8; d.AP = d.NT2 * 8;
+    d.line_pitch = (long long)D * d.S; d.band_pitch = d.S; d.vec2 = (d.S % 2 == 0);
+    ctx->B = p->bands; ctx->band_lo = p->band_lo; ctx->band_hi = p->band_hi;
+    ctx->reflectance = p->reflectance; ctx->model = p->model; ctx->nodata = p->nodata;
+    ctx->scale = p->reflectance ? 1.0 : 1.0e5;   // ppmscaling, robust_mf.py:38,:383-386
+
+    ctx->nsplit = repack_nsplit(d);
+    ctx->lps = repack_lines_per_split(d, ctx->nsplit);
+    ctx->nsplit = (d.L + ctx->lps - 1) / ctx->lps;
+    ctx->nchunk_gram = pick_chunks(d.S, d.L, 256, ctx->sm_count, 1);
+    ctx->nchunk_loo = pick_chunks(d.S, d.L, 128, ctx->sm_count, 1);
+    const int ngroups = (d.L + kScoreLines - 1) / kScoreLines;
+    const int SC = d.vec2 ? (d.S + 1) / 2 : d.S;
+    int want = std::max(1, (ctx->sm_count * 1536) / SC);
+    int per = (ngroups + want - 1) / want;
+    ctx->nlanes = (ngroups + per - 1) / per;
+
+    const size_t LS = (size_t)d.L * d.S;
+    const int Sp = (d.S + 1) & ~1;
+    const size_t frag = (size_t)(d.DP / 4) * 32;
+    cudaError_t e = cudaSuccess;
+    auto A_ = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A_(dalloc(ctx, &ctx->xt, LS * d.DP));
+    A_(dalloc(ctx, &ctx->mask, LS));
+    A_(dalloc(ctx, &ctx->colsum_part, (size_t)ctx->nsplit * d.S * d.DP));
+    A_(dalloc(ctx, &ctx->colcnt_part, (size_t)ctx->nsplit * d.S));
+    A_(dalloc(ctx, &ctx->mu, (size_t)d.S * d.DP));
+    A_(dalloc(ctx, &ctx->n, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->gram_part, gram_part_elems(d, ctx->nchunk_gram)));
+    A_(dalloc(ctx, &ctx->P, (size_t)d.S * d.DP * d.DP));
+    A_(dalloc(ctx, &ctx->Pf, (size_t)d.S * frag * d.NT));
+    A_(dalloc(ctx, &ctx->Wf, (size_t)d.S * frag * d.NT2));
+    A_(dalloc(ctx, &ctx->lam, (size_t)d.S * d.DP));
+    A_(dalloc(ctx, &ctx->logdet, (size_t)d.S * d.AP));
+    A_(dalloc(ctx, &ctx->beta, (size_t)d.S * d.AP));
+    A_(dalloc(ctx, &ctx->status, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->sweeps, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->fpart, (size_t)d.S * ctx->nchunk_loo * d.AP));
+    A_(dalloc(ctx, &ctx->nll, (size_t)d.S * d.A));
+    A_(dalloc(ctx, &ctx->mindex, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->w, (size_t)d.S * d.DP));
+    A_(dalloc(ctx, &ctx->wT, (size_t)d.DP * Sp));
+    A_(dalloc(ctx, &ctx->c0, (size_t)Sp));
+    A_(dalloc(ctx, &ctx->mf, LS));
+    A_(dalloc(ctx, &ctx->stat_part, (size_t)ctx->nlanes * d.S * 2));
+    A_(dalloc(ctx, &ctx->colstats, (size_t)3 * d.S));
+    A_(dalloc(ctx, &ctx->alphas_d, (size_t)d.A));
+    A_(dalloc(ctx, &ctx->abscf_d, (size_t)d.DP));
+    if (e != cudaSuccess) {
+        free_buffers(ctx);
+        return fail(ctx, CMF_E_NOMEM, std::string("device allocation failed: ") + cudaGetErrorString(e));
+    }
+    CK(cudaMemsetAsync(ctx->abscf_d, 0, (size_t)d.DP * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->wT, 0, (size_t)d.DP * Sp * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->c0, 0, (size_t)Sp * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->fpart, 0, (size_t)d.S * ctx->nchunk_loo * d.AP * sizeof(double), ctx->stream));
+    CK(cudaMemcpyAsync(ctx->abscf_d, p->abscf, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (loo)
+        CK(cudaMemcpyAsync(ctx->alphas_d, p->alphas, (size_t)d.A * sizeof(double), cudaMemcpyHostToDevice,
+                           ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_problem = true;
+    return CMF_OK;
+}
+
+int cmf_upload_bil(cmf_ctx* ctx, const float* host_cube) {
+    if (!ctx || !host_cube) return CMF_E_ARG;
+    if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_upload_bil before cmf_set_problem");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_own_slab(ctx);
+    if (rc) return rc;
+    const Dims& d = ctx->d;
+    const size_t width = (size_t)d.D * d.S * sizeof(float);
+    const float* src = host_cube + (size_t)(ctx->band_lo - 1) * d.S;
+    CK(cudaMemcpy2DAsync(ctx->slab_own, width, src, (size_t)ctx->B * d.S * sizeof(float), width, (size_t)d.L,
+                         cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_input = true;
+    return CMF_OK;
+}
+
+int cmf_bind_device_slab(cmf_ctx* ctx, const float* dev_slab, int64_t line_pitch, int32_t band_pitch) {
+    if (!ctx || !dev_slab) return CMF_E_ARG;
+    if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_bind_device_slab before cmf_set_problem");
+    Dims& d = ctx->d;
+    if (band_pitch < d.S || line_pitch < (int64_t)band_pitch * (d.D - 1) + d.S)
+        return fail(ctx, CMF_E_ARG, "pitches too small for the active slab");
+    ctx->slab = dev_slab;
+    d.line_pitch = line_pitch;
+    d.band_pitch = band_pitch;
+    d.vec2 = (d.S % 2 == 0) && (line_pitch % 2 == 0) && (band_pitch % 2 == 0) &&
+             ((reinterpret_cast<uintptr_t>(dev_slab) & 7) == 0);
+    ctx->have_input = true;
+    return CMF_OK;
+}
+
+int cmf_run(cmf_ctx* ctx, uint32_t flags) {
+    if (!ctx) return CMF_E_ARG;
+    if (!ctx->have_problem || !ctx->have_input) return fail(ctx, CMF_E_STATE, "cmf_run needs a problem and an input");
+    CK(cudaSetDevice(ctx->device));
+    return enqueue(ctx, (flags & CMF_RUN_TIMING) != 0, nullptr, 0);
+}
+
+int cmf_sync(cmf_ctx* ctx) {
+    if (!ctx) return CMF_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CMF_OK;
+}
+
+int cmf_run_host(cmf_ctx* ctx, const float* host_cube, double* mf_out, double* colstats_out,
+                 int32_t* alpha_index_out, uint32_t flags) {
+    if (!ctx || !host_cube) return CMF_E_ARG;
+    if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_run_host before cmf_set_problem");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_own_slab(ctx);
+    if (rc) return rc;
+    const Dims& d = ctx->d;
+    // upload in blocks of whole repack splits on the copy stream; the repack pass chases the copies
+    const int splits_per_block = std::max(1, (ctx->nsplit + 7) / 8);
+    const int lines_per_block = splits_per_block * ctx->lps;
+    const int nblocks = (d.L + lines_per_block - 1) / lines_per_block;
+    while ((int)ctx->blk_ev.size() < nblocks) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->blk_ev.push_back(e);
+    }
+    const size_t width = (size_t)d.D * d.S * sizeof(float);
+    const size_t spitch = (size_t)ctx->B * d.S * sizeof(float);
+    CK(cudaEventRecord(ctx->ev[K_COUNT], ctx->stream));           // order copies after earlier work
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[K_COUNT], 0));
+    std::vector<cudaEvent_t> ready;
+    for (int b = 0; b < nblocks; ++b) {
+        const int l0 = b * lines_per_block;
+        const int nl = std::min(lines_per_block, d.L - l0);
+        const float* src = host_cube + (size_t)l0 * ctx->B * d.S + (size_t)(ctx->band_lo - 1) * d.S;
+        CK(cudaMemcpy2DAsync(ctx->slab_own + (size_t)l0 * d.D * d.S, width, src, spitch, width, (size_t)nl,
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->blk_ev[b], ctx->copy_stream));
+        ready.push_back(ctx->blk_ev[b]);
+    }
+    ctx->have_input = true;
+    rc = enqueue(ctx, false, &ready, lines_per_block);
+    if (rc) return rc;
+    (void)flags;
+    if (mf_out)
+        CK(cudaMemcpyAsync(mf_out, ctx->mf, (size_t)d.L * d.S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (colstats_out)
+        CK(cudaMemcpyAsync(colstats_out, ctx->colstats, (size_t)3 * d.S * sizeof(double), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    if (alpha_index_out)
+        CK(cudaMemcpyAsync(alpha_index_out, ctx->mindex, (size_t)d.S * sizeof(int), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CMF_OK;
+}
+
+size_t cmf_output_bytes(const cmf_ctx* ctx, int what) {
+    if (!ctx || !ctx->have_problem) return 0;
+    return out_desc(ctx, what).bytes;
+}
+
+void* cmf_device_ptr(cmf_ctx* ctx, int what) {
+    if (!ctx || !ctx->have_problem) return nullptr;
+    return out_desc(ctx, what).ptr;
+}
+
+int cmf_download(cmf_ctx* ctx, int what, void* host_dst, size_t bytes) {
+    if (!ctx || !host_dst) return CMF_E_ARG;
+    if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_download before cmf_set_problem");
+    CK(cudaSetDevice(ctx->device));
+    const OutDesc o = out_desc(ctx, what);
+    if (!o.ptr) return fail(ctx, CMF_E_ARG, "unknown output id");
+    if (bytes < o.bytes) return fail(ctx, CMF_E_ARG, "destination buffer too small");
+    CK(cudaMemcpyAsync(host_dst, o.ptr, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CMF_OK;
+}
+
+int cmf_kernel_count(void) { return K_COUNT; }
+const char* cmf_kernel_name(int i) { return (i >= 0 && i < K_COUNT) ? kKernelNames[i] : ""; }
+
+int cmf_kernel_times(cmf_ctx* ctx, float* ms, int n) {
+    if (!ctx || !ms) return CMF_E_ARG;
+    if (!ctx->timed) return fail(ctx, CMF_E_STATE, "last cmf_run was not started with CMF_RUN_TIMING");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev[K_COUNT]));
+    const int m = std::min(n, (int)K_COUNT);
+    for (int i = 0; i < m; ++i) CK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    return m;
+}
+
+int cmf_launch_count(const cmf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* cmf_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void cmf_host_free(void* p) { if (p) cudaFreeHost(p); }
+int cmf_host_register(void* p, size_t bytes) {
+    return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? CMF_OK : CMF_E_CUDA;
+}
+int cmf_host_unregister(void* p) { return cudaHostUnregister(p) == cudaSuccess ? CMF_OK : CMF_E_CUDA; }
+
+}  // extern "C"

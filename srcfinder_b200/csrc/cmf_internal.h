@@ -1,0 +1,62 @@
+// Internal launch interface between the C-ABI host layer (cmf_api.cu) and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cmf {
+
+constexpr int kMaxNT = 12;          // active bands padded to 8*NT, NT <= 12 (D <= 96) for the shared-memory kernels
+constexpr int kRepackCG = 16;       // columns per repack tile
+constexpr int kRepackLT = 8;        // lines per repack tile
+constexpr int kGramTL = 16;         // lines per Gram tile (4 k-steps of DMMA.8x8x4)
+constexpr int kLooMT = 2;           // 8-pixel m-tiles per LOO pass
+constexpr int kScoreLines = 8;      // lines per thread in the scoring pass
+
+// column status bits (per cross-track column)
+enum : int {
+    kStatusOk = 0,
+    kStatusEmpty = 1,        // no valid pixel: MF stays nodata (cmf/robust_mf.py:303-304)
+    kStatusDegenerate = 2,   // n == 1: the reference produces NaN scores and alpha index 0
+    kStatusSingular = 4,     // C not invertible: MF := 0 (cmf/robust_mf.py:371-374)
+    kStatusNoConverge = 8,   // Jacobi hit the sweep cap (results still written)
+    kStatusAllInf = 16       // every nll was inf: alpha := 0, index -1 (cmf/robust_mf.py:123-127)
+};
+
+struct Dims {
+    int L, S, D, NT, DP;     // lines, samples, active bands, tiles, padded bands
+    int A, NT2, AP;          // alphas, alpha tiles, padded alphas
+    long long line_pitch;    // elements between consecutive lines of the active slab
+    int band_pitch;          // elements between consecutive bands (== samples of the cube)
+    int vec2;                // 8-byte loads allowed (S, pitches even and base aligned)
+};
+
+inline int ntri(int nt) { return nt * (nt + 1) / 2; }
+
+void launch_repack(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,
+                   int* colcnt_part, int lines_per_split, int line_base, int line_limit, cudaStream_t st);
+int repack_lines_per_split(const Dims& d, int nsplit);
+void launch_mean(const Dims& d, const double* colsum_part, const int* colcnt_part, int nsplit,
+                 double* mu, int* n, cudaStream_t st);
+void launch_gram(const Dims& d, const float* xt, const double* mu, int nchunk, double* gram_part,
+                 cudaStream_t st);
+void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, const double* alphas,
+                  int model, double* P, double* Pf, double* Wf, double* lam, double* logdet,
+                  double* beta, int* status, int* sweeps, cudaStream_t st);
+void launch_loo(const Dims& d, const float* xt, const double* mu, const double* Pf, const double* Wf,
+                const double* beta, int nchunk, double* fpart, cudaStream_t st);
+void launch_finalize(const Dims& d, const double* fpart, int nchunk, const double* logdet, const int* n,
+                     const double* alphas, const double* P, const double* lam, const double* mu,
+                     const double* abscf, int model, int reflectance, double scale, double* nll,
+                     int* mindex, double* w, double* wT, double* c0, int* status, cudaStream_t st);
+void launch_score(const Dims& d, const float* slab, const uint8_t* mask, const double* wT, const double* c0,
+                  const int* status, double nodata, double* mf, double* stat_part, int nlanes,
+                  cudaStream_t st);
+void launch_colstats(const Dims& d, const double* stat_part, int nlanes, const int* n, double nodata,
+                     double* colstats, cudaStream_t st);
+
+size_t gram_part_elems(const Dims& d, int nchunk);
+int repack_nsplit(const Dims& d);
+int pick_chunks(int S, int L, int min_lines, int sm_count, int ctas_per_sm);
+
+}  // namespace cmf

@@ -1,0 +1,371 @@
+// K2: per-column spectral factorisation of the shrinkage family, K4: alpha selection + filter weights.
+//
+// The reference evaluates, for each of 201 alphas, det(G), inv(G) and an n x D x D product with
+// G = n*beta*S + alpha*T, T = diag(S)  (cmf/robust_mf.py:105-117).  With R = T^-1/2 S T^-1/2 = V Lam V^T
+// (one symmetric eigendecomposition per column, done here by cyclic Jacobi in shared memory):
+//     G_alpha^-1       = T^-1/2 V (n*beta*Lam + alpha I)^-1 V^T T^-1/2
+//     r_k(alpha)       = sum_j y_kj^2 / (n*beta*lam_j + alpha),          y_k = (T^-1/2 V)^T x_k
+//     log det G_alpha  = sum_j log(1e4 T_jj) + sum_j log(n*beta*lam_j + alpha)   (1e4: the x100 scaling, :94)
+//     C_alpha^-1 t     = T^-1/2 V diag(1 / ((1-alpha) lam_j + alpha)) V^T T^-1/2 t          (:130-136, :363)
+// K2 emits P = T^-1/2 V and the table W[j][i] = 1/(n beta_i lam_j + alpha_i) in DMMA fragment order for
+// the LOO pass (K3); K4 reduces the LOO sums, reproduces the reference's argmin rules and forms the
+// matched-filter weights  w = C^-1 t / (t^T C^-1 t) * scale  (:376-384).
+#include <math.h>
+
+#include "cmf_common.cuh"
+#include "cmf_internal.h"
+
+namespace cmf {
+
+constexpr int kJacobiMaxSweeps = 30;
+
+__device__ __forceinline__ void tri_unrank(int t, int& i, int& j) {
+    // t = i(i+1)/2 + j, j <= i
+    int ii = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    while ((ii + 1) * (ii + 2) / 2 <= t) ++ii;
+    while (ii * (ii + 1) / 2 > t) --ii;
+    i = ii;
+    j = t - ii * (ii + 1) / 2;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(256)
+    eigen_kernel(const double* __restrict__ gram_part, int nchunk, const int* __restrict__ n_g,
+                 const double* __restrict__ alphas, int A, int NT2, int D, int model,
+                 double* __restrict__ P_g, double* __restrict__ Pf_g, double* __restrict__ Wf_g,
+                 double* __restrict__ lam_g, double* __restrict__ logdet_g, double* __restrict__ beta_g,
+                 int* __restrict__ status_g, int* __restrict__ sweeps_g) {
+    constexpr int DP = 8 * NT, LD = DP + 1, NTRI = NT * (NT + 1) / 2;
+    extern __shared__ double sm[];
+    double* Am = sm;                 // [DP][LD]  correlation matrix -> diagonal
+    double* Vm = Am + DP * LD;       // [DP][LD]  eigenvectors (columns)
+    double* dinv = Vm + DP * LD;     // [DP]      T^-1/2
+    double* lam = dinv + DP;         // [DP]
+    double* rc = lam + DP;           // [DP/2+1] rotation cosines
+    double* rs = rc + (DP / 2 + 1);  // [DP/2+1] rotation sines
+    __shared__ int rp[DP / 2 + 1], rq[DP / 2 + 1];
+    __shared__ int rotated;
+    __shared__ double sumlogT;
+
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int n = n_g[s];
+    const int AP = NT2 * 8;
+    double* Pout = P_g + (long long)s * DP * DP;
+    double* Pfout = Pf_g + (long long)s * (DP / 4) * NT * 32;
+    double* Wfout = Wf_g + (long long)s * (DP / 4) * NT2 * 32;
+
+    if (n < 2) {  // empty or single-pixel column: nothing to factorise (handled in K4)
+        for (int i = tid; i < DP * DP; i += blockDim.x) Pout[i] = 0.0;
+        for (int i = tid; i < (DP / 4) * NT * 32; i += blockDim.x) Pfout[i] = 0.0;
+        for (int i = tid; i < (DP / 4) * NT2 * 32; i += blockDim.x) Wfout[i] = 0.0;
+        for (int i = tid; i < DP; i += blockDim.x) lam_g[(long long)s * DP + i] = 0.0;
+        for (int i = tid; i < AP; i += blockDim.x) {
+            logdet_g[(long long)s * AP + i] = 0.0;
+            beta_g[(long long)s * AP + i] = 0.0;
+        }
+        if (tid == 0) { status_g[s] = (n == 0) ? kStatusEmpty : kStatusDegenerate; sweeps_g[s] = 0; }
+        return;
+    }
+
+    // ---- assemble the symmetric Gram from the chunk partials (fixed order) and scale to a covariance
+    const double inv_nm1 = 1.0 / (double)(n - 1);
+    for (int idx = tid; idx < NTRI * 64; idx += blockDim.x) {
+        const int t = idx >> 6, within = idx & 63;
+        const int lane = within >> 1, e = within & 1;
+        int ti, tj;
+        tri_unrank(t, ti, tj);
+        double v = 0.0;
+        for (int c = 0; c < nchunk; ++c) v += gram_part[((long long)s * nchunk + c) * NTRI * 64 + idx];
+        v *= inv_nm1;
+        const int row = 8 * ti + (lane >> 2), col = 8 * tj + 2 * (lane & 3) + e;
+        Am[row * LD + col] = v;
+        if (ti != tj) Am[col * LD + row] = v;
+    }
+    __syncthreads();
+    if (tid < DP) {
+        const double t0 = (tid < D) ? Am[tid * LD + tid] : 0.0;
+        dinv[tid] = (t0 > 0.0) ? 1.0 / sqrt(t0) : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0;
+        for (int b = 0; b < D; ++b) a += log(1.0e4 * Am[b * LD + b]);   // log det of the scaled T (:94-99)
+        sumlogT = a;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < DP * DP; idx += blockDim.x) {
+        const int r = idx / DP, c = idx % DP;
+        double v = Am[r * LD + c] * dinv[r] * dinv[c];
+        if (r == c) v = (r < D && dinv[r] > 0.0) ? 1.0 : 0.0;
+        if (r >= D || c >= D) v = 0.0;
+        Am[r * LD + c] = v;
+        Vm[r * LD + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+
+    // ---- cyclic Jacobi, round-robin ordering: m/2 disjoint rotations per step, m-1 steps per sweep
+    const int m = (D & 1) ? D + 1 : D;
+    const int half = m / 2;
+    int sweep = 0;
+    for (; sweep < kJacobiMaxSweeps; ++sweep) {
+        if (tid == 0) rotated = 0;
+        __syncthreads();
+        for (int r = 0; r < m - 1; ++r) {
+            if (tid < half) {
+                int p, q;
+                if (tid == 0) { p = m - 1; q = r; }
+                else { p = (r + tid) % (m - 1); q = (r - tid + (m - 1)) % (m - 1); }
+                if (p > q) { const int t = p; p = q; q = t; }
+                double c = 1.0, sn = 0.0;
+                int qq = -1;
+                if (q < D) {
+                    const double apq = Am[p * LD + q];
+                    const double app = Am[p * LD + p], aqq = Am[q * LD + q];
+                    if (fabs(apq) > 1.0e-300 && fabs(apq) > 1.1e-16 * sqrt(fabs(app * aqq))) {
+                        const double theta = (aqq - app) / (2.0 * apq);
+                        const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(t * t + 1.0);
+                        sn = t * c;
+                        qq = q;
+                        rotated = 1;
+                    }
+                }
+                rc[tid] = c; rs[tid] = sn; rp[tid] = p; rq[tid] = qq;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < half * D; idx += blockDim.x) {      // rows p, q
+                const int k = idx / D, col = idx - k * D;
+                const int q = rq[k];
+                if (q >= 0) {
+                    const int p = rp[k];
+                    const double c = rc[k], sn = rs[k];
+                    const double ap = Am[p * LD + col], aq = Am[q * LD + col];
+                    Am[p * LD + col] = c * ap - sn * aq;
+                    Am[q * LD + col] = sn * ap + c * aq;
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < half * D; idx += blockDim.x) {      // columns p, q of A and V
+                const int k = idx / D, row = idx - k * D;
+                const int q = rq[k];
+                if (q >= 0) {
+                    const int p = rp[k];
+                    const double c = rc[k], sn = rs[k];
+                    const double ap = Am[row * LD + p], aq = Am[row * LD + q];
+                    Am[row * LD + p] = c * ap - sn * aq;
+                    Am[row * LD + q] = sn * ap + c * aq;
+                    const double vp = Vm[row * LD + p], vq = Vm[row * LD + q];
+                    Vm[row * LD + p] = c * vp - sn * vq;
+                    Vm[row * LD + q] = sn * vp + c * vq;
+                }
+            }
+            __syncthreads();
+        }
+        if (!rotated) break;
+        __syncthreads();
+    }
+    if (tid < DP) {
+        lam[tid] = (tid < D) ? Am[tid * LD + tid] : 0.0;
+        lam_g[(long long)s * DP + tid] = lam[tid];
+    }
+    if (tid == 0) {
+        status_g[s] = (sweep >= kJacobiMaxSweeps) ? kStatusNoConverge : kStatusOk;
+        sweeps_g[s] = sweep;
+    }
+    __syncthreads();
+
+    // ---- P = T^-1/2 V : row-major copy for K4, fragment-ordered copy for the LOO pass
+    for (int idx = tid; idx < DP * DP; idx += blockDim.x) {
+        const int b = idx / DP, j = idx % DP;
+        Pout[idx] = (b < D && j < D) ? dinv[b] * Vm[b * LD + j] : 0.0;
+    }
+    // Pf[ks][nt][lane] = P[b = 4 ks + lane%4][j = 8 nt + lane/4]   (B operand of y = xc . P)
+    for (int idx = tid; idx < (DP / 4) * NT * 32; idx += blockDim.x) {
+        const int lane = idx & 31, nt = (idx >> 5) % NT, ks = (idx >> 5) / NT;
+        const int b = 4 * ks + (lane & 3), j = 8 * nt + (lane >> 2);
+        Pfout[idx] = (b < D && j < D) ? dinv[b] * Vm[b * LD + j] : 0.0;
+    }
+    if (model != 0) return;  // empirical model: no alpha search
+
+    // ---- LOO tables.  beta_i = (1-alpha_i)/(n-1);  den_ji = n beta_i lam_j + alpha_i
+    const double dn = (double)n;
+    for (int i = tid; i < AP; i += blockDim.x) {
+        double ld = 0.0, be = 0.0;
+        if (i < A) {
+            const double al = alphas[i];
+            be = (1.0 - al) / (dn - 1.0);
+            ld = sumlogT;
+            for (int j = 0; j < D; ++j) ld += log(dn * be * lam[j] + al);
+        }
+        logdet_g[(long long)s * AP + i] = ld;
+        beta_g[(long long)s * AP + i] = be;
+    }
+    // Wf[ks2][at][lane] = W[j = 8 (ks2/2) + 2 (lane%4) + ks2%2][i = 8 at + lane/4]
+    // (the j permutation lets the y^2 accumulator registers of GEMM1 feed GEMM2 without any shuffle)
+    for (int idx = tid; idx < (DP / 4) * NT2 * 32; idx += blockDim.x) {
+        const int lane = idx & 31, at = (idx >> 5) % NT2, ks2 = (idx >> 5) / NT2;
+        const int j = 8 * (ks2 >> 1) + 2 * (lane & 3) + (ks2 & 1);
+        const int i = 8 * at + (lane >> 2);
+        double w = 0.0;
+        if (j < D && i < A) {
+            const double al = alphas[i];
+            const double be = (1.0 - al) / (dn - 1.0);
+            w = 1.0 / (dn * be * lam[j] + al);
+        }
+        Wfout[idx] = w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------- K4
+__global__ void __launch_bounds__(256)
+    finalize_kernel(const double* __restrict__ fpart, int nchunk, const double* __restrict__ logdet_g,
+                    const int* __restrict__ n_g, const double* __restrict__ alphas, int A, int AP, int D,
+                    int DP, int S, const double* __restrict__ P_g, const double* __restrict__ lam_g,
+                    const double* __restrict__ mu_g, const double* __restrict__ abscf, int model,
+                    int reflectance, double scale, double* __restrict__ nll_g, int* __restrict__ mindex_g,
+                    double* __restrict__ w_g, double* __restrict__ wT_g, double* __restrict__ c0_g,
+                    int* __restrict__ status_g) {
+    extern __shared__ double sm[];
+    double* nll = sm;           // [AP]
+    double* tvec = nll + AP;    // [DP]
+    double* uvec = tvec + DP;   // [DP]
+    double* vvec = uvec + DP;   // [DP]
+    __shared__ double alpha_sel, norm_sh, c0_sh;
+    __shared__ int singular;
+
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int n = n_g[s];
+    const int Sp = (S + 1) & ~1;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+
+    if (n < 2) {
+        // n == 0: column skipped by the reference (:303-304).  n == 1: cov() is NaN, every nll is NaN,
+        // argmin returns 0 and the scores are NaN (pinned by tests/golden/degenerate_300x4).
+        const double fill = (n == 0) ? 0.0 : qnan;
+        for (int b = tid; b < DP; b += blockDim.x) {
+            w_g[(long long)s * DP + b] = fill;
+            wT_g[(long long)b * Sp + s] = fill;
+        }
+        for (int i = tid; i < A; i += blockDim.x) nll_g[(long long)s * A + i] = (n == 0) ? inf : qnan;
+        if (tid == 0) { mindex_g[s] = (n == 0) ? -2 : 0; c0_g[s] = fill; }
+        return;
+    }
+
+    if (tid == 0) singular = 0;
+    if (model == 0) {
+        const double const_term = (double)D * log(2.0 * M_PI);
+        for (int i = tid; i < A; i += blockDim.x) {
+            double fs = 0.0;
+            for (int c = 0; c < nchunk; ++c) fs += fpart[((long long)s * nchunk + c) * AP + i];
+            const double ld = logdet_g[(long long)s * AP + i];
+            double v;
+            if (ld < -744.4400719213812) v = inf;             // det underflows to 0 -> alpha skipped (:112-113)
+            else if (ld > 709.782712893384) v = inf;          // det overflows -> log(inf)
+            else v = 0.5 * (const_term + ld) + fs / (2.0 * (double)n);
+            nll[i] = v;
+            nll_g[(long long)s * A + i] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // numpy argmin: the first NaN wins, otherwise the first minimum (:121)
+            int best = 0;
+            bool have_nan = false;
+            for (int i = 0; i < A; ++i) {
+                const double v = nll[i];
+                if (v != v) { best = i; have_nan = true; break; }
+                if (v < nll[best]) best = i;
+            }
+            double al;
+            if (have_nan || nll[best] != inf) al = alphas[best];
+            else { best = -1; al = 0.0; status_g[s] |= kStatusAllInf; }
+            mindex_g[s] = best;
+            alpha_sel = al;
+        }
+    } else {
+        if (tid == 0) { mindex_g[s] = -2; alpha_sel = 0.0; }
+    }
+    __syncthreads();
+    const double al = alpha_sel;
+    const double* P = P_g + (long long)s * DP * DP;
+    const double* lam = lam_g + (long long)s * DP;
+    const double* mu = mu_g + (long long)s * DP;
+    for (int b = tid; b < DP; b += blockDim.x)
+        tvec[b] = (b < D) ? (reflectance ? abscf[b] - mu[b] : abscf[b] * mu[b]) : 0.0;
+    __syncthreads();
+    for (int j = tid; j < DP; j += blockDim.x) {
+        double a = 0.0;
+        if (j < D) {
+            for (int b = 0; b < D; ++b) a += P[b * DP + j] * tvec[b];
+            const double den = (1.0 - al) * lam[j] + al;
+            if (!(den > 0.0)) singular = 1;
+            a /= den;
+        }
+        uvec[j] = a;
+    }
+    __syncthreads();
+    for (int b = tid; b < DP; b += blockDim.x) {
+        double a = 0.0;
+        if (b < D)
+            for (int j = 0; j < D; ++j) a += P[b * DP + j] * uvec[j];
+        vvec[b] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double nrm = 0.0;
+        for (int b = 0; b < D; ++b) nrm += tvec[b] * vvec[b];
+        norm_sh = nrm;
+    }
+    __syncthreads();
+    const bool sing = singular != 0;
+    for (int b = tid; b < DP; b += blockDim.x) {
+        const double w = sing ? 0.0 : vvec[b] / norm_sh * scale;
+        vvec[b] = w;
+        w_g[(long long)s * DP + b] = w;
+        wT_g[(long long)b * Sp + s] = w;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double c = 0.0;
+        for (int b = 0; b < D; ++b) c += mu[b] * vvec[b];
+        c0_g[s] = c;
+        if (sing) status_g[s] |= kStatusSingular;
+    }
+}
+
+// ---------------------------------------------------------------------------------------- launchers
+template <int NT>
+static void launch_eigen_t(const Dims& d, const double* gram_part, int nchunk, const int* n,
+                           const double* alphas, int model, double* P, double* Pf, double* Wf, double* lam,
+                           double* logdet, double* beta, int* status, int* sweeps, cudaStream_t st) {
+    constexpr int DP = 8 * NT, LD = DP + 1;
+    const size_t smem = (size_t)(2 * DP * LD + 2 * DP + 2 * (DP / 2 + 1)) * sizeof(double);
+    cudaFuncSetAttribute(eigen_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    eigen_kernel<NT><<<d.S, 256, smem, st>>>(gram_part, nchunk, n, alphas, d.A, d.NT2, d.D, model, P, Pf, Wf,
+                                             lam, logdet, beta, status, sweeps);
+}
+
+void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, const double* alphas,
+                  int model, double* P, double* Pf, double* Wf, double* lam, double* logdet, double* beta,
+                  int* status, int* sweeps, cudaStream_t st) {
+    switch (d.NT) {
+#define CMF_CASE(k) \
+    case k: launch_eigen_t<k>(d, gram_part, nchunk, n, alphas, model, P, Pf, Wf, lam, logdet, beta, status, sweeps, st); break;
+        CMF_CASE(1) CMF_CASE(2) CMF_CASE(3) CMF_CASE(4) CMF_CASE(5) CMF_CASE(6)
+        CMF_CASE(7) CMF_CASE(8) CMF_CASE(9) CMF_CASE(10) CMF_CASE(11) CMF_CASE(12)
+#undef CMF_CASE
+        default: break;
+    }
+}
+
+void launch_finalize(const Dims& d, const double* fpart, int nchunk, const double* logdet, const int* n,
+                     const double* alphas, const double* P, const double* lam, const double* mu,
+                     const double* abscf, int model, int reflectance, double scale, double* nll, int* mindex,
+                     double* w, double* wT, double* c0, int* status, cudaStream_t st) {
+    const size_t smem = (size_t)(d.AP + 3 * d.DP) * sizeof(double);
+    finalize_kernel<<<d.S, 256, smem, st>>>(fpart, nchunk, logdet, n, alphas, d.A, d.AP, d.D, d.DP, d.S, P,
+                                            lam, mu, abscf, model, reflectance, scale, nll, mindex, w, wT, c0,
+                                            status);
+}
+
+}  // namespace cmf

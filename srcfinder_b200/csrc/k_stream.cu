@@ -1,0 +1,375 @@
+// HBM-bound streaming kernels of the columnwise matched filter (sm_100a):
+//   K0  repack_kernel   BIL active slab [L][D][S] -> column-major [S][L][DP] + valid mask + column sums
+//   K0b mean_kernel     per-column mean / valid count from the K0 partials (fixed order)
+//   K5  score_kernel    the scoring pass: one read of the slab, fused mask + mean removal + dot + scale
+//   K6  colstats_kernel per-column npix / mean / std of the written scores
+//
+// Reference steps replaced (cmf/robust_mf.py): :282,:298-304 (valid mask + gather), :347 (mean),
+// :376-386 (matched filter), :388-392 (column statistics).
+#include "cmf_common.cuh"
+#include "cmf_internal.h"
+
+namespace cmf {
+
+// ---------------------------------------------------------------------------------------- K0
+// One CTA = 16 columns x a line range.  Per 8-line tile: coalesced loads of the 16-column runs of every
+// (line, band) row into a padded shared tile, per-pixel validity (all D bands finite and >= 0), FP64
+// column sums over valid pixels kept in registers, then a transposed, fully coalesced write of each
+// column's [8][DP] block.  Invalid pixels are written as NaN in every band so later passes need no mask.
+template <int NT>
+__global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ slab, long long line_pitch,
+                                                     int band_pitch, int L, int S, int D, int vec2,
+                                                     float* __restrict__ xt, uint8_t* __restrict__ mask,
+                                                     double* __restrict__ colsum_part,
+                                                     int* __restrict__ colcnt_part, int lines_per_split,
+                                                     int line_base, int line_limit, int split_base) {
+    constexpr int DP = 8 * NT, CG = kRepackCG, LT = kRepackLT, CGP = CG + 1;
+    constexpr int NACC = (DP * CG + 255) / 256;
+    extern __shared__ float tile[];  // [LT][DP][CGP]
+    __shared__ uint8_t bad[LT * CG];
+
+    const int tid = threadIdx.x;
+    const int s0 = blockIdx.x * CG;
+    const int split = split_base + blockIdx.y;            // global index of this line range
+    const int l_begin = line_base + blockIdx.y * lines_per_split;
+    const int l_end = min(line_limit, l_begin + lines_per_split);
+
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    int cnt = 0;
+
+    for (int l0 = l_begin; l0 < l_end; l0 += LT) {
+        const int nl = min(LT, l_end - l0);
+        __syncthreads();  // previous tile fully consumed
+        if (tid < LT * CG) bad[tid] = 0;
+        if (DP != D) {    // zero the padded bands once per tile
+            const int npad = DP - D;
+            for (int i = tid; i < nl * npad * CG; i += 256) {
+                const int c = i % CG, r = i / CG;
+                const int l = r / npad, b = D + r % npad;
+                tile[(l * DP + b) * CGP + c] = 0.0f;
+            }
+        }
+        __syncthreads();
+        // ---- phase 1: load rows (l, b) of 16 columns
+        const int rows = nl * D;
+        if (vec2) {
+            const int c2 = (tid & 7) * 2;
+            const int col = s0 + c2;
+            if (col < S) {
+#pragma unroll 6
+                for (int r = tid >> 3; r < rows; r += 32) {
+                    const int l = r / D, b = r - l * D;
+                    const float2 v = ldg_nc_f2(slab + (long long)(l0 + l) * line_pitch +
+                                               (long long)b * band_pitch + col);
+                    float* t = tile + (l * DP + b) * CGP + c2;
+                    t[0] = v.x;
+                    t[1] = v.y;
+                    if (!pixel_value_ok(v.x)) bad[l * CG + c2] = 1;
+                    if (!pixel_value_ok(v.y)) bad[l * CG + c2 + 1] = 1;
+                }
+            }
+        } else {
+            const int c1 = tid & 15;
+            const int col = s0 + c1;
+            if (col < S) {
+#pragma unroll 6
+                for (int r = tid >> 4; r < rows; r += 16) {
+                    const int l = r / D, b = r - l * D;
+                    const float v = ldg_nc_f1(slab + (long long)(l0 + l) * line_pitch +
+                                              (long long)b * band_pitch + col);
+                    tile[(l * DP + b) * CGP + c1] = v;
+                    if (!pixel_value_ok(v)) bad[l * CG + c1] = 1;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: FP64 column sums over valid pixels (thread <-> fixed (band, column))
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+            const int idx = tid + k * 256;
+            if (idx < DP * CG) {
+                const int b = idx / CG, c = idx % CG;
+                double a = 0.0;
+                for (int l = 0; l < nl; ++l)
+                    if (!bad[l * CG + c]) a += (double)tile[(l * DP + b) * CGP + c];
+                acc[k] += a;
+            }
+        }
+        if (tid < CG) {
+            int k = 0;
+            for (int l = 0; l < nl; ++l) k += bad[l * CG + tid] ? 0 : 1;
+            cnt += k;
+        }
+        if (tid < LT * CG) {
+            const int l = tid / CG, c = tid % CG;
+            if (l < nl && s0 + c < S) mask[(long long)(l0 + l) * S + s0 + c] = bad[tid] ? 0 : 1;
+        }
+        // ---- phase 3: transposed write, each column's [nl][DP] block is contiguous in xt
+        const int per_col = nl * DP;
+        const float qnan = __int_as_float(0x7fc00000);
+        for (int c = 0; c < CG; ++c) {
+            if (s0 + c >= S) break;
+            float* dst = xt + ((long long)(s0 + c) * L + l0) * DP;
+            for (int i = tid; i < per_col; i += 256) {
+                const int l = i / DP;
+                const float v = tile[i * CGP + c];
+                dst[i] = bad[l * CG + c] ? qnan : v;
+            }
+        }
+    }
+    // ---- partial results of this line range
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+        const int idx = tid + k * 256;
+        if (idx < DP * CG) {
+            const int b = idx / CG, c = idx % CG;
+            if (s0 + c < S) colsum_part[((long long)split * S + s0 + c) * DP + b] = acc[k];
+        }
+    }
+    if (tid < CG && s0 + tid < S) colcnt_part[split * S + s0 + tid] = cnt;
+}
+
+// ---------------------------------------------------------------------------------------- K0b
+__global__ void mean_kernel(const double* __restrict__ colsum_part, const int* __restrict__ colcnt_part,
+                            int nsplit, int S, int DP, double* __restrict__ mu, int* __restrict__ n) {
+    const int s = blockIdx.x;
+    int cnt = 0;
+    for (int k = 0; k < nsplit; ++k) cnt += colcnt_part[k * S + s];
+    for (int b = threadIdx.x; b < DP; b += blockDim.x) {
+        double a = 0.0;
+        for (int k = 0; k < nsplit; ++k) a += colsum_part[((long long)k * S + s) * DP + b];
+        mu[(long long)s * DP + b] = cnt > 0 ? a / (double)cnt : 0.0;   // numpy mean: sum / n
+    }
+    if (threadIdx.x == 0) n[s] = cnt;
+}
+
+// ---------------------------------------------------------------------------------------- K5
+// Scoring pass.  thread <-> (column pair, group of 8 lines); per band one 16-byte weight load shared by
+// the 8 lines and eight 8-byte radiance loads; FP64 FMA on converted FP32 radiances so that the score is
+// exact to FP64 rounding given the weights.  mf = sum_b x_b w_b - mu.w ; invalid pixels keep nodata.
+template <int VEC>
+__global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ slab, long long line_pitch,
+                                                    int band_pitch, int L, int S, int D,
+                                                    const uint8_t* __restrict__ mask,
+                                                    const double* __restrict__ wT, int Sp,
+                                                    const double* __restrict__ c0,
+                                                    const int* __restrict__ status, double nodata,
+                                                    double* __restrict__ mf, double* __restrict__ stat_part,
+                                                    int nlanes) {
+    constexpr int NL = kScoreLines;
+    const int SC = (S + VEC - 1) / VEC;               // column groups per line
+    const int ngroups = (L + NL - 1) / NL;            // line groups
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)SC * nlanes) return;
+    const int sc = (int)(gid % SC);
+    const int lane_id = (int)(gid / SC);
+    const int col = sc * VEC;
+    const bool has1 = (VEC == 2) && (col + 1 < S);
+
+    double sum0 = 0.0, sum1 = 0.0, sq0 = 0.0, sq1 = 0.0;
+    const double cz0 = c0[col], cz1 = has1 ? c0[col + 1] : 0.0;
+    const bool zero0 = (status[col] & (kStatusSingular)) != 0;
+    const bool zero1 = has1 ? ((status[col + 1] & (kStatusSingular)) != 0) : false;
+
+    for (int grp = lane_id; grp < ngroups; grp += nlanes) {
+        const int l0 = grp * NL;
+        double a0[NL], a1[NL];
+#pragma unroll
+        for (int j = 0; j < NL; ++j) { a0[j] = 0.0; a1[j] = 0.0; }
+        const float* base = slab + (long long)l0 * line_pitch + col;
+        if (l0 + NL <= L) {
+#pragma unroll 2
+            for (int b = 0; b < D; ++b) {
+                double w0, w1;
+                if (VEC == 2) {
+                    const double2 w = *reinterpret_cast<const double2*>(wT + (long long)b * Sp + col);
+                    w0 = w.x; w1 = w.y;
+                } else {
+                    w0 = wT[(long long)b * Sp + col]; w1 = 0.0;
+                }
+                const float* pb = base + (long long)b * band_pitch;
+#pragma unroll
+                for (int j = 0; j < NL; ++j) {
+                    if (VEC == 2) {
+                        const float2 v = ldg_nc_f2(pb + (long long)j * line_pitch);
+                        a0[j] = fma((double)v.x, w0, a0[j]);
+                        a1[j] = fma((double)v.y, w1, a1[j]);
+                    } else {
+                        const float v = ldg_nc_f1(pb + (long long)j * line_pitch);
+                        a0[j] = fma((double)v, w0, a0[j]);
+                    }
+                }
+            }
+        } else {
+            for (int b = 0; b < D; ++b) {
+                const double w0 = wT[(long long)b * Sp + col];
+                const double w1 = has1 ? wT[(long long)b * Sp + col + 1] : 0.0;
+                const float* pb = base + (long long)b * band_pitch;
+#pragma unroll
+                for (int j = 0; j < NL; ++j) {
+                    if (l0 + j < L) {
+                        const float v = ldg_nc_f1(pb + (long long)j * line_pitch);
+                        a0[j] = fma((double)v, w0, a0[j]);
+                        if (has1) {
+                            const float u = ldg_nc_f1(pb + (long long)j * line_pitch + 1);
+                            a1[j] = fma((double)u, w1, a1[j]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+            const int l = l0 + j;
+            if (l < L) {
+                const long long o = (long long)l * S + col;
+                const bool ok0 = mask[o] != 0;
+                const double v0 = ok0 ? (zero0 ? 0.0 : a0[j] - cz0) : nodata;
+                if (ok0) { sum0 += v0; sq0 += v0 * v0; }
+                if (has1) {
+                    const bool ok1 = mask[o + 1] != 0;
+                    const double v1 = ok1 ? (zero1 ? 0.0 : a1[j] - cz1) : nodata;
+                    if (ok1) { sum1 += v1; sq1 += v1 * v1; }
+                    if ((((uintptr_t)(mf + o)) & 15) == 0) {
+                        *reinterpret_cast<double2*>(mf + o) = make_double2(v0, v1);
+                    } else {
+                        mf[o] = v0; mf[o + 1] = v1;
+                    }
+                } else {
+                    mf[o] = v0;
+                }
+            }
+        }
+    }
+    double* sp = stat_part + ((long long)lane_id * S + col) * 2;
+    sp[0] = sum0; sp[1] = sq0;
+    if (has1) { sp[2] = sum1; sp[3] = sq1; }
+}
+
+// ---------------------------------------------------------------------------------------- K6
+// colnum / colavg / colstd (np.mean, np.std ddof=0 of the written scores; cmf/robust_mf.py:388-391)
+__global__ void colstats_kernel(const double* __restrict__ stat_part, int nlanes, int S,
+                                const int* __restrict__ n, double nodata, double* __restrict__ colstats) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int cnt = n[s];
+    if (cnt == 0) {
+        colstats[s] = nodata; colstats[S + s] = nodata; colstats[2 * S + s] = nodata;
+        return;
+    }
+    double sum = 0.0, sq = 0.0;
+    for (int k = 0; k < nlanes; ++k) {
+        sum += stat_part[((long long)k * S + s) * 2];
+        sq += stat_part[((long long)k * S + s) * 2 + 1];
+    }
+    const double mean = sum / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    colstats[s] = (double)cnt;
+    colstats[S + s] = mean;
+    colstats[2 * S + s] = sqrt(var);
+}
+
+// ---------------------------------------------------------------------------------------- launchers
+int repack_nsplit(const Dims& d) {
+    const int groups = (d.S + kRepackCG - 1) / kRepackCG;
+    int want = (148 * 5 + groups - 1) / groups;                 // ~5 CTAs per SM
+    int maxsplit = (d.L + 4 * kRepackLT - 1) / (4 * kRepackLT); // at least 4 tiles per CTA
+    int ns = want < maxsplit ? want : maxsplit;
+    return ns < 1 ? 1 : ns;
+}
+
+template <int NT>
+static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,
+                            int* colcnt_part, int lps, int line_base, int line_limit, int split_base,
+                            cudaStream_t st) {
+    constexpr int DP = 8 * NT;
+    const size_t smem = (size_t)kRepackLT * DP * (kRepackCG + 1) * sizeof(float);
+    cudaFuncSetAttribute(repack_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int nblk = (line_limit - line_base + lps - 1) / lps;
+    if (nblk <= 0) return;
+    dim3 grid((d.S + kRepackCG - 1) / kRepackCG, nblk);
+    repack_kernel<NT><<<grid, 256, smem, st>>>(slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, d.vec2, xt,
+                                               mask, colsum_part, colcnt_part, lps, line_base, line_limit,
+                                               split_base);
+}
+
+#define CMF_NT_SWITCH(nt, CALL)                                                      \
+    switch (nt) {                                                                    \
+        case 1: { constexpr int NTc = 1; CALL; } break;                              \
+        case 2: { constexpr int NTc = 2; CALL; } break;                              \
+        case 3: { constexpr int NTc = 3; CALL; } break;                              \
+        case 4: { constexpr int NTc = 4; CALL; } break;                              \
+        case 5: { constexpr int NTc = 5; CALL; } break;                              \
+        case 6: { constexpr int NTc = 6; CALL; } break;                              \
+        case 7: { constexpr int NTc = 7; CALL; } break;                              \
+        case 8: { constexpr int NTc = 8; CALL; } break;                              \
+        case 9: { constexpr int NTc = 9; CALL; } break;                              \
+        case 10: { constexpr int NTc = 10; CALL; } break;                            \
+        case 11: { constexpr int NTc = 11; CALL; } break;                            \
+        case 12: { constexpr int NTc = 12; CALL; } break;                            \
+        default: break;                                                              \
+    }
+
+int repack_lines_per_split(const Dims& d, int nsplit) {
+    int lps = (d.L + nsplit - 1) / nsplit;
+    return (lps + kRepackLT - 1) / kRepackLT * kRepackLT;
+}
+
+// Repack lines [line_base, line_limit); line_base must be a multiple of lines-per-split so that the
+// partial-sum slots (split_base + i) are the same whether the cube is processed whole or in blocks.
+void launch_repack(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,
+                   int* colcnt_part, int lps, int line_base, int line_limit, cudaStream_t st) {
+    const int split_base = line_base / lps;
+    CMF_NT_SWITCH(d.NT, (launch_repack_t<NTc>(d, slab, xt, mask, colsum_part, colcnt_part, lps, line_base,
+                                              line_limit, split_base, st)));
+}
+
+void launch_mean(const Dims& d, const double* colsum_part, const int* colcnt_part, int nsplit, double* mu,
+                 int* n, cudaStream_t st) {
+    mean_kernel<<<d.S, 128, 0, st>>>(colsum_part, colcnt_part, nsplit, d.S, d.DP, mu, n);
+}
+
+void launch_score(const Dims& d, const float* slab, const uint8_t* mask, const double* wT, const double* c0,
+                  const int* status, double nodata, double* mf, double* stat_part, int nlanes,
+                  cudaStream_t st) {
+    const int Sp = (d.S + 1) & ~1;
+    if (d.vec2) {
+        const long long total = (long long)((d.S + 1) / 2) * nlanes;
+        score_kernel<2><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, mask, wT, Sp, c0, status, nodata, mf, stat_part,
+            nlanes);
+    } else {
+        const long long total = (long long)d.S * nlanes;
+        score_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, mask, wT, Sp, c0, status, nodata, mf, stat_part,
+            nlanes);
+    }
+}
+
+void launch_colstats(const Dims& d, const double* stat_part, int nlanes, const int* n, double nodata,
+                     double* colstats, cudaStream_t st) {
+    colstats_kernel<<<(d.S + 127) / 128, 128, 0, st>>>(stat_part, nlanes, d.S, n, nodata, colstats);
+}
+
+// Number of line chunks per column so that S*nchunk CTAs fill whole waves of (sm_count*ctas_per_sm).
+int pick_chunks(int S, int L, int min_lines, int sm_count, int ctas_per_sm) {
+    const int slots = sm_count * ctas_per_sm;
+    int maxc = L / min_lines;
+    if (maxc < 1) maxc = 1;
+    if (maxc > 64) maxc = 64;
+    int best = 1;
+    double best_eff = 0.0;
+    for (int c = 1; c <= maxc; ++c) {
+        const long long ctas = (long long)S * c;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double eff = (double)ctas / (double)(waves * slots);
+        if (eff > best_eff + 0.01) { best_eff = eff; best = c; }   // prefer fewer chunks unless >1 % better
+        if (best_eff > 0.985) break;
+    }
+    return best;
+}
+
+}  // namespace cmf

@@ -1,0 +1,183 @@
+// Micro-benchmarks behind cmf_microbench(): the measured denominators used in DESIGN.md / profiles/
+// for the FP64 tensor path (MEASURED_PEAKS.json only carries HBM copy and bf16 GEMM figures).
+#include <stdio.h>
+
+#include "../../include/cmf_b200.h"
+#include "cmf_common.cuh"
+
+namespace {
+
+using namespace cmf;
+
+template <int NACC>
+__global__ void __launch_bounds__(256) dmma_kernel(double* out, int iters) {
+    double c[NACC][2];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    double a = 1.0 + threadIdx.x * 1e-3, b = 1.0 - threadIdx.x * 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) mma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters) {
+    double c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = i;
+    const double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) cvt_kernel(double* out, const float* in, int iters) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = in[threadIdx.x + i];
+    double s = 0.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s += (double)x[i];
+            x[i] = __int_as_float(__float_as_int(x[i]) + 1);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) logdiv_kernel(double* out, int iters) {
+    double r = 50.0 + threadIdx.x * 0.01, s = 0.0;
+    const double beta = 5e-5;
+    for (int it = 0; it < iters; ++it) {
+        const double q = 1.0 - beta * r;
+        s += log(q) + r / q;
+        r += 1e-3;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256) read_kernel(const V* __restrict__ in, size_t n, float* out) {
+    float acc = 0.f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        V v0 = in[i], v1 = in[i + stride], v2 = in[i + 2 * stride], v3 = in[i + 3 * stride];
+        const float* f0 = reinterpret_cast<const float*>(&v0);
+        const float* f1 = reinterpret_cast<const float*>(&v1);
+        const float* f2 = reinterpret_cast<const float*>(&v2);
+        const float* f3 = reinterpret_cast<const float*>(&v3);
+        acc += f0[0] + f1[0] + f2[0] + f3[0];
+    }
+    for (; i < n; i += stride) { V v = in[i]; acc += reinterpret_cast<const float*>(&v)[0]; }
+    if (acc == 123.456f) out[0] = acc;
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(const float4* __restrict__ in, float4* __restrict__ outp, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) outp[i] = in[i];
+}
+
+// every warp streams 8 KB tiles through a 3-stage ring with 1-D bulk async copies
+__global__ void __launch_bounds__(256) bulk_read_kernel(const float* __restrict__ in, size_t ntiles, float* out) {
+    constexpr int TB = 2048, NS = 3;   // floats per tile (8 KB)
+    extern __shared__ __align__(128) unsigned char sraw[];
+    float* ring = reinterpret_cast<float*>(sraw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 8 * NS * TB);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { for (int s = 0; s < NS; ++s) mbar_init(&bars[warp * NS + s], 1); fence_mbar_init(); }
+    __syncthreads();
+    const size_t gw = (size_t)blockIdx.x * 8 + warp, nw = (size_t)gridDim.x * 8;
+    float* my = ring + warp * NS * TB;
+    auto issue = [&](size_t it) {
+        const size_t t = gw + nw * it;
+        if (t < ntiles) {
+            mbar_expect_tx(&bars[warp * NS + it % NS], TB * 4);
+            bulk_g2s(my + (it % NS) * TB, in + t * TB, TB * 4, &bars[warp * NS + it % NS]);
+        }
+    };
+    if (lane == 0) for (int it = 0; it < NS; ++it) issue(it);
+    float acc = 0.f;
+    for (size_t it = 0; gw + nw * it < ntiles; ++it) {
+        mbar_wait(&bars[warp * NS + it % NS], (uint32_t)((it / NS) & 1));
+        acc += my[(it % NS) * TB + lane * 4];
+        __syncwarp();
+        if (lane == 0) issue(it + NS);
+    }
+    if (acc == 123.456f) out[0] = acc;
+}
+
+float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+}  // namespace
+
+extern "C" double cmf_microbench(int device, int kind, int iters) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int sms = prop.multiProcessorCount;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double result = -1.0;
+    if (iters <= 0) iters = 1;
+    if (kind == 0 || kind == 1 || kind == 6 || kind == 7 || kind == 8) {
+        const int blocks = sms * ((kind == 8) ? 1 : 4);
+        double* out; cudaMalloc(&out, (size_t)blocks * 256 * sizeof(double));
+        float* fin; cudaMalloc(&fin, 4096); cudaMemset(fin, 0, 4096);
+        const int inner = 4096;
+        auto run = [&]() {
+            if (kind == 0) dmma_kernel<8><<<blocks, 256>>>(out, inner);
+            else if (kind == 8) dmma_kernel<24><<<blocks, 256>>>(out, inner);
+            else if (kind == 1) dfma_kernel<<<blocks, 256>>>(out, inner);
+            else if (kind == 6) cvt_kernel<<<blocks, 256>>>(out, fin, inner);
+            else logdiv_kernel<<<blocks, 256>>>(out, inner);
+        };
+        run(); cudaDeviceSynchronize();
+        cudaEventRecord(e0);
+        for (int i = 0; i < iters; ++i) run();
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        const double sec = time_ms(e0, e1) * 1e-3 / iters;
+        const double threads = (double)blocks * 256;
+        if (kind == 0) result = threads / 32 * inner * 8 * 512.0 / sec * 1e-12;         // TFLOP/s
+        else if (kind == 8) result = threads / 32 * inner * 24 * 512.0 / sec * 1e-12;   // TFLOP/s, 8 warps/SM
+        else if (kind == 1) result = threads * inner * 8 * 2.0 / sec * 1e-12;           // TFLOP/s
+        else if (kind == 6) result = threads * inner * 8 / sec * 1e-9;                   // Gcvt/s
+        else result = threads * inner / sec * 1e-9;                                      // G (log+div)/s
+        cudaFree(out); cudaFree(fin);
+    } else if (kind >= 2 && kind <= 5) {
+        const size_t bytes = (size_t)4 << 30;   // 4 GiB, far larger than the 126 MB L2
+        float* in; float* outp = nullptr; float* flag;
+        if (cudaMalloc(&in, bytes) != cudaSuccess) return -1.0;
+        cudaMalloc(&flag, 256);
+        cudaMemset(in, 0, bytes);
+        if (kind == 4) { if (cudaMalloc(&outp, bytes) != cudaSuccess) { cudaFree(in); return -1.0; } }
+        const int blocks = sms * 8;
+        if (kind == 5) cudaFuncSetAttribute(bulk_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 8192 + 256);
+        auto run = [&]() {
+            if (kind == 2) read_kernel<float2><<<blocks, 256>>>(reinterpret_cast<const float2*>(in), bytes / 8, flag);
+            else if (kind == 3) read_kernel<float4><<<blocks, 256>>>(reinterpret_cast<const float4*>(in), bytes / 16, flag);
+            else if (kind == 4) copy_kernel<<<blocks, 256>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(outp), bytes / 16);
+            else bulk_read_kernel<<<sms, 256, 8 * 3 * 8192 + 256>>>(in, bytes / 8192, flag);
+        };
+        run(); cudaDeviceSynchronize();
+        cudaEventRecord(e0);
+        for (int i = 0; i < iters; ++i) run();
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        const double sec = time_ms(e0, e1) * 1e-3 / iters;
+        result = (kind == 4 ? 2.0 : 1.0) * (double)bytes / sec * 1e-9;   // GB/s
+        cudaFree(in); cudaFree(flag); if (outp) cudaFree(outp);
+    }
+    if (cudaGetLastError() != cudaSuccess) result = -1.0;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return result;
+}

@@ -1,0 +1,42 @@
+"""Development probe run on the GPU box: micro-benchmarks + per-kernel timings at flightline size.
+Writes gpurun_out/probe.json."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from srcfinder_b200 import ColumnwiseMF, _lib, synth
+
+out = {}
+lib = _lib.load()
+names = {0: "dmma_tflops_32w", 8: "dmma_tflops_8w_ilp24", 1: "dfma_tflops", 6: "cvt_f32_f64_gops",
+         7: "logdiv_gops", 2: "hbm_read_8B_gbs", 3: "hbm_read_16B_gbs", 4: "hbm_copy_gbs", 5: "hbm_bulk_read_gbs"}
+for kind, name in names.items():
+    out[name] = lib.cmf_microbench(0, kind, 5)
+    print(name, out[name], flush=True)
+
+L = int(os.environ.get("PROBE_L", "20000"))
+S, active = 598, [351, 422]
+ab = synth.load_ch4_library()[active[0] - 1:active[1], 2]
+t0 = time.time()
+slab = synth.make_slab_torch(L, S, active[0], active[1], "cuda", seed=2)
+torch.cuda.synchronize()
+print("slab generated in %.1f s" % (time.time() - t0), flush=True)
+with ColumnwiseMF(L, 425, S, active, ab) as eng:
+    eng.bind_device(slab.data_ptr())
+    for i in range(3):
+        eng.run(timing=True)
+        kt = eng.kernel_times()
+        print(i, {k: round(v, 3) for k, v in kt.items()}, "total %.3f ms" % sum(kt.values()), flush=True)
+    out["kernel_ms"] = kt
+    out["total_ms"] = sum(kt.values())
+    out["mpixel_s"] = L * S / (sum(kt.values()) * 1e-3) / 1e6
+    out["sweeps_max"] = int(eng.sweeps().max())
+    out["alpha_index_range"] = [int(eng.alpha_index().min()), int(eng.alpha_index().max())]
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/probe.json", "w"), indent=1)
+print(json.dumps(out))
