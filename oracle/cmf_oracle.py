@@ -16,10 +16,23 @@ build container (``oracle/make_golden.py`` -> ``tests/golden/*.npz``);
 """
 from __future__ import annotations
 
+import contextlib
+
 import numpy as np
 from numpy.linalg import LinAlgError  # scipy.linalg.LinAlgError is this class
 from scipy.linalg import det as _lapack_det
 from scipy.linalg import inv as _lapack_inv
+
+try:                                   # tiny-matrix LAPACK calls thrash with many BLAS threads
+    from threadpoolctl import threadpool_limits as _blas_limits   # (~40x slower)
+except Exception:                      # pragma: no cover
+    _blas_limits = None
+
+
+def single_thread_blas():
+    """Context manager pinning BLAS/LAPACK to one thread (also makes the last bits reproducible)."""
+    return _blas_limits(limits=1) if _blas_limits is not None else contextlib.nullcontext()
+
 
 PPM_SCALING = 100000.0        # cmf/robust_mf.py:38
 STABILITY_SCALING = 100.0     # cmf/robust_mf.py:94
@@ -124,6 +137,13 @@ def column_filter(x_nd, abscf, alphas, nll, n_for_loo, model="looshrinkage", ref
 def cmf_cube(cube_lbs, abscf, active, alphas=None, model="looshrinkage", reflectance=False,
              nodata=-9999.0, labels=None, reject_min=None, regfull=False, columns=None,
              keep_nll=False):
+    with single_thread_blas():
+        return _cmf_cube(cube_lbs, abscf, active, alphas, model, reflectance, nodata, labels, reject_min,
+                         regfull, columns, keep_nll)
+
+
+def _cmf_cube(cube_lbs, abscf, active, alphas, model, reflectance, nodata, labels, reject_min, regfull,
+              columns, keep_nll):
     """Column loop of the reference (cmf/robust_mf.py:297-397) on an in-memory BIL cube.
 
     ``cube_lbs``  (L, B, S) float32;  ``active`` 1-based inclusive [lo, hi];

@@ -82,13 +82,13 @@ __device__ __forceinline__ bool pixel_value_ok(float x) {
 
 __device__ __forceinline__ float2 ldg_nc_f2(const float* p) {
     float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
 }
 
 __device__ __forceinline__ float ldg_nc_f1(const float* p) {
     float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 

@@ -29,7 +29,7 @@ __device__ __forceinline__ void tri_unrank(int t, int& i, int& j) {
 }
 
 template <int NT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
     eigen_kernel(const double* __restrict__ gram_part, int nchunk, const int* __restrict__ n_g,
                  const double* __restrict__ alphas, int A, int NT2, int D, int model,
                  double* __restrict__ P_g, double* __restrict__ Pf_g, double* __restrict__ Wf_g,
@@ -103,7 +103,10 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
 
-    // ---- cyclic Jacobi, round-robin ordering: m/2 disjoint rotations per step, m-1 steps per sweep
+    // ---- cyclic Jacobi, round-robin ordering: m/2 disjoint rotations per step, m-1 steps per sweep.
+    // Each step is two barriers: (1) one thread per pair picks its rotation, (2) A <- J^T A J is applied
+    // as independent 2x2 blocks (pair k rows x pair l columns, updated in place by one thread) together
+    // with V <- V J.  For odd D the bye slot is the zero padding row/column D (identity rotation).
     const int m = (D & 1) ? D + 1 : D;
     const int half = m / 2;
     int sweep = 0;
@@ -117,7 +120,6 @@ __global__ void __launch_bounds__(256)
                 else { p = (r + tid) % (m - 1); q = (r - tid + (m - 1)) % (m - 1); }
                 if (p > q) { const int t = p; p = q; q = t; }
                 double c = 1.0, sn = 0.0;
-                int qq = -1;
                 if (q < D) {
                     const double apq = Am[p * LD + q];
                     const double app = Am[p * LD + p], aqq = Am[q * LD + q];
@@ -126,37 +128,38 @@ __global__ void __launch_bounds__(256)
                         const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
                         c = 1.0 / sqrt(t * t + 1.0);
                         sn = t * c;
-                        qq = q;
                         rotated = 1;
                     }
                 }
-                rc[tid] = c; rs[tid] = sn; rp[tid] = p; rq[tid] = qq;
+                rc[tid] = c; rs[tid] = sn; rp[tid] = p; rq[tid] = q;
             }
             __syncthreads();
-            for (int idx = tid; idx < half * D; idx += blockDim.x) {      // rows p, q
-                const int k = idx / D, col = idx - k * D;
-                const int q = rq[k];
-                if (q >= 0) {
-                    const int p = rp[k];
-                    const double c = rc[k], sn = rs[k];
-                    const double ap = Am[p * LD + col], aq = Am[q * LD + col];
-                    Am[p * LD + col] = c * ap - sn * aq;
-                    Am[q * LD + col] = sn * ap + c * aq;
-                }
-            }
-            __syncthreads();
-            for (int idx = tid; idx < half * D; idx += blockDim.x) {      // columns p, q of A and V
-                const int k = idx / D, row = idx - k * D;
-                const int q = rq[k];
-                if (q >= 0) {
-                    const int p = rp[k];
-                    const double c = rc[k], sn = rs[k];
-                    const double ap = Am[row * LD + p], aq = Am[row * LD + q];
-                    Am[row * LD + p] = c * ap - sn * aq;
-                    Am[row * LD + q] = sn * ap + c * aq;
-                    const double vp = Vm[row * LD + p], vq = Vm[row * LD + q];
-                    Vm[row * LD + p] = c * vp - sn * vq;
-                    Vm[row * LD + q] = sn * vp + c * vq;
+            const int nblk = half * half;
+            for (int idx = tid; idx < nblk + half * D; idx += blockDim.x) {
+                if (idx < nblk) {
+                    const int k = idx / half, l = idx - k * half;
+                    const double ck = rc[k], sk = rs[k], cl = rc[l], sl = rs[l];
+                    if (sk != 0.0 || sl != 0.0) {
+                        const int pk = rp[k], qk = rq[k], pl = rp[l], ql = rq[l];
+                        const double b00 = Am[pk * LD + pl], b01 = Am[pk * LD + ql];
+                        const double b10 = Am[qk * LD + pl], b11 = Am[qk * LD + ql];
+                        const double t00 = ck * b00 - sk * b10, t01 = ck * b01 - sk * b11;
+                        const double t10 = sk * b00 + ck * b10, t11 = sk * b01 + ck * b11;
+                        Am[pk * LD + pl] = cl * t00 - sl * t01;
+                        Am[pk * LD + ql] = sl * t00 + cl * t01;
+                        Am[qk * LD + pl] = cl * t10 - sl * t11;
+                        Am[qk * LD + ql] = sl * t10 + cl * t11;
+                    }
+                } else {
+                    const int j = idx - nblk;
+                    const int l = j / D, row = j - l * D;
+                    const double cl = rc[l], sl = rs[l];
+                    if (sl != 0.0) {
+                        const int pl = rp[l], ql = rq[l];
+                        const double vp = Vm[row * LD + pl], vq = Vm[row * LD + ql];
+                        Vm[row * LD + pl] = cl * vp - sl * vq;
+                        Vm[row * LD + ql] = sl * vp + cl * vq;
+                    }
                 }
             }
             __syncthreads();
@@ -341,7 +344,7 @@ static void launch_eigen_t(const Dims& d, const double* gram_part, int nchunk, c
     constexpr int DP = 8 * NT, LD = DP + 1;
     const size_t smem = (size_t)(2 * DP * LD + 2 * DP + 2 * (DP / 2 + 1)) * sizeof(double);
     cudaFuncSetAttribute(eigen_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    eigen_kernel<NT><<<d.S, 256, smem, st>>>(gram_part, nchunk, n, alphas, d.A, d.NT2, d.D, model, P, Pf, Wf,
+    eigen_kernel<NT><<<d.S, 512, smem, st>>>(gram_part, nchunk, n, alphas, d.A, d.NT2, d.D, model, P, Pf, Wf,
                                              lam, logdet, beta, status, sweeps);
 }
 

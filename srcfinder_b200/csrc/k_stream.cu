@@ -52,35 +52,72 @@ __global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ s
             }
         }
         __syncthreads();
-        // ---- phase 1: load rows (l, b) of 16 columns
+        // ---- phase 1: load rows (l, b) of 16 columns; loads are issued in batches of U before any use
         const int rows = nl * D;
         if (vec2) {
             const int c2 = (tid & 7) * 2;
             const int col = s0 + c2;
+            constexpr int U = 9;
             if (col < S) {
-#pragma unroll 6
-                for (int r = tid >> 3; r < rows; r += 32) {
-                    const int l = r / D, b = r - l * D;
-                    const float2 v = ldg_nc_f2(slab + (long long)(l0 + l) * line_pitch +
-                                               (long long)b * band_pitch + col);
-                    float* t = tile + (l * DP + b) * CGP + c2;
-                    t[0] = v.x;
-                    t[1] = v.y;
-                    if (!pixel_value_ok(v.x)) bad[l * CG + c2] = 1;
-                    if (!pixel_value_ok(v.y)) bad[l * CG + c2 + 1] = 1;
+                int r = tid >> 3;
+                int l = r / D, b = r - l * D;
+                const float* p = slab + (long long)(l0 + l) * line_pitch + (long long)b * band_pitch + col;
+                while (r < rows) {
+                    float2 v[U];
+                    int off[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        off[u] = -1;
+                        if (r < rows) {
+                            v[u] = ldg_nc_f2(p);
+                            off[u] = (l * DP + b) * CGP + c2 + ((l * CG + c2) << 16);
+                        }
+                        r += 32; b += 32;
+                        p += 32LL * band_pitch;
+                        while (b >= D) { b -= D; ++l; p += line_pitch - (long long)D * band_pitch; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (off[u] >= 0) {
+                            float* t = tile + (off[u] & 0xffff);
+                            t[0] = v[u].x;
+                            t[1] = v[u].y;
+                            const int bo = off[u] >> 16;
+                            if (!pixel_value_ok(v[u].x)) bad[bo] = 1;
+                            if (!pixel_value_ok(v[u].y)) bad[bo + 1] = 1;
+                        }
+                    }
                 }
             }
         } else {
             const int c1 = tid & 15;
             const int col = s0 + c1;
+            constexpr int U = 9;
             if (col < S) {
-#pragma unroll 6
-                for (int r = tid >> 4; r < rows; r += 16) {
-                    const int l = r / D, b = r - l * D;
-                    const float v = ldg_nc_f1(slab + (long long)(l0 + l) * line_pitch +
-                                              (long long)b * band_pitch + col);
-                    tile[(l * DP + b) * CGP + c1] = v;
-                    if (!pixel_value_ok(v)) bad[l * CG + c1] = 1;
+                int r = tid >> 4;
+                int l = r / D, b = r - l * D;
+                const float* p = slab + (long long)(l0 + l) * line_pitch + (long long)b * band_pitch + col;
+                while (r < rows) {
+                    float v[U];
+                    int off[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        off[u] = -1;
+                        if (r < rows) {
+                            v[u] = ldg_nc_f1(p);
+                            off[u] = (l * DP + b) * CGP + c1 + ((l * CG + c1) << 16);
+                        }
+                        r += 16; b += 16;
+                        p += 16LL * band_pitch;
+                        while (b >= D) { b -= D; ++l; p += line_pitch - (long long)D * band_pitch; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (off[u] >= 0) {
+                            tile[off[u] & 0xffff] = v[u];
+                            if (!pixel_value_ok(v[u])) bad[off[u] >> 16] = 1;
+                        }
+                    }
                 }
             }
         }

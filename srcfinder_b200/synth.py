@@ -102,7 +102,7 @@ def make_cube(lines, samples, bands=425, seed=1, lib=None, plume=True, bad_pixel
         cube *= np.exp(absorb[None, :, None] * (ppmm[:, None, :] / 1.0e5))
     cube += noise * rng.standard_normal(cube.shape)
     np.maximum(cube, 1.0e-4, out=cube)
-    cube = cube.astype(np.float32)
+    cube = np.ascontiguousarray(cube, dtype=np.float32)      # einsum hands back a strided view
     if bad_pixels:
         npx = lines * samples
         act0, act1 = 350, 422                                        # 0-based CH4 window

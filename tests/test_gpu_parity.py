@@ -118,7 +118,7 @@ def test_device_resident_full_cube_and_run_host():
         eng.upload(cube)
         eng.run()
         base = eng.results()
-        dev = torch.from_numpy(cube).cuda()
+        dev = torch.from_numpy(np.ascontiguousarray(cube)).cuda()
         ptr = dev.data_ptr() + (active[0] - 1) * S * 4
         torch.cuda.synchronize()
         eng.bind_device(ptr, line_pitch=B * S, band_pitch=S)
