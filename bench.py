@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""Benchmark of the columnwise matched filter (BASELINE.json metric: CMF Mpixel/s on a 425-channel
+AVIRIS-NG cube).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's NumPy path on host cores
+
+A "step" is one pass of the whole hot path (repack/mask, statistics, eigen, LOO alpha search, weights,
+scoring, column statistics) over one synthetic flightline: BASELINE configs[1], 598 columns x 425 channels
+x 20 000 lines, active window 351..422.  With N > 1 every rank processes its own flightline (flightline
+sharding, no data-path collective) and the score tiles are gathered to rank 0 over NCCL inside the timed
+region.  One JSON line is printed by rank 0.
+
+`value`  device-resident throughput (inputs already in HBM), CUDA events on the launching stream,
+         max over ranks.
+`e2e`    the same metric through the C-ABI host call (cmf_run_host): pinned host cube -> H2D of the
+         active window -> all kernels -> D2H of scores, column statistics and alpha indices, every step.
+`roofline`      the dominant kernel (LOO pass, FP64 tensor bound) against the FP64 DMMA.8x8x4 peak
+                measured in this run by cmf_microbench (MEASURED_PEAKS.json has no FP64 figure).
+`roofline_hbm`  the scoring pass against the HBM copy peak of MEASURED_PEAKS.json.
+`cpu_baseline`  the oracle port of the reference (same NumPy/SciPy calls) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+for _v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+
+import numpy as np  # noqa: E402
+
+METRIC = "cmf_mpixel_per_s"
+UNIT = "Mpixel/s"
+ACTIVE = [351, 422]
+BANDS = 425
+FALLBACK_HBM_GBS = 6650.0        # B200_PROFILING.md fallback if MEASURED_PEAKS.json is absent
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": FALLBACK_HBM_GBS}, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, flag in zip(names, r[2:6]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def abscf_window():
+    from srcfinder_b200 import synth
+    return synth.load_ch4_library()[ACTIVE[0] - 1:ACTIVE[1], 2]
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    """One host core: the oracle port on `ncols` columns of a synthetic flightline (active bands only)."""
+    seed, lines, ncols = args
+    for v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"
+    from oracle import cmf_oracle as orc
+    from srcfinder_b200 import synth
+    lib = synth.load_ch4_library()[ACTIVE[0] - 1:ACTIVE[1]]
+    cube = synth.make_cube(lines, ncols, bands=lib.shape[0], seed=seed, lib=lib)
+    t0 = time.perf_counter()
+    res = orc.cmf_cube(cube, lib[:, 2], [1, lib.shape[0]])
+    dt = time.perf_counter() - t0
+    return dt, int(res["mask"].sum())
+
+
+def cpu_sample(lines, cols_per_core, cores, seed0=1000):
+    """Run the oracle port on `cores` processes at once; returns (Mpixel/s, wall s, pixels)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    jobs = [(seed0 + i, lines, cols_per_core) for i in range(cores)]
+    t0 = time.perf_counter()
+    with ctx.Pool(processes=cores) as pool:
+        out = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    compute = max(dt for dt, _ in out)          # the pool start-up (imports) is not part of the metric
+    pixels = lines * cols_per_core * cores
+    return pixels / compute / 1e6, wall, pixels, compute
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_baseline_leg(lines, budget_s=20.0):
+    cores = host_cores()
+    # one column of a 20 000-line flightline costs ~2-3 s on one core; size the sample to the budget
+    per_col = 2.5 * lines / 20000.0
+    cols = max(1, int(budget_s / max(per_col, 1e-3)))
+    cols = min(cols, 8)
+    val, wall, pixels, compute = cpu_sample(lines, cols, cores)
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d columns x %d lines on each of %d processes (1 BLAS thread each), %.1f s"
+                      % (cols, lines, cores, compute)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's NumPy/SciPy path (oracle port, cmf/robust_mf.py restated with the
+    same LAPACK calls) on the box's host cores; each step is a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    lines = args.lines
+    cores = host_cores()
+    cols = max(1, min(4, int(10.0 / max(2.5 * lines / 20000.0, 1e-3))))
+    vals, secs = [], []
+    for i in range(args.warmup):
+        cpu_sample(lines, 1, cores, seed0=500 + 10 * i)
+    for i in range(args.steps):
+        v, wall, pixels, compute = cpu_sample(lines, cols, cores, seed0=2000 + 100 * i)
+        vals.append(v); secs.append(compute)
+    value = float(np.mean(vals)) if vals else 0.0
+    sample = "%d columns x %d lines per process, %d processes, 1 BLAS thread each" % (cols, lines, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(secs) * 1e3) if secs else None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, n):
+    return {"workload": "configs[1]: full AVIRIS-NG flightline %d cols x %d ch x %d lines, single-pass "
+                        "unimodal looshrinkage CMF, active bands %d..%d, 201 alphas"
+                        % (args.samples, BANDS, args.lines, ACTIVE[0], ACTIVE[1]),
+            "lines": args.lines, "samples": args.samples, "bands": BANDS, "active_bands": ACTIVE,
+            "alphas": 201, "flightlines_per_gpu": 1, "sharding": "flightline per GPU, NCCL gather of scores",
+            "parallelism": "dp%d" % n, "timing": "inputs (3.4 GB/flightline) far larger than the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from srcfinder_b200 import ColumnwiseMF, _lib, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback "
+                         "(use --impl reference for the host baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L, S = args.lines, args.samples
+    D = ACTIVE[1] - ACTIVE[0] + 1
+    ab = abscf_window()
+    lib = _lib.load()
+
+    # FP64 tensor peak for the roofline (rank 0, before the timed region)
+    dmma_peak = lib.cmf_microbench(local, 0, 3) if rank == 0 else 0.0
+
+    slab = synth.make_slab_torch(L, S, ACTIVE[0], ACTIVE[1], dev, seed=2 + rank)
+    stream = torch.cuda.current_stream()
+    eng = ColumnwiseMF(L, BANDS, S, ACTIVE, ab, device=local, stream=stream.cuda_stream)
+    eng.bind_device(slab.data_ptr())
+    mf_dev = None
+    gathered = None
+    if world > 1:
+        # wrap the context's score buffer so NCCL gathers it without an extra copy
+        ptr = eng.device_ptr(_lib.OUT_MF)
+        mf_dev = _as_tensor(torch, ptr, (L, S), torch.float64, dev)
+        gathered = [torch.empty((L, S), dtype=torch.float64, device=dev) for _ in range(world)] if rank == 0 else None
+
+    def step(timing):
+        eng.run(timing=timing, sync=False)
+        if world > 1:
+            dist.gather(mf_dev, gathered, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step(True)
+        ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    kt = eng.kernel_times()                       # mean per-kernel ms over the timed steps (same stream)
+    launches = eng.launch_count() * args.steps + (args.steps if world > 1 else 0)
+    value = world * L * S * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the host API (rank-local; every rank does the same work)
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(torch, eng, slab, L, S, D, args, world, rank, dev, barrier)
+    out = None
+    if rank == 0:
+        peaks, src = measured_peaks()
+        flops = (2.0 * D * D + 2.0 * D * 201) * L * S          # projection + alpha contraction
+        loo_ms = kt.get("loo", float("nan"))
+        achieved = flops / (loo_ms * 1e-3) / 1e12
+        score_bytes = (4.0 * D + 8.0 + 1.0) * L * S            # one read of the slab + f64 score + mask byte
+        score_ms = kt.get("score", float("nan"))
+        traffic = load_traffic()
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
+            "roofline": {"kernel": "loo_kernel", "bound": "tensor", "achieved": achieved, "peak": dmma_peak,
+                         "unit": "TFLOP/s", "frac": achieved / dmma_peak if dmma_peak > 0 else None,
+                         "traffic": traffic.get("loo_kernel"),
+                         "peak_source": "FP64 DMMA.8x8x4 rate measured in this run by cmf_microbench(kind=0); "
+                                        "MEASURED_PEAKS.json holds no FP64 figure (bf16 %s TF/s is not the bound)"
+                                        % peaks.get("bf16_tflops"),
+                         "flops_per_launch": flops},
+            "roofline_hbm": {"kernel": "score_kernel", "bound": "hbm",
+                             "achieved": score_bytes / (score_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                             "unit": "GB/s", "frac": score_bytes / (score_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                             "traffic": traffic.get("score_kernel"), "peak_source": src + " (MEASURED_PEAKS.json hbm_gbs)",
+                             "bytes_per_launch": score_bytes},
+            "clocks": clocks.summary(), "gpu_launches": launches,
+        }
+        if e2e is not None:
+            out["e2e"] = e2e
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if not args.no_cpu and world == 1:
+            out["cpu_baseline"] = cpu_baseline_leg(L, budget_s=args.cpu_seconds)
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _as_tensor(torch, ptr, shape, dtype, dev):
+    """Zero-copy torch view of a device buffer owned by the C library."""
+    n = int(np.prod(shape))
+    itemsize = torch.empty((), dtype=dtype).element_size()
+
+    class _Arr(object):
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8" if itemsize == 8 else "<f4",
+                                    "data": (int(ptr), False), "version": 3, "strides": None}
+    return torch.as_tensor(_Arr(), device=dev).view(shape)
+
+
+def measure_e2e(torch, eng, slab, L, S, D, args, world, rank, dev, barrier):
+    """cmf_run_host on a pinned host cube shaped like the reference's input file (L, 425, S) float32."""
+    import torch.distributed as dist
+    nbytes = L * BANDS * S * 4
+    try:
+        host = torch.zeros((L, BANDS, S), dtype=torch.float32, pin_memory=True)
+    except Exception as exc:                                    # not enough lockable memory on this box
+        return {"value": None, "unit": UNIT, "error": "pinned %d-byte host cube failed: %s" % (nbytes, exc)}
+    host[:, ACTIVE[0] - 1:ACTIVE[1], :].copy_(slab)             # only the bands the path reads carry data
+    torch.cuda.synchronize()
+    mf = torch.empty((L, S), dtype=torch.float64, pin_memory=True)
+    cs = torch.empty((3, S), dtype=torch.float64, pin_memory=True)
+    ai = torch.empty((S,), dtype=torch.int32, pin_memory=True)
+    steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        eng.run_host(host.data_ptr(), mf.data_ptr(), cs.data_ptr(), ai.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.run_host(host.data_ptr(), mf.data_ptr(), cs.data_ptr(), ai.data_ptr())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    checksum = float(cs[2].sum())                               # the result really came back
+    return {"value": world * L * S * steps / dt / 1e6, "unit": UNIT, "ms_per_step": dt / steps * 1e3,
+            "h2d_bytes_per_step": L * D * S * 4, "d2h_bytes_per_step": L * S * 8 + 3 * S * 8 + S * 4,
+            "steps": steps, "host_buffer": "pinned float32 BIL cube (L,425,S); only the active window is copied",
+            "colstd_checksum": checksum}
+
+
+def load_traffic():
+    """dram bytes per launch from the committed ncu capture (profiles/traffic.json), if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            pass
+    return {}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lines", type=int, default=20000)
+    ap.add_argument("--samples", type=int, default=598)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -109,7 +109,8 @@ size_t cmf_output_bytes(const cmf_ctx* ctx, int what);
 /* ---- instrumentation ---- */
 int cmf_kernel_count(void);
 const char* cmf_kernel_name(int i);
-/* milliseconds of each kernel in the last cmf_run(CMF_RUN_TIMING); returns the number written */
+/* mean milliseconds of each kernel over every cmf_run(CMF_RUN_TIMING) since the previous call (the
+ * events sit on the context stream, inside whatever region the caller is timing); returns the count */
 int cmf_kernel_times(cmf_ctx* ctx, float* ms, int n);
 /* launches issued by the last cmf_run()/cmf_run_host() */
 int cmf_launch_count(const cmf_ctx* ctx);
@@ -121,8 +122,9 @@ int cmf_host_register(void* p, size_t bytes);
 int cmf_host_unregister(void* p);
 
 /* ---- micro-benchmarks used for the roofline denominators (profiles/): returns achieved rate ---- */
-/* kind: 0 DMMA.8x8x4 TFLOP/s, 1 DFMA TFLOP/s, 2 HBM read GB/s (8-byte loads), 3 HBM read GB/s (16-byte),
- *       4 HBM copy GB/s, 5 bulk-async-copy read GB/s */
+/* kind: 0 DMMA.8x8x4 TFLOP/s (32 warps/SM), 8 same with 8 warps/SM and 24 accumulators, 1 DFMA TFLOP/s,
+ *       2 HBM read GB/s (8-byte loads), 3 HBM read GB/s (16-byte), 4 HBM copy GB/s (read+write bytes),
+ *       5 bulk-async-copy read GB/s, 6 f32->f64 conversions G/s, 7 FP64 log+divide pairs G/s */
 double cmf_microbench(int device, int kind, int iters);
 
 #ifdef __cplusplus

@@ -51,7 +51,9 @@ struct cmf_ctx {
     int *colcnt_part = nullptr, *n = nullptr, *status = nullptr, *sweeps = nullptr, *mindex = nullptr;
     int nsplit = 1, lps = 8, nchunk_gram = 1, nchunk_loo = 1, nlanes = 1;
 
-    cudaEvent_t ev[K_COUNT + 1] = {};
+    cudaEvent_t ev[K_COUNT + 1] = {};              // scratch set (ordering events, untimed runs)
+    std::vector<std::vector<cudaEvent_t>> ev_sets;  // one set of K_COUNT+1 events per timed run
+    int timed_runs = 0;                             // timed runs recorded since the last cmf_kernel_times()
     std::vector<cudaEvent_t> blk_ev;
     bool timed = false;
     int launches = 0;
@@ -93,7 +95,18 @@ int enqueue(cmf_ctx* ctx, bool timing, const std::vector<cudaEvent_t>* blocks_re
     const Dims& d = ctx->d;
     cudaStream_t st = ctx->stream;
     ctx->launches = 0;
-    auto mark = [&](int i) { if (timing) cudaEventRecord(ctx->ev[i], st); };
+    cudaEvent_t* evs = nullptr;
+    if (timing) {
+        if (ctx->timed_runs >= 256) ctx->timed_runs = 0;      // ring: keep the last 256 timed runs
+        if ((int)ctx->ev_sets.size() <= ctx->timed_runs) {
+            std::vector<cudaEvent_t> set(K_COUNT + 1);
+            for (auto& e : set) cudaEventCreate(&e);
+            ctx->ev_sets.push_back(set);
+        }
+        evs = ctx->ev_sets[ctx->timed_runs].data();
+        ++ctx->timed_runs;
+    }
+    auto mark = [&](int i) { if (timing) cudaEventRecord(evs[i], st); };
     mark(0);
     if (blocks_ready) {
         int line = 0;
@@ -211,6 +224,7 @@ void cmf_destroy(cmf_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     free_buffers(ctx);
     for (int i = 0; i <= K_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (auto& set : ctx->ev_sets) for (cudaEvent_t e : set) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->blk_ev) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -434,11 +448,21 @@ const char* cmf_kernel_name(int i) { return (i >= 0 && i < K_COUNT) ? kKernelNam
 
 int cmf_kernel_times(cmf_ctx* ctx, float* ms, int n) {
     if (!ctx || !ms) return CMF_E_ARG;
-    if (!ctx->timed) return fail(ctx, CMF_E_STATE, "last cmf_run was not started with CMF_RUN_TIMING");
+    if (ctx->timed_runs == 0) return fail(ctx, CMF_E_STATE, "no cmf_run(CMF_RUN_TIMING) since the last query");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaEventSynchronize(ctx->ev[K_COUNT]));
     const int m = std::min(n, (int)K_COUNT);
-    for (int i = 0; i < m; ++i) CK(cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    for (int i = 0; i < m; ++i) ms[i] = 0.f;
+    for (int r = 0; r < ctx->timed_runs; ++r) {
+        cudaEvent_t* evs = ctx->ev_sets[r].data();
+        CK(cudaEventSynchronize(evs[K_COUNT]));
+        for (int i = 0; i < m; ++i) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, evs[i], evs[i + 1]));
+            ms[i] += t;
+        }
+    }
+    for (int i = 0; i < m; ++i) ms[i] /= (float)ctx->timed_runs;
+    ctx->timed_runs = 0;
     return m;
 }
 

@@ -195,3 +195,49 @@ def test_full_flightline_properties():
     assert np.array_equal(ref["alpha_index"], r1["alpha_index"][c0:c0 + 2])
     err = np.max(np.abs(ref["mf"] - r1["mf"][:, c0:c0 + 2]), axis=0) / ref["colstd"]
     assert np.max(err) < TIGHT_SIGMA
+
+
+@pytest.mark.parametrize("name", ["badpix_400x6", "co2window_300x4", "empirical_300x4"])
+def test_cli_products_match_reference_files(name, tmp_path):
+    """The drop-in CLI writes the files the reference writes: 4-band f64 BIP product (RGB copies + MF with
+    nodata), header keys, _bgmeta alpha indices, column-stats CSV."""
+    from srcfinder_b200 import envi, robust_mf
+    case = load_case(name)
+    cube = case["cube"]
+    L, B, S = cube.shape
+    inp, out = str(tmp_path / "scene_rdn"), str(tmp_path / "scene_mf")
+    lib = synth.write_library_txt(str(tmp_path / case["libname"]))
+    mm = envi.create_image(inp, {"samples": S, "lines": L, "bands": B, "data type": 4, "interleave": "bil",
+                                 "byte order": 0, "data ignore value": -9999,
+                                 "description": "synthetic AVIRIS-NG radiance", "bad pixel map": "none",
+                                 "wavelength units": "Nanometers", "fwhm": ["5.0"] * B,
+                                 "wavelength": ["%.2f" % w for w in synth.load_ch4_library()[:, 1]],
+                                 "smoothing factors": ["0"] * B})
+    mm[:] = cube
+    mm.flush()
+    rc = robust_mf.main(case["flags"] + [inp, lib, out])
+    assert rc == 0
+    hdr = envi.read_header(out + ".hdr")
+    ref_hdr = case["header"]
+    for key in ("samples", "lines", "bands", "data type", "interleave", "band names", "model parameters",
+                "data ignore value", "description", "bad pixel map"):
+        assert str(hdr[key]) == str(ref_hdr[key]), key
+    for key in ("wavelength", "fwhm", "smoothing factors", "wavelength units"):
+        assert key not in hdr
+    prod = np.asarray(envi.open_memmap(out))
+    ref = case["product"]
+    assert prod.shape == ref.shape and prod.dtype == np.float64
+    assert np.array_equal(prod[..., :3], ref[..., :3])                       # RGB copies, skipped dead columns
+    mask = ref[..., 3] != -9999.0
+    assert np.array_equal(prod[..., 3] != -9999.0, mask)
+    for c in range(S):
+        if mask[:, c].any() and np.isfinite(ref[mask[:, c], c, 3]).all():
+            err = np.max(np.abs(prod[mask[:, c], c, 3] - ref[mask[:, c], c, 3])) / np.std(ref[mask[:, c], c, 3])
+            assert err < TIGHT_SIGMA
+    if "bgmeta" in case:
+        bg = np.asarray(envi.open_memmap(out + "_bgmeta"))
+        assert bg.dtype == np.int16 and np.array_equal(bg, case["bgmeta"])
+        bh = envi.read_header(out + "_bgmeta.hdr")
+        assert bh["num alphas"] == "201" and bh["bands"] == "2"
+    rows = open(str(tmp_path / "scene_rdn_column_stats.csv")).read().splitlines()
+    assert len(rows) == 4 and rows[1].startswith("npix,")
