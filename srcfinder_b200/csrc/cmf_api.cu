@@ -49,7 +49,7 @@ struct cmf_ctx {
            *nll = nullptr, *w = nullptr, *wT = nullptr, *c0 = nullptr, *mf = nullptr, *stat_part = nullptr,
            *colstats = nullptr, *alphas_d = nullptr, *abscf_d = nullptr;
     int *colcnt_part = nullptr, *n = nullptr, *status = nullptr, *sweeps = nullptr, *mindex = nullptr;
-    int nsplit = 1, lps = 8, nchunk_gram = 1, nchunk_loo = 1, nlanes = 1;
+    int nsplit = 1, lps = 8, nchunk_gram = 1, nchunk_loo = 1, nlanes = 1, score_lpc = 0;
 
     cudaEvent_t ev[K_COUNT + 1] = {};              // scratch set (ordering events, untimed runs)
     std::vector<std::vector<cudaEvent_t>> ev_sets;  // one set of K_COUNT+1 events per timed run
@@ -142,7 +142,7 @@ int enqueue(cmf_ctx* ctx, bool timing, const std::vector<cudaEvent_t>* blocks_re
                     ctx->w, ctx->wT, ctx->c0, ctx->status, st);
     mark(6);
     launch_score(d, ctx->slab, ctx->mask, ctx->wT, ctx->c0, ctx->status, ctx->nodata, ctx->mf, ctx->stat_part,
-                 ctx->nlanes, st);
+                 ctx->nlanes, ctx->score_lpc, st);
     mark(7);
     launch_colstats(d, ctx->stat_part, ctx->nlanes, ctx->n, ctx->nodata, ctx->colstats, st);
     mark(8);
@@ -276,11 +276,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     ctx->nsplit = (d.L + ctx->lps - 1) / ctx->lps;
     ctx->nchunk_gram = pick_chunks(d.S, d.L, 256, ctx->sm_count, 1);
     ctx->nchunk_loo = pick_chunks(d.S, d.L, 128, ctx->sm_count, 1);
-    const int ngroups = (d.L + kScoreLines - 1) / kScoreLines;
-    const int SC = d.vec2 ? (d.S + 1) / 2 : d.S;
-    int want = std::max(1, (ctx->sm_count * 1536) / SC);
-    int per = (ngroups + want - 1) / want;
-    ctx->nlanes = (ngroups + per - 1) / per;
+    ctx->nlanes = score_plan(d, ctx->sm_count, &ctx->score_lpc);
 
     const size_t LS = (size_t)d.L * d.S;
     const int Sp = (d.S + 1) & ~1;

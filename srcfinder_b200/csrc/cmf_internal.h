@@ -51,7 +51,8 @@ void launch_finalize(const Dims& d, const double* fpart, int nchunk, const doubl
                      int* mindex, double* w, double* wT, double* c0, int* status, cudaStream_t st);
 void launch_score(const Dims& d, const float* slab, const uint8_t* mask, const double* wT, const double* c0,
                   const int* status, double nodata, double* mf, double* stat_part, int nlanes,
-                  cudaStream_t st);
+                  int lines_per_cta, cudaStream_t st);
+int score_plan(const Dims& d, int sm_count, int* lines_per_cta);
 void launch_colstats(const Dims& d, const double* stat_part, int nlanes, const int* n, double nodata,
                      double* colstats, cudaStream_t st);
 

@@ -6,6 +6,9 @@
 //
 // Reference steps replaced (cmf/robust_mf.py): :282,:298-304 (valid mask + gather), :347 (mean),
 // :376-386 (matched filter), :388-392 (column statistics).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "cmf_common.cuh"
 #include "cmf_internal.h"
 
@@ -285,6 +288,94 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ sl
     if (has1) { sp[2] = sum1; sp[3] = sq1; }
 }
 
+// ---------------------------------------------------------------------------------------- K5 (tiled)
+// Scoring pass, HBM-bound form.  CTA = (tile of 128 columns) x (range of lines); the tile's FP64 weights
+// (D x 64 column pairs x 16 B) stay in shared memory for the whole range, so a thread's registers hold
+// nothing but radiances in flight: thread <-> (column pair, NL consecutive lines), BC bands per batch =
+// NL*BC independent 8-byte loads issued back to back before the first FMA.  A warp reads 256 contiguous
+// bytes of each (line, band) row and writes 512 contiguous bytes of scores per line.
+constexpr int kScoreTile = 128;   // columns per CTA
+constexpr int kScoreSlots = 4;    // line slots per CTA (256 threads = 64 column pairs x 4 slots)
+
+template <int NL, int BC, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    score_tiled_kernel(const float* __restrict__ slab, long long line_pitch, int band_pitch, int L, int S,
+                       int D, const uint8_t* __restrict__ mask, const double* __restrict__ wT, int Sp,
+                       const double* __restrict__ c0, const int* __restrict__ status, double nodata,
+                       double* __restrict__ mf, double* __restrict__ stat_part, int lines_per_cta) {
+    constexpr int CP = kScoreTile / 2;
+    extern __shared__ double2 w_s[];   // [D][CP]
+    const int tid = threadIdx.x;
+    const int cp = tid & (CP - 1), slot = tid / CP;
+    const int col0 = blockIdx.x * kScoreTile;
+    for (int i = tid; i < D * CP; i += 256) {
+        const int b = i / CP, c = col0 + 2 * (i % CP);
+        w_s[i] = (c < S) ? *reinterpret_cast<const double2*>(wT + (long long)b * Sp + c) : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    const int col = col0 + 2 * cp;
+    const int part = blockIdx.y * kScoreSlots + slot;             // index of this thread's statistics partial
+    double sum0 = 0.0, sum1 = 0.0, sq0 = 0.0, sq1 = 0.0;
+    if (col < S) {                                                // S is even on this path: col + 1 < S too
+        const double cz0 = c0[col], cz1 = c0[col + 1];
+        const bool zero0 = (status[col] & kStatusSingular) != 0, zero1 = (status[col + 1] & kStatusSingular) != 0;
+        const int l_begin = blockIdx.y * lines_per_cta;
+        const int l_end = min(L, l_begin + lines_per_cta);
+        const double2* wp = w_s + cp;
+        for (int l0 = l_begin + slot * NL; l0 < l_end; l0 += kScoreSlots * NL) {
+            const float* base = slab + (long long)l0 * line_pitch + col;
+            long long lo[NL];                                     // a missing line re-reads line l0
+#pragma unroll
+            for (int j = 0; j < NL; ++j) lo[j] = (l0 + j < l_end) ? (long long)j * line_pitch : 0;
+            double a0[NL], a1[NL];
+#pragma unroll
+            for (int j = 0; j < NL; ++j) { a0[j] = 0.0; a1[j] = 0.0; }
+            int b0 = 0;
+            for (; b0 + BC <= D; b0 += BC) {
+                float2 v[NL][BC];
+                const float* pb = base + (long long)b0 * band_pitch;
+#pragma unroll
+                for (int k = 0; k < BC; ++k)
+#pragma unroll
+                    for (int j = 0; j < NL; ++j) v[j][k] = ldg_nc_f2(pb + (long long)k * band_pitch + lo[j]);
+#pragma unroll
+                for (int k = 0; k < BC; ++k) {
+                    const double2 w = wp[(b0 + k) * CP];
+#pragma unroll
+                    for (int j = 0; j < NL; ++j) {
+                        a0[j] = fma((double)v[j][k].x, w.x, a0[j]);
+                        a1[j] = fma((double)v[j][k].y, w.y, a1[j]);
+                    }
+                }
+            }
+            for (; b0 < D; ++b0) {
+                const float* pb = base + (long long)b0 * band_pitch;
+                const double2 w = wp[b0 * CP];
+#pragma unroll
+                for (int j = 0; j < NL; ++j) {
+                    const float2 u = ldg_nc_f2(pb + lo[j]);
+                    a0[j] = fma((double)u.x, w.x, a0[j]);
+                    a1[j] = fma((double)u.y, w.y, a1[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NL; ++j) {
+                if (l0 + j < l_end) {
+                    const long long o = (long long)(l0 + j) * S + col;
+                    const uchar2 ok = *reinterpret_cast<const uchar2*>(mask + o);
+                    const double r0 = ok.x ? (zero0 ? 0.0 : a0[j] - cz0) : nodata;
+                    const double r1 = ok.y ? (zero1 ? 0.0 : a1[j] - cz1) : nodata;
+                    if (ok.x) { sum0 += r0; sq0 += r0 * r0; }
+                    if (ok.y) { sum1 += r1; sq1 += r1 * r1; }
+                    *reinterpret_cast<double2*>(mf + o) = make_double2(r0, r1);
+                }
+            }
+        }
+        double* sp = stat_part + ((long long)part * S + col) * 2;
+        sp[0] = sum0; sp[1] = sq0; sp[2] = sum1; sp[3] = sq1;
+    }
+}
+
 // ---------------------------------------------------------------------------------------- K6
 // colnum / colavg / colstd (np.mean, np.std ddof=0 of the written scores; cmf/robust_mf.py:388-391)
 __global__ void colstats_kernel(const double* __restrict__ stat_part, int nlanes, int S,
@@ -369,21 +460,73 @@ void launch_mean(const Dims& d, const double* colsum_part, const int* colcnt_par
     mean_kernel<<<d.S, 128, 0, st>>>(colsum_part, colcnt_part, nsplit, d.S, d.DP, mu, n);
 }
 
+// Plan of the scoring pass: number of statistics partials per column (`nlanes`) and, on the tiled path,
+// the lines each CTA covers.  The tiled grid is sized to one wave of 3 CTAs per SM.
+struct ScoreVariant { int nl, bc, minb; };
+
+static ScoreVariant score_variant() {
+    // tuning hook (tools/ only): CMF_SCORE_VARIANT=NL,BC,MINB picks another instantiation
+    static ScoreVariant v = [] {
+        ScoreVariant r{2, 18, 2};   // measured best on B200: 0.59 ms per 20k-line flightline
+        if (const char* e = getenv("CMF_SCORE_VARIANT")) sscanf(e, "%d,%d,%d", &r.nl, &r.bc, &r.minb);
+        return r;
+    }();
+    return v;
+}
+
+int score_plan(const Dims& d, int sm_count, int* lines_per_cta) {
+    if (d.vec2) {
+        const ScoreVariant v = score_variant();
+        const int ntiles = (d.S + kScoreTile - 1) / kScoreTile;
+        const int step = kScoreSlots * v.nl;
+        int nranges = (sm_count * v.minb) / ntiles;
+        if (nranges < 1) nranges = 1;
+        int lpc = (d.L + nranges - 1) / nranges;
+        lpc = (lpc + step - 1) / step * step;
+        nranges = (d.L + lpc - 1) / lpc;
+        *lines_per_cta = lpc;
+        return nranges * kScoreSlots;
+    }
+    const int ngroups = (d.L + kScoreLines - 1) / kScoreLines;
+    int want = (sm_count * 1536) / d.S;
+    if (want < 1) want = 1;
+    const int per = (ngroups + want - 1) / want;
+    *lines_per_cta = 0;
+    return (ngroups + per - 1) / per;
+}
+
+template <int NL, int BC, int MINB>
+static void launch_score_tiled(const Dims& d, const float* slab, const uint8_t* mask, const double* wT,
+                               const double* c0, const int* status, double nodata, double* mf,
+                               double* stat_part, int nlanes, int lines_per_cta, cudaStream_t st) {
+    const int Sp = (d.S + 1) & ~1;
+    const size_t smem = (size_t)d.D * (kScoreTile / 2) * sizeof(double2);
+    cudaFuncSetAttribute(score_tiled_kernel<NL, BC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((d.S + kScoreTile - 1) / kScoreTile, nlanes / kScoreSlots);
+    score_tiled_kernel<NL, BC, MINB><<<grid, 256, smem, st>>>(slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, mask,
+                                                              wT, Sp, c0, status, nodata, mf, stat_part,
+                                                              lines_per_cta);
+}
+
 void launch_score(const Dims& d, const float* slab, const uint8_t* mask, const double* wT, const double* c0,
                   const int* status, double nodata, double* mf, double* stat_part, int nlanes,
-                  cudaStream_t st) {
+                  int lines_per_cta, cudaStream_t st) {
     const int Sp = (d.S + 1) & ~1;
     if (d.vec2) {
-        const long long total = (long long)((d.S + 1) / 2) * nlanes;
-        score_kernel<2><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-            slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, mask, wT, Sp, c0, status, nodata, mf, stat_part,
-            nlanes);
-    } else {
-        const long long total = (long long)d.S * nlanes;
-        score_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-            slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, mask, wT, Sp, c0, status, nodata, mf, stat_part,
-            nlanes);
+        const ScoreVariant v = score_variant();
+#define CMF_SV(NL, BC, MB)                                                                              \
+    if (v.nl == NL && v.bc == BC && v.minb == MB)                                                       \
+        return launch_score_tiled<NL, BC, MB>(d, slab, mask, wT, c0, status, nodata, mf, stat_part, nlanes, \
+                                              lines_per_cta, st);
+        CMF_SV(2, 18, 2) CMF_SV(2, 12, 2) CMF_SV(4, 8, 2) CMF_SV(2, 8, 3)
+#undef CMF_SV
+        return launch_score_tiled<2, 18, 2>(d, slab, mask, wT, c0, status, nodata, mf, stat_part, nlanes,
+                                            lines_per_cta, st);
     }
+    const long long total = (long long)d.S * nlanes;
+    score_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, mask, wT, Sp, c0, status, nodata, mf, stat_part,
+        nlanes);
 }
 
 void launch_colstats(const Dims& d, const double* stat_part, int nlanes, const int* n, double nodata,

@@ -66,6 +66,61 @@ __global__ void __launch_bounds__(256) logdiv_kernel(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// legacy warp-level tensor path (mma.sync, SASS HMMA): how much of it survives on sm_100a
+template <int NACC>
+__global__ void __launch_bounds__(256) mma_tf32_kernel(float* out, int iters) {
+    float c[NACC][4];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
+    uint32_t a0 = 0x3f800000u + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = a0 + 4, b1 = a0 + 5;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int NACC>
+__global__ void __launch_bounds__(256) mma_bf16_kernel(float* out, int iters) {
+    float c[NACC][4];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.f; }
+    uint32_t a0 = 0x3f803f80u + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, b0 = a0 + 4, b1 = a0 + 5;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i)
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) ffma_kernel(float* out, int iters) {
+    float c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = i;
+    const float a = 1.0f + threadIdx.x * 1e-7f, b = 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = fmaf(c[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename V>
 __global__ void __launch_bounds__(256) read_kernel(const V* __restrict__ in, size_t n, float* out) {
     float acc = 0.f;
@@ -154,6 +209,25 @@ extern "C" double cmf_microbench(int device, int kind, int iters) {
         else if (kind == 6) result = threads * inner * 8 / sec * 1e-9;                   // Gcvt/s
         else result = threads * inner / sec * 1e-9;                                      // G (log+div)/s
         cudaFree(out); cudaFree(fin);
+    } else if (kind >= 9 && kind <= 11) {
+        const int blocks = sms * 4;
+        float* out; cudaMalloc(&out, (size_t)blocks * 256 * sizeof(float));
+        const int inner = 4096;
+        auto run = [&]() {
+            if (kind == 9) mma_tf32_kernel<8><<<blocks, 256>>>(out, inner);
+            else if (kind == 10) mma_bf16_kernel<8><<<blocks, 256>>>(out, inner);
+            else ffma_kernel<<<blocks, 256>>>(out, inner);
+        };
+        run(); cudaDeviceSynchronize();
+        cudaEventRecord(e0);
+        for (int i = 0; i < iters; ++i) run();
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        const double sec = time_ms(e0, e1) * 1e-3 / iters;
+        const double threads = (double)blocks * 256;
+        if (kind == 9) result = threads / 32 * inner * 8 * (2.0 * 16 * 8 * 8) / sec * 1e-12;        // TFLOP/s
+        else if (kind == 10) result = threads / 32 * inner * 8 * (2.0 * 16 * 8 * 16) / sec * 1e-12;  // TFLOP/s
+        else result = threads * inner * 16 * 2.0 / sec * 1e-12;                                      // TFLOP/s
+        cudaFree(out);
     } else if (kind >= 2 && kind <= 5) {
         const size_t bytes = (size_t)4 << 30;   // 4 GiB, far larger than the 126 MB L2
         float* in; float* outp = nullptr; float* flag;

@@ -14,7 +14,7 @@ from srcfinder_b200 import ColumnwiseMF, _lib, synth
 out = {}
 lib = _lib.load()
 names = {0: "dmma_tflops_32w", 8: "dmma_tflops_8w_ilp24", 1: "dfma_tflops", 6: "cvt_f32_f64_gops",
-         7: "logdiv_gops", 2: "hbm_read_8B_gbs", 3: "hbm_read_16B_gbs", 4: "hbm_copy_gbs", 5: "hbm_bulk_read_gbs"}
+         7: "logdiv_gops", 9: "mma_sync_tf32_tflops", 10: "mma_sync_bf16_tflops", 11: "ffma_tflops", 2: "hbm_read_8B_gbs", 3: "hbm_read_16B_gbs", 4: "hbm_copy_gbs", 5: "hbm_bulk_read_gbs"}
 for kind, name in names.items():
     out[name] = lib.cmf_microbench(0, kind, 5)
     print(name, out[name], flush=True)
