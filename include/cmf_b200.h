@@ -51,13 +51,19 @@ enum {
     CMF_OUT_MASK = 1,         /* uint8  [L][S]   1 = pixel used (finite and >= 0 in every active band, :282) */
     CMF_OUT_COLSTATS = 2,     /* double [3][S]   npix, mean, std(ddof=0) of the written scores (:388-391) */
     CMF_OUT_ALPHA_INDEX = 3,  /* int32  [S]      argmin index, -1 all-inf, -2 not applicable (:121-127) */
-    CMF_OUT_NLL = 4,          /* double [S][A]   leave-one-out negative log likelihood (:117) */
+    CMF_OUT_NLL = 4,          /* double [S][A]   leave-one-out negative log likelihood (:117): exact FP64 under
+                                                  CMF_RUN_EXACT; otherwise exact for the alphas near the minimum and
+                                                  the screened value (error ~1e-7) elsewhere */
     CMF_OUT_MU = 5,           /* double [S][DP]  column mean over valid pixels (:347) */
     CMF_OUT_WEIGHTS = 6,      /* double [S][DP]  Cinv t / (t Cinv t) * scale (:380-384) */
     CMF_OUT_STATUS = 7,       /* int32  [S]      CMF_COL_* bits */
     CMF_OUT_NVALID = 8,       /* int32  [S]      valid pixels per column (nuse, :302) */
     CMF_OUT_EIGVALS = 9,      /* double [S][DP]  eigenvalues of the column correlation matrix */
-    CMF_OUT_SWEEPS = 10       /* int32  [S]      Jacobi sweeps used */
+    CMF_OUT_SWEEPS = 10,      /* int32  [S]      Jacobi sweeps used */
+    CMF_OUT_NCAND = 11,       /* int32  [S]      alphas the screening pass could not separate (1 = decided by the
+                                                  screen, > 1 = decided by exact FP64 re-evaluation); screened runs only */
+    CMF_OUT_SCREEN_TOL = 12   /* double [S]      nll margin within which the screen treats alphas as tied; the
+                                                  selection is exact while the screening error stays below half of it */
 };
 
 typedef struct cmf_problem {
@@ -92,7 +98,10 @@ int cmf_upload_bil(cmf_ctx* ctx, const float* host_cube);
 int cmf_bind_device_slab(cmf_ctx* ctx, const float* dev_slab, int64_t line_pitch, int32_t band_pitch);
 
 /* ---- compute: the whole column loop (:297-392) for every column, no host round trip ---- */
-enum { CMF_RUN_TIMING = 1 };      /* bracket every kernel with CUDA events (see cmf_kernel_times) */
+enum {
+    CMF_RUN_TIMING = 1,           /* bracket every kernel with CUDA events (see cmf_kernel_times) */
+    CMF_RUN_EXACT = 2             /* evaluate every alpha in FP64 (no tensor-core screening of the search) */
+};
 int cmf_run(cmf_ctx* ctx, uint32_t flags);
 int cmf_sync(cmf_ctx* ctx);
 

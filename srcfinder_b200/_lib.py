@@ -18,8 +18,9 @@ SYMBOLS = [
 ]
 
 OUT_MF, OUT_MASK, OUT_COLSTATS, OUT_ALPHA_INDEX, OUT_NLL, OUT_MU, OUT_WEIGHTS, OUT_STATUS, OUT_NVALID, \
-    OUT_EIGVALS, OUT_SWEEPS = range(11)
+    OUT_EIGVALS, OUT_SWEEPS, OUT_NCAND, OUT_SCREEN_TOL = range(13)
 RUN_TIMING = 1
+RUN_EXACT = 2
 MODEL_LOOSHRINKAGE, MODEL_EMPIRICAL = 0, 1
 COL_EMPTY, COL_DEGENERATE, COL_SINGULAR, COL_NOCONVERGE, COL_ALLINF = 1, 2, 4, 8, 16
 

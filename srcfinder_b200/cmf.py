@@ -101,8 +101,11 @@ class ColumnwiseMF(object):
         self._check(self._lib.cmf_bind_device_slab(self._ctx, C.c_void_p(int(dev_ptr)), lp, bp))
 
     # ------------------------------------------------------------------ compute
-    def run(self, timing=False, sync=True):
-        self._check(self._lib.cmf_run(self._ctx, _lib.RUN_TIMING if timing else 0))
+    def run(self, timing=False, sync=True, exact=False):
+        """All kernels on the context stream.  ``exact=True`` evaluates every alpha of the leave-one-out
+        search in FP64 instead of screening it on the tensor cores first (same selected index)."""
+        flags = (_lib.RUN_TIMING if timing else 0) | (_lib.RUN_EXACT if exact else 0)
+        self._check(self._lib.cmf_run(self._ctx, flags))
         if sync:
             self.sync()
 
@@ -170,6 +173,14 @@ class ColumnwiseMF(object):
     def sweeps(self):
         return self._get(_lib.OUT_SWEEPS, np.int32, (self.S,))
 
+    def ncand(self):
+        """Alphas per column the screening pass left to the exact FP64 re-evaluation (1 = none)."""
+        return self._get(_lib.OUT_NCAND, np.int32, (self.S,))
+
+    def screen_tol(self):
+        """Per-column nll margin used by the screen (selection is exact while its error is below half of it)."""
+        return self._get(_lib.OUT_SCREEN_TOL, np.float64, (self.S,))
+
     def results(self):
         cs = self.colstats()
         return dict(mf=self.mf(), mask=self.mask(), colnum=cs[0], colavg=cs[1], colstd=cs[2],
@@ -178,13 +189,13 @@ class ColumnwiseMF(object):
 
 
 def cmf_cube(cube_lbs, abscf, active, model="looshrinkage", reflectance=False, alphas=None,
-             nodata=-9999.0, device=0):
+             nodata=-9999.0, device=0, exact=False):
     """One-shot convenience: same inputs/outputs as the oracle's ``cmf_cube`` (for parity tests)."""
     L, B, S = cube_lbs.shape
     with ColumnwiseMF(L, B, S, active, abscf, model=model, reflectance=reflectance, alphas=alphas,
                       nodata=nodata, device=device) as eng:
         eng.upload(cube_lbs)
-        eng.run()
+        eng.run(exact=exact)
         res = eng.results()
         if model == "looshrinkage":
             res["nll"] = eng.nll()

@@ -1,6 +1,7 @@
 // Host side of the C ABI (include/cmf_b200.h): context, device buffers, the kernel sequence.
 // No arithmetic happens here and nothing falls back to the CPU.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -14,9 +15,10 @@ using namespace cmf;
 
 namespace {
 
-enum { K_REPACK = 0, K_MEAN, K_GRAM, K_EIGEN, K_LOO, K_FINALIZE, K_SCORE, K_COLSTATS, K_COUNT };
-const char* kKernelNames[K_COUNT] = {"repack", "mean", "gram", "eigen", "loo", "finalize", "score",
-                                     "colstats"};
+enum { K_REPACK = 0, K_MEAN, K_GRAM, K_EIGEN, K_TABLES, K_SCREEN, K_SELECT, K_LOO, K_FINALIZE, K_SCORE,
+       K_COLSTATS, K_COUNT };
+const char* kKernelNames[K_COUNT] = {"repack", "mean", "gram", "eigen", "tables", "screen", "select", "loo",
+                                     "finalize", "score", "colstats"};
 
 std::string g_create_error;
 
@@ -49,6 +51,15 @@ struct cmf_ctx {
            *nll = nullptr, *w = nullptr, *wT = nullptr, *c0 = nullptr, *mf = nullptr, *stat_part = nullptr,
            *colstats = nullptr, *alphas_d = nullptr, *abscf_d = nullptr;
     int *colcnt_part = nullptr, *n = nullptr, *status = nullptr, *sweeps = nullptr, *mindex = nullptr;
+    // tensor-core screening of the alpha search (K3a/K3b)
+    float *Ws = nullptr, *betaf = nullptr, *Ps = nullptr;
+    double *rsum = nullptr, *fscreen = nullptr, *tol_col = nullptr, *slogT = nullptr;
+    int eigen_method = 0;         // 0 Householder + QL, 1 cyclic Jacobi (CMF_EIGEN=jacobi, cross-checks)
+    int *sel_index = nullptr, *ncand = nullptr;
+    unsigned long long* tile_mask = nullptr;
+    bool can_screen = false;
+    double screen_tol = 2.0e-5;   // relative to the screened part of nll; measured error is <= 2.5e-6
+    int nchunk_screen = 1;
     int nsplit = 1, lps = 8, nchunk_gram = 1, nchunk_loo = 1, nlanes = 1, score_lpc = 0;
 
     cudaEvent_t ev[K_COUNT + 1] = {};              // scratch set (ordering events, untimed runs)
@@ -56,6 +67,7 @@ struct cmf_ctx {
     int timed_runs = 0;                             // timed runs recorded since the last cmf_kernel_times()
     std::vector<cudaEvent_t> blk_ev;
     bool timed = false;
+    bool screened = false;                          // the last run used the screening path
     int launches = 0;
 };
 
@@ -91,7 +103,8 @@ cudaError_t dalloc(cmf_ctx* c, T** p, size_t count) {
 
 // Launch the eight kernels on the context stream.  When `blocks_ready` is given, the repack pass runs
 // block by block, each block waiting on the event that marks its upload as complete.
-int enqueue(cmf_ctx* ctx, bool timing, const std::vector<cudaEvent_t>* blocks_ready, int lines_per_block) {
+int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t>* blocks_ready,
+            int lines_per_block) {
     const Dims& d = ctx->d;
     cudaStream_t st = ctx->stream;
     ctx->launches = 0;
@@ -128,25 +141,46 @@ int enqueue(cmf_ctx* ctx, bool timing, const std::vector<cudaEvent_t>* blocks_re
     mark(2);
     launch_gram(d, ctx->xt, ctx->mu, ctx->nchunk_gram, ctx->gram_part, st);
     mark(3);
-    launch_eigen(d, ctx->gram_part, ctx->nchunk_gram, ctx->n, ctx->alphas_d, ctx->model, ctx->P, ctx->Pf,
-                 ctx->Wf, ctx->lam, ctx->logdet, ctx->beta, ctx->status, ctx->sweeps, st);
+    const bool loo = ctx->model == CMF_MODEL_LOOSHRINKAGE;
+    const bool screen = loo && ctx->can_screen && !exact;
+    launch_eigen(d, ctx->gram_part, ctx->nchunk_gram, ctx->n, ctx->P, ctx->lam, ctx->slogT, ctx->status,
+                 ctx->sweeps, ctx->eigen_method, st);
     mark(4);
-    ctx->launches += 3;
-    if (ctx->model == CMF_MODEL_LOOSHRINKAGE) {
-        launch_loo(d, ctx->xt, ctx->mu, ctx->Pf, ctx->Wf, ctx->beta, ctx->nchunk_loo, ctx->fpart, st);
+    launch_tables(d, ctx->n, ctx->alphas_d, ctx->model, ctx->P, ctx->lam, ctx->slogT, ctx->Pf, ctx->Wf,
+                  ctx->logdet, ctx->beta, screen ? ctx->Ws : nullptr, ctx->betaf, ctx->rsum,
+                  screen ? ctx->Ps : nullptr, st);
+    mark(5);
+    ctx->launches += 4;
+    if (screen) {
+        launch_screen(d, ctx->xt, ctx->mu, ctx->Pf, ctx->Ps, ctx->Ws, ctx->betaf, ctx->n, ctx->nchunk_screen,
+                      ctx->fscreen, st);
         ++ctx->launches;
     }
-    mark(5);
+    mark(6);
+    if (screen) {
+        launch_select(d, ctx->fscreen, ctx->nchunk_screen, ctx->logdet, ctx->rsum, ctx->n, ctx->screen_tol,
+                      ctx->nll, ctx->sel_index, ctx->tile_mask, ctx->ncand, ctx->tol_col, st);
+        ++ctx->launches;
+    }
+    mark(7);
+    if (loo) {
+        launch_loo(d, ctx->xt, ctx->mu, ctx->Pf, ctx->Wf, ctx->beta, ctx->nchunk_loo, ctx->fpart,
+                   screen ? ctx->tile_mask : nullptr, st);
+        ++ctx->launches;
+    }
+    mark(8);
     launch_finalize(d, ctx->fpart, ctx->nchunk_loo, ctx->logdet, ctx->n, ctx->alphas_d, ctx->P, ctx->lam,
                     ctx->mu, ctx->abscf_d, ctx->model, ctx->reflectance, ctx->scale, ctx->nll, ctx->mindex,
-                    ctx->w, ctx->wT, ctx->c0, ctx->status, st);
-    mark(6);
+                    ctx->w, ctx->wT, ctx->c0, ctx->status, screen ? ctx->sel_index : nullptr,
+                    screen ? ctx->tile_mask : nullptr, st);
+    mark(9);
     launch_score(d, ctx->slab, ctx->mask, ctx->wT, ctx->c0, ctx->status, ctx->nodata, ctx->mf, ctx->stat_part,
                  ctx->nlanes, ctx->score_lpc, st);
-    mark(7);
+    mark(10);
     launch_colstats(d, ctx->stat_part, ctx->nlanes, ctx->n, ctx->nodata, ctx->colstats, st);
-    mark(8);
+    mark(11);
     ctx->launches += 3;
+    ctx->screened = screen;
     ctx->timed = timing;
     CK(cudaGetLastError());
     return CMF_OK;
@@ -184,6 +218,8 @@ OutDesc out_desc(const cmf_ctx* c, int what) {
         case CMF_OUT_NVALID: return {c->n, (size_t)d.S * sizeof(int)};
         case CMF_OUT_EIGVALS: return {c->lam, (size_t)d.S * d.DP * sizeof(double)};
         case CMF_OUT_SWEEPS: return {c->sweeps, (size_t)d.S * sizeof(int)};
+        case CMF_OUT_NCAND: return {c->ncand, (size_t)d.S * sizeof(int)};
+        case CMF_OUT_SCREEN_TOL: return {c->tol_col, (size_t)d.S * sizeof(double)};
         default: return {nullptr, 0};
     }
 }
@@ -266,6 +302,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     d.L = p->lines; d.S = p->samples; d.D = D; d.NT = NT; d.DP = 8 * NT;
     d.A = loo ? p->num_alphas : 1;
     d.NT2 = (d.A + 7) / 8; d.AP = d.NT2 * 8;
+    d.NT16 = (d.A + 15) / 16; d.AP16 = d.NT16 * 16;
     d.line_pitch = (long long)D * d.S; d.band_pitch = d.S; d.vec2 = (d.S % 2 == 0);
     ctx->B = p->bands; ctx->band_lo = p->band_lo; ctx->band_hi = p->band_hi;
     ctx->reflectance = p->reflectance; ctx->model = p->model; ctx->nodata = p->nodata;
@@ -277,6 +314,11 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     ctx->nchunk_gram = pick_chunks(d.S, d.L, 256, ctx->sm_count, 1);
     ctx->nchunk_loo = pick_chunks(d.S, d.L, 128, ctx->sm_count, 1);
     ctx->nlanes = score_plan(d, ctx->sm_count, &ctx->score_lpc);
+    ctx->nchunk_screen = ctx->nchunk_loo;
+    // the screening pass needs its tables in shared memory and a 64-bit tile mask (A <= 512)
+    ctx->can_screen = loo && d.NT2 <= 64 && screen_smem_bytes(d) <= 227 * 1024;
+    if (const char* e = getenv("CMF_SCREEN_TOL")) ctx->screen_tol = atof(e);      // tuning hook (tools/ only)
+    if (const char* e = getenv("CMF_EIGEN")) ctx->eigen_method = (strcmp(e, "jacobi") == 0) ? 1 : 0;
 
     const size_t LS = (size_t)d.L * d.S;
     const int Sp = (d.S + 1) & ~1;
@@ -309,6 +351,18 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     A_(dalloc(ctx, &ctx->colstats, (size_t)3 * d.S));
     A_(dalloc(ctx, &ctx->alphas_d, (size_t)d.A));
     A_(dalloc(ctx, &ctx->abscf_d, (size_t)d.DP));
+    A_(dalloc(ctx, &ctx->rsum, (size_t)d.S * d.AP));
+    A_(dalloc(ctx, &ctx->betaf, (size_t)d.S * d.AP16));
+    A_(dalloc(ctx, &ctx->sel_index, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->ncand, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->tile_mask, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->tol_col, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->slogT, (size_t)d.S));
+    if (ctx->can_screen) {
+        A_(dalloc(ctx, &ctx->Ws, (size_t)d.S * 2 * d.NT16 * d.NT * 32 * 4));
+        A_(dalloc(ctx, &ctx->fscreen, (size_t)d.S * ctx->nchunk_screen * d.AP16));
+        A_(dalloc(ctx, &ctx->Ps, (size_t)d.S * 2 * d.NT * d.NT * 32 * 2));
+    }
     if (e != cudaSuccess) {
         free_buffers(ctx);
         return fail(ctx, CMF_E_NOMEM, std::string("device allocation failed: ") + cudaGetErrorString(e));
@@ -360,7 +414,7 @@ int cmf_run(cmf_ctx* ctx, uint32_t flags) {
     if (!ctx) return CMF_E_ARG;
     if (!ctx->have_problem || !ctx->have_input) return fail(ctx, CMF_E_STATE, "cmf_run needs a problem and an input");
     CK(cudaSetDevice(ctx->device));
-    return enqueue(ctx, (flags & CMF_RUN_TIMING) != 0, nullptr, 0);
+    return enqueue(ctx, (flags & CMF_RUN_TIMING) != 0, (flags & CMF_RUN_EXACT) != 0, nullptr, 0);
 }
 
 int cmf_sync(cmf_ctx* ctx) {
@@ -402,9 +456,8 @@ int cmf_run_host(cmf_ctx* ctx, const float* host_cube, double* mf_out, double* c
         ready.push_back(ctx->blk_ev[b]);
     }
     ctx->have_input = true;
-    rc = enqueue(ctx, false, &ready, lines_per_block);
+    rc = enqueue(ctx, false, (flags & CMF_RUN_EXACT) != 0, &ready, lines_per_block);
     if (rc) return rc;
-    (void)flags;
     if (mf_out)
         CK(cudaMemcpyAsync(mf_out, ctx->mf, (size_t)d.L * d.S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (colstats_out)

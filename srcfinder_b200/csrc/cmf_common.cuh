@@ -26,6 +26,24 @@ __device__ __forceinline__ void mma884(double& c0, double& c1, double a, double 
         : "d"(a), "d"(b));
 }
 
+// ------------------------------------------------------------------ TF32 warp MMA (screening pass)
+// D(16x8) += A(16x8) * B(8x8), FP32 accumulate.  Fragments (PTX ISA, mma.m16n8k8 .tf32), g = lane/4, q = lane%4:
+//   A: a0 (g, q)  a1 (g+8, q)  a2 (g, q+4)  a3 (g+8, q+4)        B: b0 (k=q, n=g)  b1 (k=q+4, n=g)
+//   C: c0 (g, 2q)  c1 (g, 2q+1)  c2 (g+8, 2q)  c3 (g+8, 2q+1)
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const float4& a, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)),
+          "r"(__float_as_uint(a.w)), "r"(b0), "r"(b1));
+}
+
+// round-to-nearest FP32 -> TF32 (10-bit mantissa), returned in an FP32 container
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 // ------------------------------------------------------------------ mbarrier + bulk copy
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

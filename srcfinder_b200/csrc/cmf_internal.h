@@ -25,7 +25,8 @@ enum : int {
 
 struct Dims {
     int L, S, D, NT, DP;     // lines, samples, active bands, tiles, padded bands
-    int A, NT2, AP;          // alphas, alpha tiles, padded alphas
+    int A, NT2, AP;          // alphas, 8-alpha tiles, padded alphas
+    int NT16, AP16;          // 16-alpha tiles of the screening pass, padded alphas
     long long line_pitch;    // elements between consecutive lines of the active slab
     int band_pitch;          // elements between consecutive bands (== samples of the cube)
     int vec2;                // 8-byte loads allowed (S, pitches even and base aligned)
@@ -40,15 +41,26 @@ void launch_mean(const Dims& d, const double* colsum_part, const int* colcnt_par
                  double* mu, int* n, cudaStream_t st);
 void launch_gram(const Dims& d, const float* xt, const double* mu, int nchunk, double* gram_part,
                  cudaStream_t st);
-void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, const double* alphas,
-                  int model, double* P, double* Pf, double* Wf, double* lam, double* logdet,
-                  double* beta, int* status, int* sweeps, cudaStream_t st);
+void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, double* P, double* lam,
+                  double* slogT, int* status, int* sweeps, int method, cudaStream_t st);
+void launch_tables(const Dims& d, const int* n, const double* alphas, int model, const double* P,
+                   const double* lam, const double* slogT, double* Pf, double* Wf, double* logdet, double* beta,
+                   float* Ws, float* betaf, double* rsum, float* Ps, cudaStream_t st);
 void launch_loo(const Dims& d, const float* xt, const double* mu, const double* Pf, const double* Wf,
-                const double* beta, int nchunk, double* fpart, cudaStream_t st);
+                const double* beta, int nchunk, double* fpart, const unsigned long long* tile_mask,
+                cudaStream_t st);
+void launch_screen(const Dims& d, const float* xt, const double* mu, const double* Pf, const float* Ps,
+                   const float* Ws, const float* betaf, const int* n, int nchunk, double* fscreen,
+                   cudaStream_t st);
+size_t screen_smem_bytes(const Dims& d);
+void launch_select(const Dims& d, const double* fscreen, int nchunk, const double* logdet, const double* rsum,
+                   const int* n, double tol, double* nll, int* sel_index, unsigned long long* tile_mask,
+                   int* ncand, double* tol_out, cudaStream_t st);
 void launch_finalize(const Dims& d, const double* fpart, int nchunk, const double* logdet, const int* n,
                      const double* alphas, const double* P, const double* lam, const double* mu,
                      const double* abscf, int model, int reflectance, double scale, double* nll,
-                     int* mindex, double* w, double* wT, double* c0, int* status, cudaStream_t st);
+                     int* mindex, double* w, double* wT, double* c0, int* status, const int* sel_index,
+                     const unsigned long long* tile_mask, cudaStream_t st);
 void launch_score(const Dims& d, const float* slab, const uint8_t* mask, const double* wT, const double* c0,
                   const int* status, double nodata, double* mf, double* stat_part, int nlanes,
                   int lines_per_cta, cudaStream_t st);

@@ -30,10 +30,8 @@ __device__ __forceinline__ void tri_unrank(int t, int& i, int& j) {
 
 template <int NT>
 __global__ void __launch_bounds__(512)
-    eigen_kernel(const double* __restrict__ gram_part, int nchunk, const int* __restrict__ n_g,
-                 const double* __restrict__ alphas, int A, int NT2, int D, int model,
-                 double* __restrict__ P_g, double* __restrict__ Pf_g, double* __restrict__ Wf_g,
-                 double* __restrict__ lam_g, double* __restrict__ logdet_g, double* __restrict__ beta_g,
+    eigen_kernel(const double* __restrict__ gram_part, int nchunk, const int* __restrict__ n_g, int D,
+                 double* __restrict__ P_g, double* __restrict__ lam_g, double* __restrict__ slogT_g,
                  int* __restrict__ status_g, int* __restrict__ sweeps_g) {
     constexpr int DP = 8 * NT, LD = DP + 1, NTRI = NT * (NT + 1) / 2;
     extern __shared__ double sm[];
@@ -49,21 +47,16 @@ __global__ void __launch_bounds__(512)
 
     const int s = blockIdx.x, tid = threadIdx.x;
     const int n = n_g[s];
-    const int AP = NT2 * 8;
     double* Pout = P_g + (long long)s * DP * DP;
-    double* Pfout = Pf_g + (long long)s * (DP / 4) * NT * 32;
-    double* Wfout = Wf_g + (long long)s * (DP / 4) * NT2 * 32;
 
     if (n < 2) {  // empty or single-pixel column: nothing to factorise (handled in K4)
         for (int i = tid; i < DP * DP; i += blockDim.x) Pout[i] = 0.0;
-        for (int i = tid; i < (DP / 4) * NT * 32; i += blockDim.x) Pfout[i] = 0.0;
-        for (int i = tid; i < (DP / 4) * NT2 * 32; i += blockDim.x) Wfout[i] = 0.0;
         for (int i = tid; i < DP; i += blockDim.x) lam_g[(long long)s * DP + i] = 0.0;
-        for (int i = tid; i < AP; i += blockDim.x) {
-            logdet_g[(long long)s * AP + i] = 0.0;
-            beta_g[(long long)s * AP + i] = 0.0;
+        if (tid == 0) {
+            status_g[s] = (n == 0) ? kStatusEmpty : kStatusDegenerate;
+            sweeps_g[s] = 0;
+            slogT_g[s] = 0.0;
         }
-        if (tid == 0) { status_g[s] = (n == 0) ? kStatusEmpty : kStatusDegenerate; sweeps_g[s] = 0; }
         return;
     }
 
@@ -177,31 +170,359 @@ __global__ void __launch_bounds__(512)
     }
     __syncthreads();
 
-    // ---- P = T^-1/2 V : row-major copy for K4, fragment-ordered copy for the LOO pass
+    // ---- P = T^-1/2 V (row-major; K2b derives the fragment-ordered tables)
     for (int idx = tid; idx < DP * DP; idx += blockDim.x) {
         const int b = idx / DP, j = idx % DP;
         Pout[idx] = (b < D && j < D) ? dinv[b] * Vm[b * LD + j] : 0.0;
     }
-    // Pf[ks][nt][lane] = P[b = 4 ks + lane%4][j = 8 nt + lane/4]   (B operand of y = xc . P)
+    if (tid == 0) slogT_g[s] = sumlogT;
+}
+
+// ---------------------------------------------------------------------------------------- K2 (QL)
+// Householder tridiagonalisation + implicit-shift QL with accumulated transformations (the EISPACK
+// tred2 / tql2 pair; the same reduction LAPACK's dsteqr path uses) of the D x D correlation matrix, one
+// 128-thread CTA per column with the matrix in shared memory.  Against the cyclic Jacobi above it needs
+// ~10x fewer shared-memory passes (Jacobi: ~10 sweeps x 71 steps x the whole of A and V; QL: ~1.7
+// iterations per eigenvalue, each a chain of plane rotations on two columns), so all columns of a
+// flightline are resident at once (5 CTAs per SM) and the pass is bound by the serial rotation recurrence.
+constexpr int kQlThreads = 128;
+constexpr int kQlMaxIter = 60;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum of one double per thread (all threads get the result); red has one slot per warp
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kQlThreads / 32; ++w) t += red[w];
+    return t;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kQlThreads)
+    eigen_ql_kernel(const double* __restrict__ gram_part, int nchunk, const int* __restrict__ n_g, int D,
+                    double* __restrict__ P_g, double* __restrict__ lam_g, double* __restrict__ slogT_g,
+                    int* __restrict__ status_g, int* __restrict__ sweeps_g) {
+    constexpr int DP = 8 * NT, LD = DP + 1, NTRI = NT * (NT + 1) / 2;
+    extern __shared__ double sm[];
+    double* a = sm;                  // [DP][LD]  correlation matrix -> Householder vectors -> eigenvectors
+    double* dinv = a + DP * LD;      // [DP]      T^-1/2
+    double* d = dinv + DP;           // [DP]      diagonal -> eigenvalues
+    double* e = d + DP;              // [DP]      off-diagonal
+    double* cs = e + DP;             // [2*DP]    rotation (c, s) pairs of one QL iteration
+    double* red = cs + 2 * DP;       // [8]       reduction scratch / broadcast
+    __shared__ int sh_m, sh_cnt, sh_flag;
+
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kQlThreads / 32;
+    const int n = n_g[s];
+    double* Pout = P_g + (long long)s * DP * DP;
+    if (n < 2) {
+        for (int i = tid; i < DP * DP; i += blockDim.x) Pout[i] = 0.0;
+        for (int i = tid; i < DP; i += blockDim.x) lam_g[(long long)s * DP + i] = 0.0;
+        if (tid == 0) {
+            status_g[s] = (n == 0) ? kStatusEmpty : kStatusDegenerate;
+            sweeps_g[s] = 0;
+            slogT_g[s] = 0.0;
+        }
+        return;
+    }
+    // ---- covariance from the Gram partials (fixed order), correlation scaling
+    const double inv_nm1 = 1.0 / (double)(n - 1);
+    for (int idx = tid; idx < NTRI * 64; idx += blockDim.x) {
+        const int t = idx >> 6, within = idx & 63;
+        const int ln = within >> 1, ee = within & 1;
+        int ti, tj;
+        tri_unrank(t, ti, tj);
+        double v = 0.0;
+        for (int c = 0; c < nchunk; ++c) v += gram_part[((long long)s * nchunk + c) * NTRI * 64 + idx];
+        v *= inv_nm1;
+        const int row = 8 * ti + (ln >> 2), col = 8 * tj + 2 * (ln & 3) + ee;
+        a[row * LD + col] = v;
+        if (ti != tj) a[col * LD + row] = v;
+    }
+    __syncthreads();
+    if (tid < DP) {
+        const double t0 = (tid < D) ? a[tid * LD + tid] : 0.0;
+        dinv[tid] = (t0 > 0.0) ? 1.0 / sqrt(t0) : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double acc = 0.0;
+        for (int b = 0; b < D; ++b) acc += log(1.0e4 * a[b * LD + b]);   // log det of the scaled T (:94-99)
+        slogT_g[s] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < DP * DP; idx += blockDim.x) {
+        const int r = idx / DP, c = idx % DP;
+        double v = a[r * LD + c] * dinv[r] * dinv[c];
+        if (r == c) v = (r < D && dinv[r] > 0.0) ? 1.0 : 0.0;
+        if (r >= D || c >= D) v = 0.0;
+        a[r * LD + c] = v;
+    }
+    __syncthreads();
+
+    // ---- tred2: reduce to tridiagonal form, lower triangle, rows n-1 .. 1
+    for (int i = D - 1; i >= 1; --i) {
+        const int l = i - 1;
+        double h = 0.0;
+        if (l > 0) {
+            double part = 0.0;
+            for (int k = tid; k <= l; k += blockDim.x) part += fabs(a[i * LD + k]);
+            const double scale = block_sum(part, red);
+            if (scale == 0.0) {
+                if (tid == 0) e[i] = a[i * LD + l];
+            } else {
+                part = 0.0;
+                for (int k = tid; k <= l; k += blockDim.x) {
+                    const double v = a[i * LD + k] / scale;
+                    a[i * LD + k] = v;
+                    part += v * v;
+                }
+                h = block_sum(part, red);
+                double f = a[i * LD + l];
+                const double g = (f >= 0.0) ? -sqrt(h) : sqrt(h);
+                h -= f * g;
+                __syncthreads();                       // everyone has read a[i][l]
+                if (tid == 0) { e[i] = scale * g; a[i * LD + l] = f - g; }
+                __syncthreads();
+                // p = A u / h  ->  e[0..l]
+                part = 0.0;
+                for (int j = tid; j <= l; j += blockDim.x) {
+                    a[j * LD + i] = a[i * LD + j] / h;
+                    double gj = 0.0;
+                    for (int k = 0; k <= j; ++k) gj += a[j * LD + k] * a[i * LD + k];
+                    for (int k = j + 1; k <= l; ++k) gj += a[k * LD + j] * a[i * LD + k];
+                    gj /= h;
+                    e[j] = gj;
+                    part += gj * a[i * LD + j];
+                }
+                f = block_sum(part, red);
+                const double hh = f / (h + h);
+                for (int j = tid; j <= l; j += blockDim.x) e[j] -= hh * a[i * LD + j];
+                __syncthreads();
+                // A <- A - u q^T - q u^T on the lower triangle
+                for (int j = warp; j <= l; j += NW) {
+                    const double fj = a[i * LD + j], gj = e[j];
+                    for (int k = lane; k <= j; k += 32) a[j * LD + k] -= fj * e[k] + gj * a[i * LD + k];
+                }
+            }
+        } else {
+            if (tid == 0) e[i] = a[i * LD + l];
+        }
+        if (tid == 0) d[i] = h;
+        __syncthreads();
+    }
+    if (tid == 0) { d[0] = 0.0; e[0] = 0.0; }
+    __syncthreads();
+    // ---- accumulate the transformations: a becomes the orthogonal matrix Q
+    for (int i = 0; i < D; ++i) {
+        const int l = i - 1;
+        if (d[i] != 0.0) {
+            // g_j = sum_k a[i][k] a[k][j]; kept in cs[] (free until the QL phase)
+            for (int j = tid; j <= l; j += blockDim.x) {
+                double g = 0.0;
+                for (int k = 0; k <= l; ++k) g += a[i * LD + k] * a[k * LD + j];
+                cs[j] = g;
+            }
+            __syncthreads();
+            for (int k = warp; k <= l; k += NW) {
+                const double aki = a[k * LD + i];
+                for (int j = lane; j <= l; j += 32) a[k * LD + j] -= cs[j] * aki;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { d[i] = a[i * LD + i]; a[i * LD + i] = 1.0; }
+        for (int j = tid; j <= l; j += blockDim.x) { a[j * LD + i] = 0.0; a[i * LD + j] = 0.0; }
+        __syncthreads();
+    }
+
+    // ---- tql2: implicit-shift QL on (d, e); thread 0 runs the rotation recurrence of one iteration and
+    // leaves the (c, s) sequence in shared memory, then every thread applies it to its row of Q.
+    if (tid == 0) {
+        for (int i = 1; i < D; ++i) e[i - 1] = e[i];
+        e[D - 1] = 0.0;
+        sh_flag = 0;
+    }
+    __syncthreads();
+    int total_iter = 0;
+    for (int l = 0; l < D; ++l) {
+        for (int iter = 0;; ++iter) {
+            if (tid == 0) {
+                int m = l;
+                for (; m < D - 1; ++m) {
+                    const double dd = fabs(d[m]) + fabs(d[m + 1]);
+                    if (fabs(e[m]) <= 1.1102230246251565e-16 * dd) break;
+                }
+                int cnt = 0;
+                if (m != l && iter < kQlMaxIter) {
+                    double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                    double r = sqrt(g * g + 1.0);
+                    g = d[m] - d[l] + e[l] / (g + copysign(r, g));
+                    double sn = 1.0, c = 1.0, p = 0.0;
+                    int i = m - 1;
+                    bool under = false;
+                    for (; i >= l; --i) {
+                        double f = sn * e[i];
+                        const double b = c * e[i];
+                        r = sqrt(f * f + g * g);
+                        e[i + 1] = r;
+                        if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; under = true; break; }
+                        const double rinv = 1.0 / r;
+                        sn = f * rinv;
+                        c = g * rinv;
+                        g = d[i + 1] - p;
+                        r = (d[i] - g) * sn + 2.0 * c * b;
+                        p = sn * r;
+                        d[i + 1] = g + p;
+                        g = c * r - b;
+                        cs[2 * cnt] = c; cs[2 * cnt + 1] = sn;      // rotation of columns (i, i+1)
+                        ++cnt;
+                    }
+                    if (!under) { d[l] -= p; e[l] = g; e[m] = 0.0; }
+                } else if (m != l) {
+                    sh_flag = 1;       // iteration cap: give up on this eigenvalue (status NoConverge)
+                    m = l;
+                }
+                sh_m = m; sh_cnt = cnt;
+            }
+            __syncthreads();
+            const int m = sh_m, cnt = sh_cnt;
+            if (m == l) break;
+            ++total_iter;
+            // apply: rotation t acts on columns (i, i+1), i = m-1-t
+            for (int k = tid; k < D; k += blockDim.x) {
+                double* row = a + k * LD;
+                double f = row[m];
+                for (int t = 0; t < cnt; ++t) {
+                    const int i = m - 1 - t;
+                    const double c = cs[2 * t], sn = cs[2 * t + 1];
+                    const double zi = row[i];
+                    row[i + 1] = sn * zi + c * f;
+                    f = c * zi - sn * f;
+                }
+                row[m - cnt] = f;
+            }
+            __syncthreads();
+        }
+    }
+    if (tid < DP) lam_g[(long long)s * DP + tid] = (tid < D) ? d[tid] : 0.0;
+    if (tid == 0) {
+        status_g[s] = sh_flag ? kStatusNoConverge : kStatusOk;
+        sweeps_g[s] = total_iter;
+    }
+    for (int idx = tid; idx < DP * DP; idx += blockDim.x) {
+        const int b = idx / DP, j = idx % DP;
+        Pout[idx] = (b < D && j < D) ? dinv[b] * a[b * LD + j] : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------- K2b
+// Fragment-ordered tables for the LOO passes from (lam, P): Pf (FP64 DMMA B operand of y = xc . P),
+// Wf (FP64 DMMA A operand of r = W^T z), log det G_alpha, beta, the closed-form sum_k r_k, and for the
+// screening pass the TF32 hi/lo splits Ws (W) and Ps (P) in mma.m16n8k8 fragment order.
+template <int NT>
+__global__ void __launch_bounds__(512)
+    tables_kernel(const int* __restrict__ n_g, const double* __restrict__ alphas, int A, int NT2, int NT16,
+                  int D, int model, const double* __restrict__ P_g, const double* __restrict__ lam_g,
+                  const double* __restrict__ slogT_g, double* __restrict__ Pf_g, double* __restrict__ Wf_g,
+                  double* __restrict__ logdet_g, double* __restrict__ beta_g, float* __restrict__ Ws_g,
+                  float* __restrict__ betaf_g, double* __restrict__ rsum_g, float* __restrict__ Ps_g) {
+    constexpr int DP = 8 * NT;
+    __shared__ double lam[DP];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int n = n_g[s];
+    const int AP = NT2 * 8, AP16 = NT16 * 16;
+    const double* P = P_g + (long long)s * DP * DP;
+    double* Pfout = Pf_g + (long long)s * (DP / 4) * NT * 32;
+    double* Wfout = Wf_g + (long long)s * (DP / 4) * NT2 * 32;
+    const long long ws_half = (long long)NT16 * NT * 32 * 4;      // floats per (column, hi|lo) table
+    float* Wsout = Ws_g ? Ws_g + (long long)s * 2 * ws_half : nullptr;
+    if (n < 2) {
+        for (int i = tid; i < (DP / 4) * NT * 32; i += blockDim.x) Pfout[i] = 0.0;
+        if (model == 0) {
+            for (int i = tid; i < (DP / 4) * NT2 * 32; i += blockDim.x) Wfout[i] = 0.0;
+            for (int i = tid; i < AP; i += blockDim.x) {
+                logdet_g[(long long)s * AP + i] = 0.0;
+                beta_g[(long long)s * AP + i] = 0.0;
+                rsum_g[(long long)s * AP + i] = 0.0;
+            }
+        }
+        return;                         // the screening and exact passes skip columns with n < 2
+    }
+    if (tid < DP) lam[tid] = lam_g[(long long)s * DP + tid];
+    __syncthreads();
+    // Pf[ks][nt][lane] = P[b = 4 ks + lane%4][j = 8 nt + lane/4]
     for (int idx = tid; idx < (DP / 4) * NT * 32; idx += blockDim.x) {
         const int lane = idx & 31, nt = (idx >> 5) % NT, ks = (idx >> 5) / NT;
         const int b = 4 * ks + (lane & 3), j = 8 * nt + (lane >> 2);
-        Pfout[idx] = (b < D && j < D) ? dinv[b] * Vm[b * LD + j] : 0.0;
+        Pfout[idx] = P[b * DP + j];
+    }
+    // Ps[hl][ks][nt][lane] = float2{ P[b0][j], P[b0+4][j] }, b0 = 8 ks + lane%4, j = 8 nt + lane/4
+    if (Ps_g) {
+        float* Psout = Ps_g + (long long)s * 2 * NT * NT * 32 * 2;
+        for (int idx = tid; idx < NT * NT * 32 * 2; idx += blockDim.x) {
+            const int e = idx & 1, lane = (idx >> 1) & 31, nt = (idx >> 6) % NT, ks = (idx >> 6) / NT;
+            const int b = 8 * ks + (lane & 3) + 4 * e, j = 8 * nt + (lane >> 2);
+            const double pv = P[b * DP + j];
+            const float hi = to_tf32((float)pv);
+            Psout[idx] = hi;
+            Psout[NT * NT * 32 * 2 + idx] = to_tf32((float)(pv - (double)hi));
+        }
     }
     if (model != 0) return;  // empirical model: no alpha search
 
     // ---- LOO tables.  beta_i = (1-alpha_i)/(n-1);  den_ji = n beta_i lam_j + alpha_i
     const double dn = (double)n;
+    const double sumlogT = slogT_g[s];
     for (int i = tid; i < AP; i += blockDim.x) {
-        double ld = 0.0, be = 0.0;
+        double ld = 0.0, be = 0.0, rs = 0.0;
         if (i < A) {
             const double al = alphas[i];
             be = (1.0 - al) / (dn - 1.0);
             ld = sumlogT;
-            for (int j = 0; j < D; ++j) ld += log(dn * be * lam[j] + al);
+            for (int j = 0; j < D; ++j) {
+                const double den = dn * be * lam[j] + al;
+                ld += log(den);
+                rs += lam[j] / den;          // sum_k r_k(alpha) = (n-1) sum_j lam_j / den_j  (exact identity)
+            }
+            rs *= (dn - 1.0);
         }
         logdet_g[(long long)s * AP + i] = ld;
         beta_g[(long long)s * AP + i] = be;
+        rsum_g[(long long)s * AP + i] = rs;
+    }
+    // Ws[hl][at][ks][lane] = float4{ W[j0][i0], W[j0][i0+8], W[j0+1][i0], W[j0+1][i0+8] },
+    //   i0 = 16 at + lane/4, j0 = 8 ks + 2 (lane%4)   (same j permutation as Wf: GEMM1 accumulators feed GEMM2)
+    if (Wsout) {
+        for (int i = tid; i < AP16; i += blockDim.x) {
+            float bf = 0.f;
+            if (i < A) bf = (float)((1.0 - alphas[i]) / (dn - 1.0));
+            betaf_g[(long long)s * AP16 + i] = bf;
+        }
+        for (int idx = tid; idx < NT16 * NT * 32 * 4; idx += blockDim.x) {
+            const int e = idx & 3, lane = (idx >> 2) & 31, ks = (idx >> 7) % NT, at = (idx >> 7) / NT;
+            const int i = 16 * at + (lane >> 2) + ((e & 1) ? 8 : 0);
+            const int j = 8 * ks + 2 * (lane & 3) + ((e & 2) ? 1 : 0);
+            double w = 0.0;
+            if (j < D && i < A) {
+                const double al = alphas[i];
+                const double be = (1.0 - al) / (dn - 1.0);
+                w = 1.0 / (dn * be * lam[j] + al);
+            }
+            const float hi = to_tf32((float)w);
+            const float lo = to_tf32((float)(w - (double)hi));
+            Wsout[idx] = hi;
+            Wsout[ws_half + idx] = lo;
+        }
     }
     // Wf[ks2][at][lane] = W[j = 8 (ks2/2) + 2 (lane%4) + ks2%2][i = 8 at + lane/4]
     // (the j permutation lets the y^2 accumulator registers of GEMM1 feed GEMM2 without any shuffle)
@@ -227,7 +548,8 @@ __global__ void __launch_bounds__(256)
                     const double* __restrict__ mu_g, const double* __restrict__ abscf, int model,
                     int reflectance, double scale, double* __restrict__ nll_g, int* __restrict__ mindex_g,
                     double* __restrict__ w_g, double* __restrict__ wT_g, double* __restrict__ c0_g,
-                    int* __restrict__ status_g) {
+                    int* __restrict__ status_g, const int* __restrict__ sel_index,
+                    const unsigned long long* __restrict__ tile_mask) {
     extern __shared__ double sm[];
     double* nll = sm;           // [AP]
     double* tvec = nll + AP;    // [DP]
@@ -257,31 +579,48 @@ __global__ void __launch_bounds__(256)
 
     if (tid == 0) singular = 0;
     if (model == 0) {
+        // screened run (K3a/K3b): sel >= 0 index decided by the screen, -1 all inf, -2 exact values of the
+        // tiles in `tmask` decide; alphas outside the mask keep the screened nll (never the minimum).
+        const bool screened = sel_index != nullptr;
+        const int sel = screened ? sel_index[s] : -2;
+        const unsigned long long tmask = screened ? tile_mask[s] : ~0ull;
         const double const_term = (double)D * log(2.0 * M_PI);
         for (int i = tid; i < A; i += blockDim.x) {
-            double fs = 0.0;
-            for (int c = 0; c < nchunk; ++c) fs += fpart[((long long)s * nchunk + c) * AP + i];
-            const double ld = logdet_g[(long long)s * AP + i];
             double v;
-            if (ld < -744.4400719213812) v = inf;             // det underflows to 0 -> alpha skipped (:112-113)
-            else if (ld > 709.782712893384) v = inf;          // det overflows -> log(inf)
-            else v = 0.5 * (const_term + ld) + fs / (2.0 * (double)n);
+            if (!screened || ((tmask >> ((i >> 3) & 63)) & 1ull)) {
+                double fs = 0.0;
+                for (int c = 0; c < nchunk; ++c) fs += fpart[((long long)s * nchunk + c) * AP + i];
+                const double ld = logdet_g[(long long)s * AP + i];
+                if (ld < -744.4400719213812) v = inf;             // det underflows to 0 -> alpha skipped (:112-113)
+                else if (ld > 709.782712893384) v = inf;          // det overflows -> log(inf)
+                else v = 0.5 * (const_term + ld) + fs / (2.0 * (double)n);
+                nll_g[(long long)s * A + i] = v;
+            } else {
+                v = nll_g[(long long)s * A + i];
+            }
             nll[i] = v;
-            nll_g[(long long)s * A + i] = v;
         }
         __syncthreads();
         if (tid == 0) {
-            // numpy argmin: the first NaN wins, otherwise the first minimum (:121)
-            int best = 0;
-            bool have_nan = false;
-            for (int i = 0; i < A; ++i) {
-                const double v = nll[i];
-                if (v != v) { best = i; have_nan = true; break; }
-                if (v < nll[best]) best = i;
-            }
+            int best;
             double al;
-            if (have_nan || nll[best] != inf) al = alphas[best];
-            else { best = -1; al = 0.0; status_g[s] |= kStatusAllInf; }
+            if (screened && sel >= 0) {
+                best = sel; al = alphas[best];
+            } else if (screened && sel == -1) {
+                best = -1; al = 0.0; status_g[s] |= kStatusAllInf;
+            } else {
+                // numpy argmin: the first NaN wins, otherwise the first minimum (:121)
+                best = -1;
+                bool have_nan = false;
+                for (int i = 0; i < A; ++i) {
+                    if (screened && !((tmask >> ((i >> 3) & 63)) & 1ull)) continue;
+                    const double v = nll[i];
+                    if (v != v) { best = i; have_nan = true; break; }
+                    if (best < 0 || v < nll[best]) best = i;
+                }
+                if (best >= 0 && (have_nan || nll[best] != inf)) al = alphas[best];
+                else { best = -1; al = 0.0; status_g[s] |= kStatusAllInf; }
+            }
             mindex_g[s] = best;
             alpha_sel = al;
         }
@@ -338,22 +677,42 @@ __global__ void __launch_bounds__(256)
 
 // ---------------------------------------------------------------------------------------- launchers
 template <int NT>
-static void launch_eigen_t(const Dims& d, const double* gram_part, int nchunk, const int* n,
-                           const double* alphas, int model, double* P, double* Pf, double* Wf, double* lam,
-                           double* logdet, double* beta, int* status, int* sweeps, cudaStream_t st) {
+static void launch_eigen_t(const Dims& d, const double* gram_part, int nchunk, const int* n, double* P,
+                           double* lam, double* slogT, int* status, int* sweeps, int method, cudaStream_t st) {
     constexpr int DP = 8 * NT, LD = DP + 1;
-    const size_t smem = (size_t)(2 * DP * LD + 2 * DP + 2 * (DP / 2 + 1)) * sizeof(double);
-    cudaFuncSetAttribute(eigen_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    eigen_kernel<NT><<<d.S, 512, smem, st>>>(gram_part, nchunk, n, alphas, d.A, d.NT2, d.D, model, P, Pf, Wf,
-                                             lam, logdet, beta, status, sweeps);
+    if (method == 1) {
+        const size_t smem = (size_t)(2 * DP * LD + 2 * DP + 2 * (DP / 2 + 1)) * sizeof(double);
+        cudaFuncSetAttribute(eigen_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        eigen_kernel<NT><<<d.S, 512, smem, st>>>(gram_part, nchunk, n, d.D, P, lam, slogT, status, sweeps);
+    } else {
+        const size_t smem = (size_t)(DP * LD + 5 * DP + 8) * sizeof(double);
+        cudaFuncSetAttribute(eigen_ql_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        eigen_ql_kernel<NT><<<d.S, kQlThreads, smem, st>>>(gram_part, nchunk, n, d.D, P, lam, slogT, status, sweeps);
+    }
 }
 
-void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, const double* alphas,
-                  int model, double* P, double* Pf, double* Wf, double* lam, double* logdet, double* beta,
-                  int* status, int* sweeps, cudaStream_t st) {
+// method: 0 = Householder + implicit QL (default), 1 = cyclic Jacobi (cross-check)
+void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, double* P, double* lam,
+                  double* slogT, int* status, int* sweeps, int method, cudaStream_t st) {
     switch (d.NT) {
 #define CMF_CASE(k) \
-    case k: launch_eigen_t<k>(d, gram_part, nchunk, n, alphas, model, P, Pf, Wf, lam, logdet, beta, status, sweeps, st); break;
+    case k: launch_eigen_t<k>(d, gram_part, nchunk, n, P, lam, slogT, status, sweeps, method, st); break;
+        CMF_CASE(1) CMF_CASE(2) CMF_CASE(3) CMF_CASE(4) CMF_CASE(5) CMF_CASE(6)
+        CMF_CASE(7) CMF_CASE(8) CMF_CASE(9) CMF_CASE(10) CMF_CASE(11) CMF_CASE(12)
+#undef CMF_CASE
+        default: break;
+    }
+}
+
+void launch_tables(const Dims& d, const int* n, const double* alphas, int model, const double* P,
+                   const double* lam, const double* slogT, double* Pf, double* Wf, double* logdet, double* beta,
+                   float* Ws, float* betaf, double* rsum, float* Ps, cudaStream_t st) {
+    switch (d.NT) {
+#define CMF_CASE(k)                                                                                           \
+    case k:                                                                                                   \
+        tables_kernel<k><<<d.S, 512, 0, st>>>(n, alphas, d.A, d.NT2, d.NT16, d.D, model, P, lam, slogT, Pf, Wf, \
+                                              logdet, beta, Ws, betaf, rsum, Ps);                             \
+        break;
         CMF_CASE(1) CMF_CASE(2) CMF_CASE(3) CMF_CASE(4) CMF_CASE(5) CMF_CASE(6)
         CMF_CASE(7) CMF_CASE(8) CMF_CASE(9) CMF_CASE(10) CMF_CASE(11) CMF_CASE(12)
 #undef CMF_CASE
@@ -364,11 +723,12 @@ void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int*
 void launch_finalize(const Dims& d, const double* fpart, int nchunk, const double* logdet, const int* n,
                      const double* alphas, const double* P, const double* lam, const double* mu,
                      const double* abscf, int model, int reflectance, double scale, double* nll, int* mindex,
-                     double* w, double* wT, double* c0, int* status, cudaStream_t st) {
+                     double* w, double* wT, double* c0, int* status, const int* sel_index,
+                     const unsigned long long* tile_mask, cudaStream_t st) {
     const size_t smem = (size_t)(d.AP + 3 * d.DP) * sizeof(double);
     finalize_kernel<<<d.S, 256, smem, st>>>(fpart, nchunk, logdet, n, alphas, d.A, d.AP, d.D, d.DP, d.S, P,
                                             lam, mu, abscf, model, reflectance, scale, nll, mindex, w, wT, c0,
-                                            status);
+                                            status, sel_index, tile_mask);
 }
 
 }  // namespace cmf

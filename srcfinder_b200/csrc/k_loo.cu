@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kLooWarps * 32, 1)
     loo_kernel(const float* __restrict__ xt, const double* __restrict__ mu_g,
                const double* __restrict__ Pf_g, const double* __restrict__ Wf_g,
                const double* __restrict__ beta_g, int L, int NT2, int lines_per_chunk,
-               double* __restrict__ fpart) {
+               double* __restrict__ fpart, const unsigned long long* __restrict__ tile_mask) {
     constexpr int DP = 8 * NT, KS = DP / 4, MT = kLooMT, TL = 8 * MT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int AP = NT2 * 8;
@@ -76,6 +76,9 @@ __global__ void __launch_bounds__(kLooWarps * 32, 1)
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kLooWarps * TL * DP);   // [warps] + 1
 
     const int s = blockIdx.x, chunk = blockIdx.y;
+    // refinement mode: bit t of the mask = "8-alpha tile t holds a candidate" (K3b); 0 = column decided
+    const unsigned long long tmask = tile_mask ? tile_mask[s] : ~0ull;
+    if (tmask == 0ull) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q4 = lane & 3;
     const int c_begin = chunk * lines_per_chunk;
@@ -163,6 +166,7 @@ __global__ void __launch_bounds__(kLooWarps * 32, 1)
         }
         // ---- GEMM2 + epilogue, two alpha tiles at a time for ILP on the tensor pipe
         for (int at = 0; at < NT2; at += 2) {
+            if (tile_mask && !((tmask >> (at & 63)) & 3ull)) continue;
             const bool two = (at + 1 < NT2);
             double c0[MT][2], c1[MT][2];
 #pragma unroll
@@ -208,7 +212,8 @@ __global__ void __launch_bounds__(kLooWarps * 32, 1)
 
 template <int NT>
 static void launch_loo_t(const Dims& d, const float* xt, const double* mu, const double* Pf, const double* Wf,
-                         const double* beta, int nchunk, double* fpart, cudaStream_t st) {
+                         const double* beta, int nchunk, double* fpart, const unsigned long long* tile_mask,
+                         cudaStream_t st) {
     constexpr int DP = 8 * NT, KS = DP / 4, TL = 8 * kLooMT;
     const size_t base = (size_t)(KS * NT * 32 + DP + d.AP + kLooWarps * d.AP) * sizeof(double) +
                         (size_t)kLooWarps * TL * DP * sizeof(float) + (kLooWarps + 1) * sizeof(uint64_t);
@@ -218,17 +223,18 @@ static void launch_loo_t(const Dims& d, const float* xt, const double* mu, const
     dim3 grid(d.S, nchunk);
     if (base + wtab <= 227 * 1024) {
         cudaFuncSetAttribute(loo_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + wtab));
-        loo_kernel<NT, true><<<grid, kLooWarps * 32, base + wtab, st>>>(xt, mu, Pf, Wf, beta, d.L, d.NT2, lpc, fpart);
+        loo_kernel<NT, true><<<grid, kLooWarps * 32, base + wtab, st>>>(xt, mu, Pf, Wf, beta, d.L, d.NT2, lpc, fpart, tile_mask);
     } else {
         cudaFuncSetAttribute(loo_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
-        loo_kernel<NT, false><<<grid, kLooWarps * 32, base, st>>>(xt, mu, Pf, Wf, beta, d.L, d.NT2, lpc, fpart);
+        loo_kernel<NT, false><<<grid, kLooWarps * 32, base, st>>>(xt, mu, Pf, Wf, beta, d.L, d.NT2, lpc, fpart, tile_mask);
     }
 }
 
 void launch_loo(const Dims& d, const float* xt, const double* mu, const double* Pf, const double* Wf,
-                const double* beta, int nchunk, double* fpart, cudaStream_t st) {
+                const double* beta, int nchunk, double* fpart, const unsigned long long* tile_mask,
+                cudaStream_t st) {
     switch (d.NT) {
-#define CMF_CASE(k) case k: launch_loo_t<k>(d, xt, mu, Pf, Wf, beta, nchunk, fpart, st); break;
+#define CMF_CASE(k) case k: launch_loo_t<k>(d, xt, mu, Pf, Wf, beta, nchunk, fpart, tile_mask, st); break;
         CMF_CASE(1) CMF_CASE(2) CMF_CASE(3) CMF_CASE(4) CMF_CASE(5) CMF_CASE(6)
         CMF_CASE(7) CMF_CASE(8) CMF_CASE(9) CMF_CASE(10) CMF_CASE(11) CMF_CASE(12)
 #undef CMF_CASE

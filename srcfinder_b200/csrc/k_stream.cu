@@ -461,7 +461,7 @@ void launch_mean(const Dims& d, const double* colsum_part, const int* colcnt_par
 }
 
 // Plan of the scoring pass: number of statistics partials per column (`nlanes`) and, on the tiled path,
-// the lines each CTA covers.  The tiled grid is sized to one wave of 3 CTAs per SM.
+// the lines each CTA covers.  The tiled grid is sized to one wave of MINB CTAs per SM.
 struct ScoreVariant { int nl, bc, minb; };
 
 static ScoreVariant score_variant() {

@@ -41,7 +41,8 @@ def test_header_symbols_are_exported(lib):
 def test_kernel_table(lib):
     n = lib.cmf_kernel_count()
     names = [lib.cmf_kernel_name(i).decode() for i in range(n)]
-    assert names == ["repack", "mean", "gram", "eigen", "loo", "finalize", "score", "colstats"]
+    assert names == ["repack", "mean", "gram", "eigen", "tables", "screen", "select", "loo", "finalize", "score",
+                     "colstats"]
     assert b"sm_100a" in lib.cmf_version()
 
 

@@ -80,7 +80,10 @@ def test_oracle_seeded(L, S, seed, bad):
     active = [351, 422]
     ab = _abscf(active)
     ref = orc.cmf_cube(cube, ab, active, keep_nll=True)
-    got = cmf_cube(cube, ab, active)
+    got = cmf_cube(cube, ab, active, exact=True)          # every alpha in FP64: nll comparable to the oracle's
+    fast = cmf_cube(cube, ab, active)                     # default path: tensor-core screen + exact refinement
+    assert np.array_equal(fast["alpha_index"], got["alpha_index"])
+    assert np.array_equal(fast["mf"], got["mf"], equal_nan=True)
     tight = L > 200
     _check_against(got, ref["mf"], ref["mask"], ref["alpha_index"], np.where(ref["colstd"] > 0, ref["colstd"], 1.0),
                    tight=tight)
@@ -94,6 +97,57 @@ def test_oracle_seeded(L, S, seed, bad):
         assert np.max(np.abs(got["weights"] - ref["weights"]) / wscale) < 1e-8
         assert np.allclose(got["colstd"], ref["colstd"], rtol=1e-9)
         assert np.all(np.abs(got["colavg"] - ref["colavg"]) < 1e-9 * ref["colstd"])
+
+
+@pytest.mark.parametrize("L,S,seed,bad", [(2000, 24, 61, True), (600, 16, 62, False), (90, 6, 63, True)])
+def test_screening_selects_the_exact_argmin(L, S, seed, bad):
+    """The tensor-core screen (TF32 contraction + FP32 terms) followed by the exact FP64 re-evaluation of the
+    near-minimal alphas must pick the index the all-FP64 search picks, bit for bit the same scores, and its
+    approximate nll must sit within the documented error (tol/2 = 1e-6) of the exact one."""
+    cube = synth.make_cube(L, S, seed=seed, bad_pixels=bad)
+    active = [351, 422]
+    ab = _abscf(active)
+    Lc, B, Sc = cube.shape
+    with ColumnwiseMF(Lc, B, Sc, active, ab) as eng:
+        eng.upload(cube)
+        eng.run(exact=True)
+        ex = eng.results(); ex_nll = eng.nll()
+        eng.run()
+        sc = eng.results(); sc_nll = eng.nll(); ncand = eng.ncand(); tol = eng.screen_tol()
+    assert np.array_equal(ex["alpha_index"], sc["alpha_index"])
+    assert np.array_equal(ex["mf"], sc["mf"], equal_nan=True)
+    fin = np.isfinite(ex_nll) & np.isfinite(sc_nll)
+    assert np.array_equal(np.isfinite(ex_nll), np.isfinite(sc_nll))
+    # the selection is provably the exact argmin while the screening error is below half the margin the
+    # screen used for that column; require a further factor 2 of head-room
+    err = np.where(fin, np.abs(ex_nll - sc_nll), 0.0).max(axis=1)
+    assert np.all(err <= 0.25 * tol), (err / tol).max()
+    assert np.all(ncand >= 1) and np.all(ncand <= 201)
+    ref = orc.cmf_cube(cube, ab, active)
+    assert np.array_equal(ref["alpha_index"], sc["alpha_index"])
+
+
+def test_ql_and_jacobi_eigensolvers_agree(monkeypatch):
+    """The default Householder + QL factorisation against the cyclic Jacobi cross-check: same spectrum to
+    1e-12 of the largest eigenvalue, same alpha indices, scores within 1e-8 sigma."""
+    cube = synth.make_cube(700, 12, seed=71, bad_pixels=True)
+    active = [351, 422]
+    ab = _abscf(active)
+    L, B, S = cube.shape
+    out = {}
+    for method in ("ql", "jacobi"):
+        monkeypatch.setenv("CMF_EIGEN", method)
+        with ColumnwiseMF(L, B, S, active, ab) as eng:
+            eng.upload(cube)
+            eng.run()
+            out[method] = (eng.results(), np.sort(eng.eigvals(), axis=1), eng.status())
+    monkeypatch.delenv("CMF_EIGEN")
+    (rq, lq, sq), (rj, lj, sj) = out["ql"], out["jacobi"]
+    assert np.all(sq == 0) and np.all(sj == 0)
+    assert np.max(np.abs(lq - lj)) < 1e-12 * lj.max()
+    assert np.array_equal(rq["alpha_index"], rj["alpha_index"])
+    err = np.nanmax(np.abs(rq["mf"] - rj["mf"]), axis=0) / rq["colstd"]
+    assert np.max(err) < 1e-8
 
 
 def test_empirical_and_co2_window():

@@ -32,6 +32,19 @@ with ColumnwiseMF(L, 425, S, active, ab) as eng:
         eng.run(timing=True)
         kt = eng.kernel_times()
         print(i, {k: round(v, 3) for k, v in kt.items()}, "total %.3f ms" % sum(kt.values()), flush=True)
+    # screening quality: exact FP64 search vs screened search on the same flightline
+    ai_s, nll_s, ncand = eng.alpha_index(), eng.nll(), eng.ncand()
+    eng.run(timing=True, exact=True)
+    kte = eng.kernel_times()
+    ai_e, nll_e = eng.alpha_index(), eng.nll()
+    fin = np.isfinite(nll_e) & np.isfinite(nll_s)
+    err = np.abs(nll_e - nll_s)
+    d_e, d_s = np.diff(nll_e, axis=1), np.diff(nll_s, axis=1)
+    out["screen"] = {"index_mismatch": int((ai_s != ai_e).sum()), "max_abs_nll_err": float(err[fin].max()),
+                     "max_abs_adjacent_diff_err": float(np.nanmax(np.abs(d_e - d_s))),
+                     "ncand_hist": np.bincount(np.minimum(ncand, 10)).tolist(),
+                     "refined_columns": int((ncand > 1).sum()), "exact_kernel_ms": kte}
+    print("screen", out["screen"], flush=True)
     out["kernel_ms"] = kt
     out["total_ms"] = sum(kt.values())
     out["mpixel_s"] = L * S / (sum(kt.values()) * 1e-3) / 1e6

@@ -19,7 +19,7 @@ with ColumnwiseMF(L, 425, S, active, ab) as eng:
     print(json.dumps({"score_ms": kt["score"], "colstats_ms": kt["colstats"], "sum": float(eng.colstats()[2].sum())}))
 ''' % ROOT
 out = {}
-for v in ["2,8,3", "2,12,2", "4,8,2", "4,6,2", "4,4,3", "2,18,2", "1,12,3", "1,24,3", "2,6,3"]:
+for v in ["2,18,2", "2,12,2", "4,8,2", "2,8,3"]:
     env = dict(os.environ, CMF_SCORE_VARIANT=v)
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
     line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
