@@ -5,8 +5,8 @@ AVIRIS-NG cube).
     python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's NumPy path on host cores
 
-A "step" is one pass of the whole hot path (repack/mask, statistics, eigen, LOO alpha search, weights,
-scoring, column statistics) over one synthetic flightline: BASELINE configs[1], 598 columns x 425 channels
+A "step" is one pass of the whole hot path (repack/mask, statistics, eigen-decomposition, tensor-core screen
+of the LOO alpha search + exact FP64 refinement, weights, scoring, column statistics) over one synthetic flightline: BASELINE configs[1], 598 columns x 425 channels
 x 20 000 lines, active window 351..422.  With N > 1 every rank processes its own flightline (flightline
 sharding, no data-path collective) and the score tiles are gathered to rank 0 over NCCL inside the timed
 region.  One JSON line is printed by rank 0.
@@ -15,8 +15,9 @@ region.  One JSON line is printed by rank 0.
          max over ranks.
 `e2e`    the same metric through the C-ABI host call (cmf_run_host): pinned host cube -> H2D of the
          active window -> all kernels -> D2H of scores, column statistics and alpha indices, every step.
-`roofline`      the dominant kernel (LOO pass, FP64 tensor bound) against the FP64 DMMA.8x8x4 peak
-                measured in this run by cmf_microbench (MEASURED_PEAKS.json has no FP64 figure).
+`roofline`      the dominant kernel (screening pass of the alpha search, TF32 tensor bound) against the dense
+                TF32 peak (half the measured bf16 figure of MEASURED_PEAKS.json); `roofline_fp64` the Gram
+                kernel against the FP64 DMMA rate measured in this run (MEASURED_PEAKS.json has no FP64 figure).
 `roofline_hbm`  the scoring pass against the HBM copy peak of MEASURED_PEAKS.json.
 `cpu_baseline`  the oracle port of the reference (same NumPy/SciPy calls) on the host cores, bounded sample.
 """
@@ -227,6 +228,7 @@ def run_gpu(args):
 
     # FP64 tensor peak for the roofline (rank 0, before the timed region)
     dmma_peak = lib.cmf_microbench(local, 0, 3) if rank == 0 else 0.0
+    mma_peak = lib.cmf_microbench(local, 9, 3) if rank == 0 else 0.0
 
     slab = synth.make_slab_torch(L, S, ACTIVE[0], ACTIVE[1], dev, seed=2 + rank)
     stream = torch.cuda.current_stream()
@@ -277,9 +279,13 @@ def run_gpu(args):
     out = None
     if rank == 0:
         peaks, src = measured_peaks()
-        flops = (2.0 * D * D + 2.0 * D * 201) * L * S          # projection + alpha contraction
-        loo_ms = kt.get("loo", float("nan"))
-        achieved = flops / (loo_ms * 1e-3) / 1e12
+        # dominant kernel: the tensor-core screening pass of the alpha search.  Algorithmic work per pixel
+        # (SURVEY 8(d)): the projection 2 D^2 plus the alpha contraction 2 D A; the kernel executes three
+        # TF32 products per FP64-equivalent product (hi/lo splits), which is not counted as useful work.
+        flops = (2.0 * D * D + 2.0 * D * 201) * L * S
+        screen_ms = kt.get("screen", float("nan"))
+        achieved = flops / (screen_ms * 1e-3) / 1e12
+        tf32_peak = 0.5 * float(peaks.get("bf16_tflops", 1590.0))
         score_bytes = (4.0 * D + 8.0 + 1.0) * L * S            # one read of the slab + f64 score + mask byte
         score_ms = kt.get("score", float("nan"))
         traffic = load_traffic()
@@ -289,17 +295,23 @@ def run_gpu(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world),
             "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
-            "roofline": {"kernel": "loo_kernel", "bound": "tensor", "achieved": achieved, "peak": dmma_peak,
-                         "unit": "TFLOP/s", "frac": achieved / dmma_peak if dmma_peak > 0 else None,
-                         "traffic": traffic.get("loo_kernel"),
-                         "peak_source": "FP64 DMMA.8x8x4 rate measured in this run by cmf_microbench(kind=0); "
-                                        "MEASURED_PEAKS.json holds no FP64 figure (bf16 %s TF/s is not the bound)"
-                                        % peaks.get("bf16_tflops"),
-                         "flops_per_launch": flops},
-            "roofline_hbm": {"kernel": "score_kernel", "bound": "hbm",
+            "roofline": {"kernel": "loo_screen_kernel", "bound": "tensor", "achieved": achieved, "peak": tf32_peak,
+                         "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic.get("loo_screen_kernel"),
+                         "peak_source": "%s: dense TF32 = half of MEASURED_PEAKS.json bf16_tflops (%s); the kernel "
+                                        "issues TF32 through mma.sync (SASS HMMA), whose measured ceiling in this run "
+                                        "is %.0f TFLOP/s, and executes 3 split products per algorithmic product"
+                                        % (src, peaks.get("bf16_tflops"), mma_peak),
+                         "flops_per_launch": flops, "executed_tflops": 3.0 * (2.0 * D * D + 2.0 * D * 208) * L * S
+                         / (screen_ms * 1e-3) / 1e12, "mma_sync_tf32_peak": mma_peak},
+            "roofline_fp64": {"kernel": "gram_kernel", "bound": "tensor", "achieved": D * (D + 8.0) * L * S
+                              / (kt.get("gram", float("nan")) * 1e-3) / 1e12, "peak": dmma_peak, "unit": "TFLOP/s",
+                              "peak_source": "FP64 DMMA.8x8x4 rate measured in this run (cmf_microbench kind 0)",
+                              "note": "lower-triangle 8x8 tiles only: D(D+8) flop per pixel"},
+            "roofline_hbm": {"kernel": "score_tiled_kernel", "bound": "hbm",
                              "achieved": score_bytes / (score_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                              "unit": "GB/s", "frac": score_bytes / (score_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                             "traffic": traffic.get("score_kernel"), "peak_source": src + " (MEASURED_PEAKS.json hbm_gbs)",
+                             "traffic": traffic.get("score_tiled_kernel"),
+                             "peak_source": src + " (MEASURED_PEAKS.json hbm_gbs)",
                              "bytes_per_launch": score_bytes},
             "clocks": clocks.summary(), "gpu_launches": launches,
         }

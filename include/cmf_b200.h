@@ -62,8 +62,11 @@ enum {
     CMF_OUT_SWEEPS = 10,      /* int32  [S]      Jacobi sweeps used */
     CMF_OUT_NCAND = 11,       /* int32  [S]      alphas the screening pass could not separate (1 = decided by the
                                                   screen, > 1 = decided by exact FP64 re-evaluation); screened runs only */
-    CMF_OUT_SCREEN_TOL = 12   /* double [S]      nll margin within which the screen treats alphas as tied; the
+    CMF_OUT_SCREEN_TOL = 12,  /* double [S]      nll margin within which the screen treats alphas as tied; the
                                                   selection is exact while the screening error stays below half of it */
+    CMF_OUT_CLUSTER_ID = 13,  /* int16  [L][S]   _bgmeta band 0 (:327): cluster label, negated when rejected; labelled runs */
+    CMF_OUT_ALPHA_IMAGE = 14, /* int16  [L][S]   _bgmeta band 1 (:365): alpha index of the mode that scored the pixel */
+    CMF_OUT_MODE_LIST = 15    /* int8   [S][32]  the column's mode list (bgulab, :313-332); 127 = past the end */
 };
 
 typedef struct cmf_problem {
@@ -96,6 +99,14 @@ int cmf_upload_bil(cmf_ctx* ctx, const float* host_cube);
 /* Input already on the device: pointer to element (line 0, band band_lo, sample 0); consecutive lines are
  * line_pitch floats apart, consecutive bands band_pitch floats apart (a full BIL cube: B*S and S). */
 int cmf_bind_device_slab(cmf_ctx* ctx, const float* dev_slab, int64_t line_pitch, int32_t band_pitch);
+
+/* Background modes (-k > 1, cmf/robust_mf.py:306-344).  labels[l*S + s] in 0..kmodes-1 is the cluster of pixel
+ * (l, s) (ignored where the pixel is invalid); the reference obtains them from an unseeded MiniBatchKMeans
+ * (:312), here they are an input so that the path is deterministic.  reject_min > 0 is -r with bgminsamp =
+ * reject_min (:200, :316-324).  Everything downstream -- cluster counts, rejection, the mode list, the
+ * per-mode fits with n = the column's valid count (:355-356), the overwrite order (:339-386), the inlier
+ * statistics (:388-391) -- runs on the device.  labels == NULL returns to the unimodal path.  Host pointer. */
+int cmf_set_labels(cmf_ctx* ctx, const int32_t* labels, int kmodes, int reject_min);
 
 /* ---- compute: the whole column loop (:297-392) for every column, no host round trip ---- */
 enum {

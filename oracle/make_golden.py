@@ -48,6 +48,13 @@ CASES = [
     # note: ``--rgb_bands []`` cannot be pinned -- the reference crashes at :395 (rgb_bands[0])
     dict(name="degenerate_300x4", L=300, S=4, seed=17, kw={}, flags=["-m"], lib="ang_ch4_unit.txt",
          few_valid={1: 50, 2: 1, 3: 74}),
+    # background modes: the reference's MiniBatchKMeans draws from numpy's global RandomState, so seeding it
+    # before the (unmodified) script runs makes the partition reproducible; the labels the script used are
+    # recovered from _bgmeta band 0.  A block of 40 bright lines forms a cluster below bgminsamp = 85.
+    dict(name="modes_k3r_900x4", L=900, S=4, seed=21, kw=dict(bad_pixels=True), flags=["-k", "3", "-r", "-m"],
+         lib="ang_ch4_unit.txt", np_seed=5, bright_lines=(100, 140)),
+    dict(name="modes_k2_600x3", L=600, S=3, seed=22, kw={}, flags=["-k", "2", "-m"], lib="ang_ch4_unit.txt",
+         np_seed=7),
 ]
 
 
@@ -69,6 +76,10 @@ def run_case(case, tmp):
         cube[::3, 360, case["sparse_column"]] = np.nan
     for c, nvalid in case.get("few_valid", {}).items():   # columns with n < D, n == 1, n ~ D+2
         cube[nvalid:, 355, c] = np.nan
+    if "bright_lines" in case:           # a small, spectrally distinct population (rejected with -r)
+        l0, l1 = case["bright_lines"]
+        ok = cube[l0:l1] > 0
+        cube[l0:l1] = np.where(ok, cube[l0:l1] * 2.5, cube[l0:l1])
     libname = case["lib"]
     refl = "-R" in case["flags"]
     lo, hi = (5, 420) if (refl and "ch4" in libname) else ((351, 422) if "ch4" in libname else (309, 391))
@@ -86,6 +97,8 @@ def run_case(case, tmp):
         "wavelength": ["%.2f" % w for w in synth.load_ch4_library()[:, 1]],
         "fwhm": ["5.0"] * cube.shape[1], "smoothing factors": ["0"] * cube.shape[1],
         "bad pixel map": "none"})
+    if "np_seed" in case:
+        np.random.seed(case["np_seed"])
     stdout = ref_shim.run_reference_cli(case["flags"] + [inp, libpath, out])
     hdr = ref_shim.parse_envi_header(out + ".hdr")
     nb = int(hdr["bands"]) if "-m" not in case["flags"] else (4 if rgb else 1)

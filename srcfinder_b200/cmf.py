@@ -100,6 +100,29 @@ class ColumnwiseMF(object):
         bp = self.S if band_pitch is None else int(band_pitch)
         self._check(self._lib.cmf_bind_device_slab(self._ctx, C.c_void_p(int(dev_ptr)), lp, bp))
 
+    def set_labels(self, labels_ls, kmodes=None, reject_min=0):
+        """Background-mode labels (L, S) int in 0..kmodes-1 (cmf/robust_mf.py:312-313); ``reject_min`` > 0 is
+        ``-r`` with bgminsamp = reject_min.  ``None`` returns to the unimodal path."""
+        if labels_ls is None:
+            self._check(self._lib.cmf_set_labels(self._ctx, C.c_void_p(None), 1, 0))
+            self._labelled = False
+            return
+        lab = np.ascontiguousarray(labels_ls, dtype=np.int32)
+        if lab.shape != (self.L, self.S):
+            raise CmfError("labels shape %r != %r" % (lab.shape, (self.L, self.S)))
+        k = int(lab.max()) + 1 if kmodes is None else int(kmodes)
+        self._check(self._lib.cmf_set_labels(self._ctx, C.c_void_p(lab.ctypes.data), k, int(reject_min)))
+        self._labelled = True
+
+    def cluster_id(self):
+        return self._get(_lib.OUT_CLUSTER_ID, np.int16, (self.L, self.S))
+
+    def alpha_image(self):
+        return self._get(_lib.OUT_ALPHA_IMAGE, np.int16, (self.L, self.S))
+
+    def mode_list(self):
+        return self._get(_lib.OUT_MODE_LIST, np.int8, (self.S, 32))
+
     # ------------------------------------------------------------------ compute
     def run(self, timing=False, sync=True, exact=False):
         """All kernels on the context stream.  ``exact=True`` evaluates every alpha of the leave-one-out
@@ -189,14 +212,18 @@ class ColumnwiseMF(object):
 
 
 def cmf_cube(cube_lbs, abscf, active, model="looshrinkage", reflectance=False, alphas=None,
-             nodata=-9999.0, device=0, exact=False):
+             nodata=-9999.0, device=0, exact=False, labels=None, reject_min=0):
     """One-shot convenience: same inputs/outputs as the oracle's ``cmf_cube`` (for parity tests)."""
     L, B, S = cube_lbs.shape
     with ColumnwiseMF(L, B, S, active, abscf, model=model, reflectance=reflectance, alphas=alphas,
                       nodata=nodata, device=device) as eng:
         eng.upload(cube_lbs)
+        if labels is not None:
+            eng.set_labels(labels, reject_min=reject_min)
         eng.run(exact=exact)
         res = eng.results()
+        if labels is not None:
+            res["cluster_id"], res["alpha_image"] = eng.cluster_id(), eng.alpha_image()
         if model == "looshrinkage":
             res["nll"] = eng.nll()
         return res

@@ -57,6 +57,15 @@ struct cmf_ctx {
     int eigen_method = 0;         // 0 Householder + QL, 1 cyclic Jacobi (CMF_EIGEN=jacobi, cross-checks)
     int *sel_index = nullptr, *ncand = nullptr;
     unsigned long long* tile_mask = nullptr;
+    // background modes (-k > 1, -r): labels are an input, everything derived from them lives on the device
+    bool have_labels = false;
+    int kmodes = 1, reject_min = 0;
+    int32_t* labels_d = nullptr;
+    int8_t* entries = nullptr;
+    uint32_t* rejmask = nullptr;
+    int *nentries = nullptr, *nuse = nullptr;
+    uint8_t *sel = nullptr, *inlier = nullptr;
+    int16_t *cluster_img = nullptr, *alpha_img = nullptr;
     bool can_screen = false;
     double screen_tol = 2.0e-5;   // relative to the screened part of nll; measured error is <= 2.5e-6
     int nchunk_screen = 1;
@@ -101,8 +110,59 @@ cudaError_t dalloc(cmf_ctx* c, T** p, size_t count) {
     return e;
 }
 
-// Launch the eight kernels on the context stream.  When `blocks_ready` is given, the repack pass runs
-// block by block, each block waiting on the event that marks its upload as complete.
+// One pass of the per-column model fit and scoring on the context stream: statistics of the selected
+// pixels (sel == NULL: every valid pixel), factorisation, alpha search, weights, scores.  `mark` records
+// the per-kernel timing events of an unlabelled run.
+template <class Mark>
+void fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* sel, const int* nloo, Mark mark) {
+    const Dims& d = ctx->d;
+    cudaStream_t st = ctx->stream;
+    launch_mean(d, ctx->colsum_part, ctx->colcnt_part, ctx->nsplit, ctx->mu, ctx->n, st);
+    mark(2);
+    launch_gram(d, ctx->xt, ctx->mu, ctx->nchunk_gram, ctx->gram_part, st);
+    mark(3);
+    const bool loo = ctx->model == CMF_MODEL_LOOSHRINKAGE;
+    const bool screen = loo && ctx->can_screen && !exact;
+    launch_eigen(d, ctx->gram_part, ctx->nchunk_gram, ctx->n, ctx->P, ctx->lam, ctx->slogT, ctx->status,
+                 ctx->sweeps, ctx->eigen_method, st);
+    mark(4);
+    launch_tables(d, ctx->n, nloo, ctx->alphas_d, ctx->model, ctx->P, ctx->lam, ctx->slogT, ctx->Pf, ctx->Wf,
+                  ctx->logdet, ctx->beta, screen ? ctx->Ws : nullptr, ctx->betaf, ctx->rsum,
+                  screen ? ctx->Ps : nullptr, st);
+    mark(5);
+    ctx->launches += 4;
+    if (screen) {
+        launch_screen(d, ctx->xt, ctx->mu, ctx->Pf, ctx->Ps, ctx->Ws, ctx->betaf, ctx->n, ctx->nchunk_screen,
+                      ctx->fscreen, st);
+        ++ctx->launches;
+    }
+    mark(6);
+    if (screen) {
+        launch_select(d, ctx->fscreen, ctx->nchunk_screen, ctx->logdet, ctx->rsum, ctx->n, nloo, ctx->screen_tol,
+                      ctx->nll, ctx->sel_index, ctx->tile_mask, ctx->ncand, ctx->tol_col, st);
+        ++ctx->launches;
+    }
+    mark(7);
+    if (loo) {
+        launch_loo(d, ctx->xt, ctx->mu, ctx->Pf, ctx->Wf, ctx->beta, ctx->nchunk_loo, ctx->fpart,
+                   screen ? ctx->tile_mask : nullptr, st);
+        ++ctx->launches;
+    }
+    mark(8);
+    launch_finalize(d, ctx->fpart, ctx->nchunk_loo, ctx->logdet, ctx->n, ctx->alphas_d, ctx->P, ctx->lam,
+                    ctx->mu, ctx->abscf_d, ctx->model, ctx->reflectance, ctx->scale, ctx->nll, ctx->mindex,
+                    ctx->w, ctx->wT, ctx->c0, ctx->status, screen ? ctx->sel_index : nullptr,
+                    screen ? ctx->tile_mask : nullptr, nloo, st);
+    mark(9);
+    launch_score(d, ctx->slab, ctx->mask, ctx->wT, ctx->c0, ctx->status, ctx->nodata, ctx->mf, ctx->stat_part,
+                 ctx->nlanes, ctx->score_lpc, sel, ctx->mindex, ctx->alpha_img, st);
+    mark(10);
+    ctx->launches += 2;
+    ctx->screened = screen;
+}
+
+// Launch the whole column loop on the context stream.  When `blocks_ready` is given, the first repack pass
+// runs block by block, each block waiting on the event that marks its upload as complete.
 int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t>* blocks_ready,
             int lines_per_block) {
     const Dims& d = ctx->d;
@@ -119,68 +179,53 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
         evs = ctx->ev_sets[ctx->timed_runs].data();
         ++ctx->timed_runs;
     }
-    auto mark = [&](int i) { if (timing) cudaEventRecord(evs[i], st); };
+    const bool modes = ctx->have_labels;
+    auto mark = [&](int i) { if (timing && !modes) cudaEventRecord(evs[i], st); };
+    auto no_mark = [](int) {};
+    if (timing && modes) cudaEventRecord(evs[0], st);
     mark(0);
+    // ---- pass over every valid pixel: validity mask, column-major copy, column sums
     if (blocks_ready) {
         int line = 0;
         for (size_t b = 0; b < blocks_ready->size(); ++b) {
             const int lim = std::min(d.L, line + lines_per_block);
             cudaStreamWaitEvent(st, (*blocks_ready)[b], 0);
             launch_repack(d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, line,
-                          lim, st);
+                          lim, nullptr, 1, st);
             ++ctx->launches;
             line = lim;
         }
     } else {
         launch_repack(d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, 0, d.L,
-                      st);
+                      nullptr, 1, st);
         ++ctx->launches;
     }
     mark(1);
-    launch_mean(d, ctx->colsum_part, ctx->colcnt_part, ctx->nsplit, ctx->mu, ctx->n, st);
-    mark(2);
-    launch_gram(d, ctx->xt, ctx->mu, ctx->nchunk_gram, ctx->gram_part, st);
-    mark(3);
-    const bool loo = ctx->model == CMF_MODEL_LOOSHRINKAGE;
-    const bool screen = loo && ctx->can_screen && !exact;
-    launch_eigen(d, ctx->gram_part, ctx->nchunk_gram, ctx->n, ctx->P, ctx->lam, ctx->slogT, ctx->status,
-                 ctx->sweeps, ctx->eigen_method, st);
-    mark(4);
-    launch_tables(d, ctx->n, ctx->alphas_d, ctx->model, ctx->P, ctx->lam, ctx->slogT, ctx->Pf, ctx->Wf,
-                  ctx->logdet, ctx->beta, screen ? ctx->Ws : nullptr, ctx->betaf, ctx->rsum,
-                  screen ? ctx->Ps : nullptr, st);
-    mark(5);
-    ctx->launches += 4;
-    if (screen) {
-        launch_screen(d, ctx->xt, ctx->mu, ctx->Pf, ctx->Ps, ctx->Ws, ctx->betaf, ctx->n, ctx->nchunk_screen,
-                      ctx->fscreen, st);
+    if (!modes) {
+        fit_and_score(ctx, exact, nullptr, nullptr, mark);
+        launch_colstats(d, ctx->stat_part, ctx->nlanes, ctx->n, ctx->nodata, ctx->colstats, st);
         ++ctx->launches;
-    }
-    mark(6);
-    if (screen) {
-        launch_select(d, ctx->fscreen, ctx->nchunk_screen, ctx->logdet, ctx->rsum, ctx->n, ctx->screen_tol,
-                      ctx->nll, ctx->sel_index, ctx->tile_mask, ctx->ncand, ctx->tol_col, st);
+        mark(11);
+    } else {
+        // ---- background modes (cmf/robust_mf.py:306-344): one fit-and-score pass per mode-list entry
+        const size_t LS = (size_t)d.L * d.S;
+        launch_mean(d, ctx->colsum_part, ctx->colcnt_part, ctx->nsplit, ctx->mu, ctx->nuse, st);   // nuse (:302)
+        launch_modes(d, ctx->labels_d, ctx->mask, ctx->reject_min, ctx->entries, ctx->rejmask, ctx->nentries, st);
+        launch_fill_f64(ctx->mf, (long long)LS, ctx->nodata, st);
+        CK(cudaMemsetAsync(ctx->alpha_img, 0, LS * sizeof(int16_t), st));
+        ctx->launches += 3;
+        for (int t = 0; t < ctx->kmodes; ++t) {
+            launch_members(d, ctx->labels_d, ctx->mask, t, ctx->entries, ctx->rejmask, ctx->sel,
+                           t == 0 ? ctx->cluster_img : nullptr, ctx->inlier, st);
+            launch_repack(d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, 0, d.L,
+                          ctx->sel, 0, st);
+            ctx->launches += 2;
+            fit_and_score(ctx, exact, ctx->sel, ctx->nuse, no_mark);
+        }
+        launch_colstats_modes(d, ctx->mf, ctx->inlier, ctx->nuse, ctx->nodata, ctx->colstats, st);
         ++ctx->launches;
+        if (timing) for (int i = 1; i <= K_COUNT; ++i) cudaEventRecord(evs[i], st);
     }
-    mark(7);
-    if (loo) {
-        launch_loo(d, ctx->xt, ctx->mu, ctx->Pf, ctx->Wf, ctx->beta, ctx->nchunk_loo, ctx->fpart,
-                   screen ? ctx->tile_mask : nullptr, st);
-        ++ctx->launches;
-    }
-    mark(8);
-    launch_finalize(d, ctx->fpart, ctx->nchunk_loo, ctx->logdet, ctx->n, ctx->alphas_d, ctx->P, ctx->lam,
-                    ctx->mu, ctx->abscf_d, ctx->model, ctx->reflectance, ctx->scale, ctx->nll, ctx->mindex,
-                    ctx->w, ctx->wT, ctx->c0, ctx->status, screen ? ctx->sel_index : nullptr,
-                    screen ? ctx->tile_mask : nullptr, st);
-    mark(9);
-    launch_score(d, ctx->slab, ctx->mask, ctx->wT, ctx->c0, ctx->status, ctx->nodata, ctx->mf, ctx->stat_part,
-                 ctx->nlanes, ctx->score_lpc, st);
-    mark(10);
-    launch_colstats(d, ctx->stat_part, ctx->nlanes, ctx->n, ctx->nodata, ctx->colstats, st);
-    mark(11);
-    ctx->launches += 3;
-    ctx->screened = screen;
     ctx->timed = timing;
     CK(cudaGetLastError());
     return CMF_OK;
@@ -220,6 +265,9 @@ OutDesc out_desc(const cmf_ctx* c, int what) {
         case CMF_OUT_SWEEPS: return {c->sweeps, (size_t)d.S * sizeof(int)};
         case CMF_OUT_NCAND: return {c->ncand, (size_t)d.S * sizeof(int)};
         case CMF_OUT_SCREEN_TOL: return {c->tol_col, (size_t)d.S * sizeof(double)};
+        case CMF_OUT_CLUSTER_ID: return {c->cluster_img, c->have_labels ? LS * sizeof(int16_t) : 0};
+        case CMF_OUT_ALPHA_IMAGE: return {c->alpha_img, c->have_labels ? LS * sizeof(int16_t) : 0};
+        case CMF_OUT_MODE_LIST: return {c->entries, (size_t)d.S * kMaxLabels};
         default: return {nullptr, 0};
     }
 }
@@ -298,6 +346,9 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
 
     CK(cudaStreamSynchronize(ctx->stream));
     free_buffers(ctx);
+    ctx->have_labels = false;
+    ctx->labels_d = nullptr; ctx->sel = nullptr; ctx->inlier = nullptr; ctx->cluster_img = nullptr;
+    ctx->alpha_img = nullptr;
     Dims& d = ctx->d;
     d.L = p->lines; d.S = p->samples; d.D = D; d.NT = NT; d.DP = 8 * NT;
     d.A = loo ? p->num_alphas : 1;
@@ -358,6 +409,10 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     A_(dalloc(ctx, &ctx->tile_mask, (size_t)d.S));
     A_(dalloc(ctx, &ctx->tol_col, (size_t)d.S));
     A_(dalloc(ctx, &ctx->slogT, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->nuse, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->nentries, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->rejmask, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->entries, (size_t)d.S * kMaxLabels));
     if (ctx->can_screen) {
         A_(dalloc(ctx, &ctx->Ws, (size_t)d.S * 2 * d.NT16 * d.NT * 32 * 4));
         A_(dalloc(ctx, &ctx->fscreen, (size_t)d.S * ctx->nchunk_screen * d.AP16));
@@ -407,6 +462,35 @@ int cmf_bind_device_slab(cmf_ctx* ctx, const float* dev_slab, int64_t line_pitch
     d.vec2 = (d.S % 2 == 0) && (line_pitch % 2 == 0) && (band_pitch % 2 == 0) &&
              ((reinterpret_cast<uintptr_t>(dev_slab) & 7) == 0);
     ctx->have_input = true;
+    return CMF_OK;
+}
+
+int cmf_set_labels(cmf_ctx* ctx, const int32_t* labels, int kmodes, int reject_min) {
+    if (!ctx) return CMF_E_ARG;
+    if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_set_labels before cmf_set_problem");
+    CK(cudaSetDevice(ctx->device));
+    if (labels == nullptr) { ctx->have_labels = false; return CMF_OK; }
+    if (kmodes < 1 || kmodes > kMaxLabels) return fail(ctx, CMF_E_ARG, "kmodes must be 1..32");
+    const Dims& d = ctx->d;
+    const size_t LS = (size_t)d.L * d.S;
+    for (size_t i = 0; i < LS; ++i)
+        if (labels[i] < 0 || labels[i] >= kmodes)
+            return fail(ctx, CMF_E_ARG, "labels must lie in 0..kmodes-1 (rejection is derived on the device)");
+    if (!ctx->labels_d) {
+        cudaError_t e = cudaSuccess;
+        auto A_ = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+        A_(dalloc(ctx, &ctx->labels_d, LS));
+        A_(dalloc(ctx, &ctx->sel, LS));
+        A_(dalloc(ctx, &ctx->inlier, LS));
+        A_(dalloc(ctx, &ctx->cluster_img, LS));
+        A_(dalloc(ctx, &ctx->alpha_img, LS));
+        if (e != cudaSuccess) return fail(ctx, CMF_E_NOMEM, std::string("label buffers: ") + cudaGetErrorString(e));
+    }
+    CK(cudaMemcpyAsync(ctx->labels_d, labels, LS * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->kmodes = kmodes;
+    ctx->reject_min = reject_min > 0 ? reject_min : 0;
+    ctx->have_labels = true;
     return CMF_OK;
 }
 

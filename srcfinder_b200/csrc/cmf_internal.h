@@ -11,7 +11,9 @@ constexpr int kRepackCG = 16;       // columns per repack tile
 constexpr int kRepackLT = 8;        // lines per repack tile
 constexpr int kGramTL = 16;         // lines per Gram tile (4 k-steps of DMMA.8x8x4)
 constexpr int kLooMT = 2;           // 8-pixel m-tiles per LOO pass
-constexpr int kScoreLines = 8;      // lines per thread in the scoring pass
+constexpr int kScoreLines = 8;      // lines per thread in the scoring pass (scalar kernel)
+constexpr int kMaxLabels = 32;      // background-mode labels are 0 .. kMaxLabels-1
+constexpr int kModeNone = 127;      // mode-list slot past the end of a column's list
 
 // column status bits (per cross-track column)
 enum : int {
@@ -35,7 +37,8 @@ struct Dims {
 inline int ntri(int nt) { return nt * (nt + 1) / 2; }
 
 void launch_repack(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,
-                   int* colcnt_part, int lines_per_split, int line_base, int line_limit, cudaStream_t st);
+                   int* colcnt_part, int lines_per_split, int line_base, int line_limit, const uint8_t* sel,
+                   int write_mask, cudaStream_t st);
 int repack_lines_per_split(const Dims& d, int nsplit);
 void launch_mean(const Dims& d, const double* colsum_part, const int* colcnt_part, int nsplit,
                  double* mu, int* n, cudaStream_t st);
@@ -43,7 +46,7 @@ void launch_gram(const Dims& d, const float* xt, const double* mu, int nchunk, d
                  cudaStream_t st);
 void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, double* P, double* lam,
                   double* slogT, int* status, int* sweeps, int method, cudaStream_t st);
-void launch_tables(const Dims& d, const int* n, const double* alphas, int model, const double* P,
+void launch_tables(const Dims& d, const int* n, const int* nloo, const double* alphas, int model, const double* P,
                    const double* lam, const double* slogT, double* Pf, double* Wf, double* logdet, double* beta,
                    float* Ws, float* betaf, double* rsum, float* Ps, cudaStream_t st);
 void launch_loo(const Dims& d, const float* xt, const double* mu, const double* Pf, const double* Wf,
@@ -54,16 +57,24 @@ void launch_screen(const Dims& d, const float* xt, const double* mu, const doubl
                    cudaStream_t st);
 size_t screen_smem_bytes(const Dims& d);
 void launch_select(const Dims& d, const double* fscreen, int nchunk, const double* logdet, const double* rsum,
-                   const int* n, double tol, double* nll, int* sel_index, unsigned long long* tile_mask,
-                   int* ncand, double* tol_out, cudaStream_t st);
+                   const int* n, const int* nloo, double tol, double* nll, int* sel_index,
+                   unsigned long long* tile_mask, int* ncand, double* tol_out, cudaStream_t st);
 void launch_finalize(const Dims& d, const double* fpart, int nchunk, const double* logdet, const int* n,
                      const double* alphas, const double* P, const double* lam, const double* mu,
                      const double* abscf, int model, int reflectance, double scale, double* nll,
                      int* mindex, double* w, double* wT, double* c0, int* status, const int* sel_index,
-                     const unsigned long long* tile_mask, cudaStream_t st);
+                     const unsigned long long* tile_mask, const int* nloo, cudaStream_t st);
 void launch_score(const Dims& d, const float* slab, const uint8_t* mask, const double* wT, const double* c0,
                   const int* status, double nodata, double* mf, double* stat_part, int nlanes,
-                  int lines_per_cta, cudaStream_t st);
+                  int lines_per_cta, const uint8_t* sel, const int* mindex, int16_t* alpha_img, cudaStream_t st);
+void launch_modes(const Dims& d, const int32_t* labels, const uint8_t* mask, int reject_min, int8_t* entries,
+                  uint32_t* rejmask, int* nentries, cudaStream_t st);
+void launch_members(const Dims& d, const int32_t* labels, const uint8_t* mask, int t, const int8_t* entries,
+                    const uint32_t* rejmask, uint8_t* sel, int16_t* cluster_img, uint8_t* inlier,
+                    cudaStream_t st);
+void launch_fill_f64(double* p, long long n, double v, cudaStream_t st);
+void launch_colstats_modes(const Dims& d, const double* mf, const uint8_t* inlier, const int* nuse,
+                           double nodata, double* colstats, cudaStream_t st);
 int score_plan(const Dims& d, int sm_count, int* lines_per_cta);
 void launch_colstats(const Dims& d, const double* stat_part, int nlanes, const int* n, double nodata,
                      double* colstats, cudaStream_t st);

@@ -431,7 +431,8 @@ __global__ void __launch_bounds__(kQlThreads)
 // screening pass the TF32 hi/lo splits Ws (W) and Ps (P) in mma.m16n8k8 fragment order.
 template <int NT>
 __global__ void __launch_bounds__(512)
-    tables_kernel(const int* __restrict__ n_g, const double* __restrict__ alphas, int A, int NT2, int NT16,
+    tables_kernel(const int* __restrict__ n_g, const int* __restrict__ nloo_g, const double* __restrict__ alphas,
+                  int A, int NT2, int NT16,
                   int D, int model, const double* __restrict__ P_g, const double* __restrict__ lam_g,
                   const double* __restrict__ slogT_g, double* __restrict__ Pf_g, double* __restrict__ Wf_g,
                   double* __restrict__ logdet_g, double* __restrict__ beta_g, float* __restrict__ Ws_g,
@@ -480,8 +481,10 @@ __global__ void __launch_bounds__(512)
     }
     if (model != 0) return;  // empirical model: no alpha search
 
-    // ---- LOO tables.  beta_i = (1-alpha_i)/(n-1);  den_ji = n beta_i lam_j + alpha_i
-    const double dn = (double)n;
+    // ---- LOO tables.  beta_i = (1-alpha_i)/(n-1);  den_ji = n beta_i lam_j + alpha_i, where n is the count the
+    // reference hands to looshrinkage: the column's valid pixels even when a cluster subset is fitted
+    // (cmf/robust_mf.py:355-356), while the covariance itself is over the m = n_g pixels of the subset
+    const double dn = (double)(nloo_g ? nloo_g[s] : n);
     const double sumlogT = slogT_g[s];
     for (int i = tid; i < AP; i += blockDim.x) {
         double ld = 0.0, be = 0.0, rs = 0.0;
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(512)
                 ld += log(den);
                 rs += lam[j] / den;          // sum_k r_k(alpha) = (n-1) sum_j lam_j / den_j  (exact identity)
             }
-            rs *= (dn - 1.0);
+            rs *= ((double)n - 1.0);
         }
         logdet_g[(long long)s * AP + i] = ld;
         beta_g[(long long)s * AP + i] = be;
@@ -549,7 +552,7 @@ __global__ void __launch_bounds__(256)
                     int reflectance, double scale, double* __restrict__ nll_g, int* __restrict__ mindex_g,
                     double* __restrict__ w_g, double* __restrict__ wT_g, double* __restrict__ c0_g,
                     int* __restrict__ status_g, const int* __restrict__ sel_index,
-                    const unsigned long long* __restrict__ tile_mask) {
+                    const unsigned long long* __restrict__ tile_mask, const int* __restrict__ nloo_g) {
     extern __shared__ double sm[];
     double* nll = sm;           // [AP]
     double* tvec = nll + AP;    // [DP]
@@ -561,6 +564,10 @@ __global__ void __launch_bounds__(256)
     const int s = blockIdx.x, tid = threadIdx.x;
     const int n = n_g[s];
     const int Sp = (S + 1) & ~1;
+    // background-mode pass without members in this column (or past the end of its mode list): the column
+    // keeps what earlier passes produced; the scoring pass has no member to write either
+    if (nloo_g != nullptr && n == 0) return;
+    const double nl = (double)(nloo_g ? nloo_g[s] : n);
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
 
@@ -593,7 +600,7 @@ __global__ void __launch_bounds__(256)
                 const double ld = logdet_g[(long long)s * AP + i];
                 if (ld < -744.4400719213812) v = inf;             // det underflows to 0 -> alpha skipped (:112-113)
                 else if (ld > 709.782712893384) v = inf;          // det overflows -> log(inf)
-                else v = 0.5 * (const_term + ld) + fs / (2.0 * (double)n);
+                else v = 0.5 * (const_term + ld) + fs / (2.0 * nl);
                 nll_g[(long long)s * A + i] = v;
             } else {
                 v = nll_g[(long long)s * A + i];
@@ -704,13 +711,13 @@ void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int*
     }
 }
 
-void launch_tables(const Dims& d, const int* n, const double* alphas, int model, const double* P,
+void launch_tables(const Dims& d, const int* n, const int* nloo, const double* alphas, int model, const double* P,
                    const double* lam, const double* slogT, double* Pf, double* Wf, double* logdet, double* beta,
                    float* Ws, float* betaf, double* rsum, float* Ps, cudaStream_t st) {
     switch (d.NT) {
 #define CMF_CASE(k)                                                                                           \
     case k:                                                                                                   \
-        tables_kernel<k><<<d.S, 512, 0, st>>>(n, alphas, d.A, d.NT2, d.NT16, d.D, model, P, lam, slogT, Pf, Wf, \
+        tables_kernel<k><<<d.S, 512, 0, st>>>(n, nloo, alphas, d.A, d.NT2, d.NT16, d.D, model, P, lam, slogT, Pf, Wf, \
                                               logdet, beta, Ws, betaf, rsum, Ps);                             \
         break;
         CMF_CASE(1) CMF_CASE(2) CMF_CASE(3) CMF_CASE(4) CMF_CASE(5) CMF_CASE(6)
@@ -724,11 +731,11 @@ void launch_finalize(const Dims& d, const double* fpart, int nchunk, const doubl
                      const double* alphas, const double* P, const double* lam, const double* mu,
                      const double* abscf, int model, int reflectance, double scale, double* nll, int* mindex,
                      double* w, double* wT, double* c0, int* status, const int* sel_index,
-                     const unsigned long long* tile_mask, cudaStream_t st) {
+                     const unsigned long long* tile_mask, const int* nloo, cudaStream_t st) {
     const size_t smem = (size_t)(d.AP + 3 * d.DP) * sizeof(double);
     finalize_kernel<<<d.S, 256, smem, st>>>(fpart, nchunk, logdet, n, alphas, d.A, d.AP, d.D, d.DP, d.S, P,
                                             lam, mu, abscf, model, reflectance, scale, nll, mindex, w, wT, c0,
-                                            status, sel_index, tile_mask);
+                                            status, sel_index, tile_mask, nloo);
 }
 
 }  // namespace cmf

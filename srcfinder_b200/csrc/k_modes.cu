@@ -1,0 +1,149 @@
+// Background modes (-k > 1 / -r): per-column mode lists from per-pixel labels, the per-pass member
+// masks, and the final column statistics over the inlier pixels.
+//
+// Reference (cmf/robust_mf.py:306-344, 388-391): labels come from a k-means on the column's leading
+// principal components; clusters with fewer than bgminsamp samples are relabelled -l when -r is given
+// (label 0 can never flip: -0 == 0, :323-324); if every cluster was flagged the flips are undone
+// (:330-332).  The modes are then fitted in the order of the (partly negated) unique-label list: an entry
+// ki >= 0 fits and scores the pixels of that cluster, an entry ki < 0 fits and scores ALL inlier pixels
+// (labels >= 0) with the pooled model (:341), later entries overwriting earlier ones (:386).
+// Here the labels are an input (the reference's MiniBatchKMeans is unseeded, :312); everything that
+// follows from them is computed on the device in this file, one pass of the pipeline per list entry.
+#include "cmf_common.cuh"
+#include "cmf_internal.h"
+
+namespace cmf {
+
+// One CTA per column: histogram of the labels of the valid pixels, rejection flags, entry list.
+//   entries[s][t]  t-th entry of the mode list (kModeNone when the list is shorter)
+//   rejmask[s]     bit l set = cluster l is rejected (its pixels are outliers)
+__global__ void __launch_bounds__(256)
+    modes_kernel(const int32_t* __restrict__ labels, const uint8_t* __restrict__ mask, int L, int S,
+                 int reject_min, int8_t* __restrict__ entries, uint32_t* __restrict__ rejmask,
+                 int* __restrict__ nentries) {
+    __shared__ int cnt[kMaxLabels];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    if (tid < kMaxLabels) cnt[tid] = 0;
+    __syncthreads();
+    int local[4] = {0, 0, 0, 0};          // most columns use a handful of labels: count 0..3 in registers
+    for (int l = tid; l < L; l += blockDim.x) {
+        const long long o = (long long)l * S + s;
+        if (mask[o]) {
+            const int lab = labels[o];
+            if (lab >= 0 && lab < 4) ++local[lab];
+            else if (lab >= 4 && lab < kMaxLabels) atomicAdd(&cnt[lab], 1);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (local[k]) atomicAdd(&cnt[k], local[k]);
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t rej = 0u;
+        int ne = 0, nneg = 0;
+        int8_t list[kMaxLabels];
+        for (int l = 0; l < kMaxLabels; ++l) {
+            if (cnt[l] == 0) continue;
+            const bool flag = reject_min > 0 && cnt[l] < reject_min && l != 0;   // -0 == 0 never flips
+            if (flag) { rej |= 1u << l; ++nneg; }
+            list[ne++] = (int8_t)(flag ? -l : l);
+        }
+        if (ne > 0 && nneg == ne) {            // all clusters rejected: proceed without rejection (:330-332)
+            rej = 0u;
+            for (int t = 0; t < ne; ++t) list[t] = (int8_t)(-list[t]);
+        }
+        for (int t = 0; t < kMaxLabels; ++t) entries[(long long)s * kMaxLabels + t] = (t < ne) ? list[t] : kModeNone;
+        rejmask[s] = rej;
+        nentries[s] = ne;
+    }
+}
+
+// Member mask of pass t, cluster-id image (first pass only) and inlier mask.
+__global__ void __launch_bounds__(256)
+    members_kernel(const int32_t* __restrict__ labels, const uint8_t* __restrict__ mask, long long LS, int S,
+                   int t, const int8_t* __restrict__ entries, const uint32_t* __restrict__ rejmask,
+                   uint8_t* __restrict__ sel, int16_t* __restrict__ cluster_img, uint8_t* __restrict__ inlier) {
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= LS) return;
+    const int s = (int)(o % S);
+    const bool valid = mask[o] != 0;
+    const int lab = labels[o];
+    const bool known = valid && lab >= 0 && lab < kMaxLabels;
+    const uint32_t rej = rejmask[s];
+    const bool rejected = known && ((rej >> lab) & 1u);
+    const int e = entries[(long long)s * kMaxLabels + t];
+    bool member = false;
+    if (known && e != kModeNone) member = (e >= 0) ? (lab == e && !rejected) : !rejected;
+    sel[o] = member ? 1 : 0;
+    if (cluster_img != nullptr) {
+        cluster_img[o] = known ? (int16_t)(rejected ? -lab : lab) : (int16_t)0;
+        inlier[o] = (known && !rejected) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_f64_kernel(double* __restrict__ p, long long n, double v) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// colnum = nuse, colavg / colstd (ddof = 0) of the final scores of the inlier pixels (:388-391).
+// One CTA per column, fixed reduction order.
+__global__ void __launch_bounds__(256)
+    colstats_modes_kernel(const double* __restrict__ mf, const uint8_t* __restrict__ inlier,
+                          const int* __restrict__ nuse, int L, int S, double nodata,
+                          double* __restrict__ colstats) {
+    __shared__ double ssum[256], ssq[256];
+    __shared__ int scnt[256];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    double sum = 0.0, sq = 0.0;
+    int cnt = 0;
+    for (int l = tid; l < L; l += blockDim.x) {
+        const long long o = (long long)l * S + s;
+        if (inlier[o]) { const double v = mf[o]; sum += v; sq += v * v; ++cnt; }
+    }
+    ssum[tid] = sum; ssq[tid] = sq; scnt[tid] = cnt;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (tid < w) { ssum[tid] += ssum[tid + w]; ssq[tid] += ssq[tid + w]; scnt[tid] += scnt[tid + w]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int n = nuse[s];
+        if (n == 0) {
+            colstats[s] = nodata; colstats[S + s] = nodata; colstats[2 * S + s] = nodata;
+        } else {
+            // np.mean / np.std of an empty selection are NaN; otherwise population statistics
+            const double c = (double)scnt[0];
+            const double mean = ssum[0] / c;
+            double var = ssq[0] / c - mean * mean;
+            if (var < 0.0) var = 0.0;
+            colstats[s] = (double)n;
+            colstats[S + s] = mean;
+            colstats[2 * S + s] = sqrt(var);
+        }
+    }
+}
+
+void launch_modes(const Dims& d, const int32_t* labels, const uint8_t* mask, int reject_min, int8_t* entries,
+                  uint32_t* rejmask, int* nentries, cudaStream_t st) {
+    modes_kernel<<<d.S, 256, 0, st>>>(labels, mask, d.L, d.S, reject_min, entries, rejmask, nentries);
+}
+
+void launch_members(const Dims& d, const int32_t* labels, const uint8_t* mask, int t, const int8_t* entries,
+                    const uint32_t* rejmask, uint8_t* sel, int16_t* cluster_img, uint8_t* inlier,
+                    cudaStream_t st) {
+    const long long LS = (long long)d.L * d.S;
+    members_kernel<<<(unsigned)((LS + 255) / 256), 256, 0, st>>>(labels, mask, LS, d.S, t, entries, rejmask, sel,
+                                                                 cluster_img, inlier);
+}
+
+void launch_fill_f64(double* p, long long n, double v, cudaStream_t st) {
+    fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+}
+
+void launch_colstats_modes(const Dims& d, const double* mf, const uint8_t* inlier, const int* nuse,
+                           double nodata, double* colstats, cudaStream_t st) {
+    colstats_modes_kernel<<<d.S, 256, 0, st>>>(mf, inlier, nuse, d.L, d.S, nodata, colstats);
+}
+
+}  // namespace cmf

@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(kScreenWarps * 32, 1)
 // One warp per column: approximate nll, its minimum, the candidate set and the refinement tile mask.
 __global__ void __launch_bounds__(128)
     select_kernel(const double* __restrict__ fscreen, int nchunk, const double* __restrict__ logdet_g,
-                  const double* __restrict__ rsum_g, const int* __restrict__ n_g, int A, int AP, int AP16,
+                  const double* __restrict__ rsum_g, const int* __restrict__ n_g,
+                  const int* __restrict__ nloo_g, int A, int AP, int AP16,
                   int D, int S, double tol, double* __restrict__ nll_g, int* __restrict__ sel_index,
                   unsigned long long* __restrict__ tile_mask, int* __restrict__ ncand_g,
                   double* __restrict__ tol_g) {
@@ -332,6 +333,7 @@ __global__ void __launch_bounds__(128)
     }
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const double const_term = (double)D * log(2.0 * M_PI);
+    const double nl = (double)(nloo_g ? nloo_g[s] : n);       // the n of looshrinkage (:355-356)
     double vmin = inf, hmax = 0.0;
     bool bad = false;                          // a non-finite sum: the exact pass decides everything
     for (int i = lane; i < A; i += 32) {
@@ -341,9 +343,9 @@ __global__ void __launch_bounds__(128)
         double v;
         if (ld < -744.4400719213812 || ld > 709.782712893384) v = inf;   // det under/overflow (:112-113)
         else {
-            v = 0.5 * (const_term + ld) + (rsum_g[(long long)s * AP + i] + fs) / (2.0 * (double)n);
+            v = 0.5 * (const_term + ld) + (rsum_g[(long long)s * AP + i] + fs) / (2.0 * nl);
             if (!(fabs(v) < inf)) bad = true;  // NaN or +-inf out of the data
-            hmax = fmax(hmax, fabs(fs) / (2.0 * (double)n));
+            hmax = fmax(hmax, fabs(fs) / (2.0 * nl));
         }
         nll_g[(long long)s * A + i] = v;
         if (v < vmin) vmin = v;
@@ -435,9 +437,9 @@ void launch_screen(const Dims& d, const float* xt, const double* mu, const doubl
 }
 
 void launch_select(const Dims& d, const double* fscreen, int nchunk, const double* logdet, const double* rsum,
-                   const int* n, double tol, double* nll, int* sel_index, unsigned long long* tile_mask,
-                   int* ncand, double* tol_out, cudaStream_t st) {
-    select_kernel<<<(d.S + 3) / 4, 128, 0, st>>>(fscreen, nchunk, logdet, rsum, n, d.A, d.AP, d.AP16, d.D, d.S, tol,
+                   const int* n, const int* nloo, double tol, double* nll, int* sel_index,
+                   unsigned long long* tile_mask, int* ncand, double* tol_out, cudaStream_t st) {
+    select_kernel<<<(d.S + 3) / 4, 128, 0, st>>>(fscreen, nchunk, logdet, rsum, n, nloo, d.A, d.AP, d.AP16, d.D, d.S, tol,
                                                  nll, sel_index, tile_mask, ncand, tol_out);
 }
 

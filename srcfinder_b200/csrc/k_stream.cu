@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ s
                                                      float* __restrict__ xt, uint8_t* __restrict__ mask,
                                                      double* __restrict__ colsum_part,
                                                      int* __restrict__ colcnt_part, int lines_per_split,
-                                                     int line_base, int line_limit, int split_base) {
+                                                     int line_base, int line_limit, int split_base,
+                                                     const uint8_t* __restrict__ sel, int write_mask) {
     constexpr int DP = 8 * NT, CG = kRepackCG, LT = kRepackLT, CGP = CG + 1;
     constexpr int NACC = (DP * CG + 255) / 256;
     extern __shared__ float tile[];  // [LT][DP][CGP]
@@ -125,7 +126,18 @@ __global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ s
             }
         }
         __syncthreads();
-        // ---- phase 2: FP64 column sums over valid pixels (thread <-> fixed (band, column))
+        // validity is a property of the pixel (cmf/robust_mf.py:282); a background-mode pass (sel != NULL)
+        // additionally drops the valid pixels that are not members of the mode being fitted (:341)
+        if (tid < LT * CG) {
+            const int l = tid / CG, c = tid % CG;
+            if (l < nl && s0 + c < S) {
+                const long long o = (long long)(l0 + l) * S + s0 + c;
+                if (write_mask) mask[o] = bad[tid] ? 0 : 1;
+                if (sel != nullptr && sel[o] == 0) bad[tid] = 1;
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: FP64 column sums over the included pixels (thread <-> fixed (band, column))
 #pragma unroll
         for (int k = 0; k < NACC; ++k) {
             const int idx = tid + k * 256;
@@ -141,10 +153,6 @@ __global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ s
             int k = 0;
             for (int l = 0; l < nl; ++l) k += bad[l * CG + tid] ? 0 : 1;
             cnt += k;
-        }
-        if (tid < LT * CG) {
-            const int l = tid / CG, c = tid % CG;
-            if (l < nl && s0 + c < S) mask[(long long)(l0 + l) * S + s0 + c] = bad[tid] ? 0 : 1;
         }
         // ---- phase 3: transposed write, each column's [nl][DP] block is contiguous in xt
         const int per_col = nl * DP;
@@ -197,7 +205,9 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ sl
                                                     const double* __restrict__ c0,
                                                     const int* __restrict__ status, double nodata,
                                                     double* __restrict__ mf, double* __restrict__ stat_part,
-                                                    int nlanes) {
+                                                    int nlanes, const uint8_t* __restrict__ sel,
+                                                    const int* __restrict__ mindex,
+                                                    int16_t* __restrict__ alpha_img) {
     constexpr int NL = kScoreLines;
     const int SC = (S + VEC - 1) / VEC;               // column groups per line
     const int ngroups = (L + NL - 1) / NL;            // line groups
@@ -265,6 +275,15 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ sl
             const int l = l0 + j;
             if (l < L) {
                 const long long o = (long long)l * S + col;
+                if (sel != nullptr) {
+                    // background-mode pass: only the members of this mode are (over)written (:383-386)
+                    if (sel[o]) { mf[o] = zero0 ? 0.0 : a0[j] - cz0; alpha_img[o] = (int16_t)mindex[col]; }
+                    if (has1 && sel[o + 1]) {
+                        mf[o + 1] = zero1 ? 0.0 : a1[j] - cz1;
+                        alpha_img[o + 1] = (int16_t)mindex[col + 1];
+                    }
+                    continue;
+                }
                 const bool ok0 = mask[o] != 0;
                 const double v0 = ok0 ? (zero0 ? 0.0 : a0[j] - cz0) : nodata;
                 if (ok0) { sum0 += v0; sq0 += v0 * v0; }
@@ -283,6 +302,7 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ sl
             }
         }
     }
+    if (sel != nullptr) return;
     double* sp = stat_part + ((long long)lane_id * S + col) * 2;
     sp[0] = sum0; sp[1] = sq0;
     if (has1) { sp[2] = sum1; sp[3] = sq1; }
@@ -302,7 +322,9 @@ __global__ void __launch_bounds__(256, MINB)
     score_tiled_kernel(const float* __restrict__ slab, long long line_pitch, int band_pitch, int L, int S,
                        int D, const uint8_t* __restrict__ mask, const double* __restrict__ wT, int Sp,
                        const double* __restrict__ c0, const int* __restrict__ status, double nodata,
-                       double* __restrict__ mf, double* __restrict__ stat_part, int lines_per_cta) {
+                       double* __restrict__ mf, double* __restrict__ stat_part, int lines_per_cta,
+                       const uint8_t* __restrict__ sel, const int* __restrict__ mindex,
+                       int16_t* __restrict__ alpha_img) {
     constexpr int CP = kScoreTile / 2;
     extern __shared__ double2 w_s[];   // [D][CP]
     const int tid = threadIdx.x;
@@ -362,17 +384,26 @@ __global__ void __launch_bounds__(256, MINB)
             for (int j = 0; j < NL; ++j) {
                 if (l0 + j < l_end) {
                     const long long o = (long long)(l0 + j) * S + col;
-                    const uchar2 ok = *reinterpret_cast<const uchar2*>(mask + o);
-                    const double r0 = ok.x ? (zero0 ? 0.0 : a0[j] - cz0) : nodata;
-                    const double r1 = ok.y ? (zero1 ? 0.0 : a1[j] - cz1) : nodata;
-                    if (ok.x) { sum0 += r0; sq0 += r0 * r0; }
-                    if (ok.y) { sum1 += r1; sq1 += r1 * r1; }
-                    *reinterpret_cast<double2*>(mf + o) = make_double2(r0, r1);
+                    if (sel == nullptr) {
+                        const uchar2 ok = *reinterpret_cast<const uchar2*>(mask + o);
+                        const double r0 = ok.x ? (zero0 ? 0.0 : a0[j] - cz0) : nodata;
+                        const double r1 = ok.y ? (zero1 ? 0.0 : a1[j] - cz1) : nodata;
+                        if (ok.x) { sum0 += r0; sq0 += r0 * r0; }
+                        if (ok.y) { sum1 += r1; sq1 += r1 * r1; }
+                        *reinterpret_cast<double2*>(mf + o) = make_double2(r0, r1);
+                    } else {
+                        // background-mode pass: only the members of this mode are (over)written (:383-386)
+                        const uchar2 ok = *reinterpret_cast<const uchar2*>(sel + o);
+                        if (ok.x) { mf[o] = zero0 ? 0.0 : a0[j] - cz0; alpha_img[o] = (int16_t)mindex[col]; }
+                        if (ok.y) { mf[o + 1] = zero1 ? 0.0 : a1[j] - cz1; alpha_img[o + 1] = (int16_t)mindex[col + 1]; }
+                    }
                 }
             }
         }
-        double* sp = stat_part + ((long long)part * S + col) * 2;
-        sp[0] = sum0; sp[1] = sq0; sp[2] = sum1; sp[3] = sq1;
+        if (sel == nullptr) {
+            double* sp = stat_part + ((long long)part * S + col) * 2;
+            sp[0] = sum0; sp[1] = sq0; sp[2] = sum1; sp[3] = sq1;
+        }
     }
 }
 
@@ -412,7 +443,7 @@ int repack_nsplit(const Dims& d) {
 template <int NT>
 static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,
                             int* colcnt_part, int lps, int line_base, int line_limit, int split_base,
-                            cudaStream_t st) {
+                            const uint8_t* sel, int write_mask, cudaStream_t st) {
     constexpr int DP = 8 * NT;
     const size_t smem = (size_t)kRepackLT * DP * (kRepackCG + 1) * sizeof(float);
     cudaFuncSetAttribute(repack_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -421,7 +452,7 @@ static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t
     dim3 grid((d.S + kRepackCG - 1) / kRepackCG, nblk);
     repack_kernel<NT><<<grid, 256, smem, st>>>(slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, d.vec2, xt,
                                                mask, colsum_part, colcnt_part, lps, line_base, line_limit,
-                                               split_base);
+                                               split_base, sel, write_mask);
 }
 
 #define CMF_NT_SWITCH(nt, CALL)                                                      \
@@ -449,10 +480,11 @@ int repack_lines_per_split(const Dims& d, int nsplit) {
 // Repack lines [line_base, line_limit); line_base must be a multiple of lines-per-split so that the
 // partial-sum slots (split_base + i) are the same whether the cube is processed whole or in blocks.
 void launch_repack(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,
-                   int* colcnt_part, int lps, int line_base, int line_limit, cudaStream_t st) {
+                   int* colcnt_part, int lps, int line_base, int line_limit, const uint8_t* sel, int write_mask,
+                   cudaStream_t st) {
     const int split_base = line_base / lps;
     CMF_NT_SWITCH(d.NT, (launch_repack_t<NTc>(d, slab, xt, mask, colsum_part, colcnt_part, lps, line_base,
-                                              line_limit, split_base, st)));
+                                              line_limit, split_base, sel, write_mask, st)));
 }
 
 void launch_mean(const Dims& d, const double* colsum_part, const int* colcnt_part, int nsplit, double* mu,
@@ -498,35 +530,37 @@ int score_plan(const Dims& d, int sm_count, int* lines_per_cta) {
 template <int NL, int BC, int MINB>
 static void launch_score_tiled(const Dims& d, const float* slab, const uint8_t* mask, const double* wT,
                                const double* c0, const int* status, double nodata, double* mf,
-                               double* stat_part, int nlanes, int lines_per_cta, cudaStream_t st) {
+                               double* stat_part, int nlanes, int lines_per_cta, const uint8_t* sel,
+                               const int* mindex, int16_t* alpha_img, cudaStream_t st) {
     const int Sp = (d.S + 1) & ~1;
     const size_t smem = (size_t)d.D * (kScoreTile / 2) * sizeof(double2);
     cudaFuncSetAttribute(score_tiled_kernel<NL, BC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((d.S + kScoreTile - 1) / kScoreTile, nlanes / kScoreSlots);
     score_tiled_kernel<NL, BC, MINB><<<grid, 256, smem, st>>>(slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, mask,
                                                               wT, Sp, c0, status, nodata, mf, stat_part,
-                                                              lines_per_cta);
+                                                              lines_per_cta, sel, mindex, alpha_img);
 }
 
 void launch_score(const Dims& d, const float* slab, const uint8_t* mask, const double* wT, const double* c0,
                   const int* status, double nodata, double* mf, double* stat_part, int nlanes,
-                  int lines_per_cta, cudaStream_t st) {
+                  int lines_per_cta, const uint8_t* sel, const int* mindex, int16_t* alpha_img,
+                  cudaStream_t st) {
     const int Sp = (d.S + 1) & ~1;
     if (d.vec2) {
         const ScoreVariant v = score_variant();
 #define CMF_SV(NL, BC, MB)                                                                              \
     if (v.nl == NL && v.bc == BC && v.minb == MB)                                                       \
         return launch_score_tiled<NL, BC, MB>(d, slab, mask, wT, c0, status, nodata, mf, stat_part, nlanes, \
-                                              lines_per_cta, st);
+                                              lines_per_cta, sel, mindex, alpha_img, st);
         CMF_SV(2, 18, 2) CMF_SV(2, 12, 2) CMF_SV(4, 8, 2) CMF_SV(2, 8, 3)
 #undef CMF_SV
         return launch_score_tiled<2, 18, 2>(d, slab, mask, wT, c0, status, nodata, mf, stat_part, nlanes,
-                                            lines_per_cta, st);
+                                            lines_per_cta, sel, mindex, alpha_img, st);
     }
     const long long total = (long long)d.S * nlanes;
     score_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
         slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, mask, wT, Sp, c0, status, nodata, mf, stat_part,
-        nlanes);
+        nlanes, sel, mindex, alpha_img);
 }
 
 void launch_colstats(const Dims& d, const double* stat_part, int nlanes, const int* n, double nodata,

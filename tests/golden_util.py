@@ -27,4 +27,10 @@ def load_case(name):
     flags = case["flags"]
     case["model"] = flags[flags.index("-M") + 1] if "-M" in flags else "looshrinkage"
     case["reflectance"] = "-R" in flags
+    case["kmodes"] = int(flags[flags.index("-k") + 1]) if "-k" in flags else 1
+    case["reject_min"] = int((case["active"][1] - case["active"][0]) * 1.2) if "-r" in flags else 0   # :200
+    if case["kmodes"] > 1:
+        # the partition the (seeded) reference run used: _bgmeta band 0 holds l, or -l for rejected clusters
+        # (:321-327); rejected pixels keep nodata in the score band, so validity needs both bands
+        case["labels"] = np.abs(case["bgmeta"][..., 0]).astype(np.int32)
     return case

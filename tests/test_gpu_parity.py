@@ -49,8 +49,25 @@ def _check_against(got, ref_mf, ref_mask, ref_aidx, ref_colstd, tight=True):
 def test_golden_reference_run(name):
     case = load_case(name)
     cube, active = case["cube"], case["active"]
-    got = cmf_cube(cube, _abscf(active), active, model=case["model"], reflectance=case["reflectance"])
+    got = cmf_cube(cube, _abscf(active), active, model=case["model"], reflectance=case["reflectance"],
+                   labels=case.get("labels"), reject_min=case["reject_min"])
     ref_mf = case["product"][..., -1]
+    if case["kmodes"] > 1:
+        # background modes: the partition of the seeded reference run is the input; rejected clusters keep
+        # nodata (:341, :386), _bgmeta holds the signed cluster label and the per-pixel alpha index (:327, :365)
+        bg = case["bgmeta"]
+        rejected = bg[..., 0] < 0
+        assert np.array_equal(got["mf"] == -9999.0, ref_mf == -9999.0)
+        assert np.array_equal(got["mask"] & ~rejected, ref_mf != -9999.0)
+        assert np.array_equal(got["cluster_id"][got["mask"]], bg[..., 0][got["mask"]])
+        assert np.array_equal(got["alpha_image"][got["mask"]], bg[..., 1][got["mask"]])
+        for c in range(cube.shape[2]):
+            ok = ref_mf[:, c] != -9999.0
+            err = np.max(np.abs(got["mf"][ok, c] - ref_mf[ok, c])) / np.std(ref_mf[ok, c])
+            assert err <= TIGHT_SIGMA, "column %d: %.3g sigma" % (c, err)
+            assert got["colstd"][c] == pytest.approx(case["stdout_std"][c], rel=2e-6)
+            assert got["colnum"][c] == got["mask"][:, c].sum()
+        return
     ref_mask = ref_mf != -9999.0
     aidx = None
     if "bgmeta" in case:
@@ -70,6 +87,40 @@ def test_golden_reference_run(name):
             assert got["colnum"][c] == nvalid[c]
         elif nvalid[c] == 0:
             assert got["colnum"][c] == -9999.0 and got["colavg"][c] == -9999.0
+
+
+@pytest.mark.parametrize("S,k,reject", [(8, 3, True), (5, 4, False)])
+def test_background_modes_against_oracle(S, k, reject):
+    """Seeded labels (brightness terciles plus a small block) through the oracle and the CUDA path: per-mode
+    fits with n = column count (:355-356), pooled re-fit for rejected clusters, overwrite order, inlier stats."""
+    L = 1500
+    cube = synth.make_cube(L, S, seed=81, bad_pixels=True)
+    active = [351, 422]
+    ab = _abscf(active)
+    bright = cube[:, 380, :]
+    labels = np.zeros((L, S), dtype=np.int32)
+    for c in range(S):
+        qs = np.quantile(bright[:, c][np.isfinite(bright[:, c])], np.linspace(0, 1, k + 1)[1:-1])
+        labels[:, c] = np.searchsorted(qs, bright[:, c])
+    labels[200:230, ::2] = k - 1                       # a 30-line block: below bgminsamp in some columns
+    labels[:, 1] = np.where(labels[:, 1] == 1, 2, labels[:, 1]) if k > 2 else labels[:, 1]   # a missing label
+    rmin = orc.min_cluster_samples(active) if reject else None
+    if reject:
+        labels[labels == k - 1] = np.where(np.arange(L)[:, None].repeat(S, 1)[labels == k - 1] < 260, k - 1, 0)
+    ref = orc.cmf_cube(cube, ab, active, labels=labels, reject_min=rmin)
+    got = cmf_cube(cube, ab, active, labels=labels, reject_min=rmin or 0)
+    assert np.array_equal(got["mask"], ref["mask"])
+    assert np.array_equal(got["mf"] == -9999.0, ref["mf"] == -9999.0)
+    for c in range(S):
+        ok = ref["mf"][:, c] != -9999.0
+        a, b = got["mf"][ok, c], ref["mf"][ok, c]
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        fin = np.isfinite(b)
+        err = np.max(np.abs(a[fin] - b[fin])) / np.std(b[fin])
+        assert err <= 1e-6, "column %d: %.3g sigma" % (c, err)
+        assert got["colnum"][c] == ref["colnum"][c]
+        assert got["colstd"][c] == pytest.approx(ref["colstd"][c], rel=1e-8)
+    assert np.array_equal(got["alpha_index"], ref["alpha_index"])
 
 
 @pytest.mark.parametrize("L,S,seed,bad", [(512, 16, 31, False), (2000, 10, 32, True), (333, 5, 33, True),

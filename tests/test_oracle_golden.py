@@ -22,18 +22,25 @@ def test_restatement_matches_reference_run(name):
     cube, active = case["cube"], case["active"]
     assert orc.active_window(case["libname"], case["reflectance"]) == active
     res = orc.cmf_cube(cube, _abscf(active), active, model=case["model"],
-                       reflectance=case["reflectance"])
+                       reflectance=case["reflectance"], labels=case.get("labels"),
+                       reject_min=case["reject_min"] or None)
     ref_mf = case["product"][..., -1]
-    # masks: pixels left at nodata must be identical
-    assert np.array_equal(ref_mf == -9999.0, ~res["mask"])
-    ok = res["mask"]
+    # masks: pixels left at nodata must be identical (invalid pixels, plus the rejected clusters with -r)
+    if case["kmodes"] > 1:
+        rejected = case["bgmeta"][..., 0] < 0
+        assert np.array_equal(ref_mf == -9999.0, ~res["mask"] | rejected)
+        assert np.array_equal(res["mf"] == -9999.0, ref_mf == -9999.0)
+        ok = res["mask"] & ~rejected
+    else:
+        assert np.array_equal(ref_mf == -9999.0, ~res["mask"])
+        ok = res["mask"]
     a, b = res["mf"][ok], ref_mf[ok]
     assert np.array_equal(np.isnan(a), np.isnan(b))
     fin = np.isfinite(b)
     # same LAPACK calls in the same order -> agreement far below the 1e-3 sigma tolerance
     scale = np.nanstd(b[fin]) if fin.any() else 1.0
     assert np.max(np.abs(a[fin] - b[fin])) <= 1e-9 * scale
-    if "bgmeta" in case:
+    if "bgmeta" in case and case["kmodes"] == 1:
         for col in range(cube.shape[2]):
             used = ok[:, col]
             if used.any():
