@@ -52,7 +52,8 @@ struct cmf_ctx {
            *colstats = nullptr, *alphas_d = nullptr, *abscf_d = nullptr;
     int *colcnt_part = nullptr, *n = nullptr, *status = nullptr, *sweeps = nullptr, *mindex = nullptr;
     // tensor-core screening of the alpha search (K3a/K3b)
-    float *Ws = nullptr, *betaf = nullptr, *Ps = nullptr;
+    float *Ws = nullptr, *betaf = nullptr, *Ps = nullptr, *tab5 = nullptr;
+    bool use_screen5 = false;     // tcgen05/TMEM screening kernel (k_screen5.cu)
     double *rsum = nullptr, *fscreen = nullptr, *tol_col = nullptr, *slogT = nullptr;
     int eigen_method = 0;         // 0 Householder + QL, 1 cyclic Jacobi (CMF_EIGEN=jacobi, cross-checks)
     int *sel_index = nullptr, *ncand = nullptr;
@@ -127,11 +128,15 @@ void fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* sel, const int* nloo
                  ctx->sweeps, ctx->eigen_method, st);
     mark(4);
     launch_tables(d, ctx->n, nloo, ctx->alphas_d, ctx->model, ctx->P, ctx->lam, ctx->slogT, ctx->Pf, ctx->Wf,
-                  ctx->logdet, ctx->beta, screen ? ctx->Ws : nullptr, ctx->betaf, ctx->rsum,
-                  screen ? ctx->Ps : nullptr, st);
+                  ctx->logdet, ctx->beta, (screen && !ctx->use_screen5) ? ctx->Ws : nullptr, ctx->betaf, ctx->rsum,
+                  (screen && !ctx->use_screen5) ? ctx->Ps : nullptr, st);
     mark(5);
     ctx->launches += 4;
-    if (screen) {
+    if (screen && ctx->use_screen5) {
+        launch_screen5(d, ctx->xt, ctx->mu, ctx->n, nloo, ctx->alphas_d, ctx->P, ctx->lam, ctx->tab5, ctx->betaf,
+                       ctx->nchunk_screen, ctx->fscreen, st);
+        ctx->launches += 2;
+    } else if (screen) {
         launch_screen(d, ctx->xt, ctx->mu, ctx->Pf, ctx->Ps, ctx->Ws, ctx->betaf, ctx->n, ctx->nchunk_screen,
                       ctx->fscreen, st);
         ++ctx->launches;
@@ -369,6 +374,8 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     // the screening pass needs its tables in shared memory and a 64-bit tile mask (A <= 512)
     ctx->can_screen = loo && d.NT2 <= 64 && screen_smem_bytes(d) <= 227 * 1024;
     if (const char* e = getenv("CMF_SCREEN_TOL")) ctx->screen_tol = atof(e);      // tuning hook (tools/ only)
+    ctx->use_screen5 = ctx->can_screen && screen5_supported(d);
+    if (const char* e = getenv("CMF_SCREEN_IMPL")) if (strcmp(e, "legacy") == 0) ctx->use_screen5 = false;
     if (const char* e = getenv("CMF_EIGEN")) ctx->eigen_method = (strcmp(e, "jacobi") == 0) ? 1 : 0;
 
     const size_t LS = (size_t)d.L * d.S;
@@ -417,6 +424,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
         A_(dalloc(ctx, &ctx->Ws, (size_t)d.S * 2 * d.NT16 * d.NT * 32 * 4));
         A_(dalloc(ctx, &ctx->fscreen, (size_t)d.S * ctx->nchunk_screen * d.AP16));
         A_(dalloc(ctx, &ctx->Ps, (size_t)d.S * 2 * d.NT * d.NT * 32 * 2));
+        if (ctx->use_screen5) A_(dalloc(ctx, &ctx->tab5, (size_t)d.S * screen5_table_floats(d)));
     }
     if (e != cudaSuccess) {
         free_buffers(ctx);

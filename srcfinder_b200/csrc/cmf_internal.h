@@ -56,6 +56,13 @@ void launch_screen(const Dims& d, const float* xt, const double* mu, const doubl
                    const float* Ws, const float* betaf, const int* n, int nchunk, double* fscreen,
                    cudaStream_t st);
 size_t screen_smem_bytes(const Dims& d);
+// tcgen05 / TMEM form of the screening pass (k_screen5.cu); falls back to launch_screen when unsupported
+bool screen5_supported(const Dims& d);
+size_t screen5_table_floats(const Dims& d);
+void launch_screen5(const Dims& d, const float* xt, const double* mu, const int* n, const int* nloo,
+                    const double* alphas, const double* P, const double* lam, float* tab, float* betaf,
+                    int nchunk, double* fscreen, cudaStream_t st);
+double screen5_selftest(int N, int K, int row_off, int swap_lbo_sbo);
 void launch_select(const Dims& d, const double* fscreen, int nchunk, const double* logdet, const double* rsum,
                    const int* n, const int* nloo, double tol, double* nll, int* sel_index,
                    unsigned long long* tile_mask, int* ncand, double* tol_out, cudaStream_t st);

@@ -1,0 +1,625 @@
+// K3a on the 5th-generation tensor cores: the screening pass of the leave-one-out alpha search
+// (cmf/robust_mf.py:105-117) as two chained tcgen05.mma contractions with TMEM accumulators.
+//
+// Same arithmetic as k_screen.cu (which stays as the path for windows that do not fit TMEM):
+//     GEMM1  Y = Xc . P                 3 x TF32 (xh.Ph + xl.Ph + xh.Pl), FP32 accumulate in TMEM
+//     GEMM2  R = (Y*Y) . W              3 x TF32 (zh.Wh + zh.Wl + zl.Wh), FP32 accumulate in TMEM
+//     h(r)   = log(1-u) + r u/(1-u), u = beta r, FP32 series, summed per alpha
+// but organised for the Blackwell tensor pipe instead of per-warp mma.sync fragments:
+//   * one CTA per (column, line chunk), 128-pixel tiles: the pixel is the TMEM lane (M = 128),
+//   * the A operand never touches shared memory: the converting threads write xh|xl straight into
+//     TMEM with tcgen05.st, GEMM1 leaves Y in TMEM, the squaring threads read it with tcgen05.ld and
+//     write zh|zl back, GEMM2 takes them as its TMEM A operand (tcgen05.mma "TS" form),
+//   * the B operands (P and W, hi and lo TF32 parts) sit in shared memory for the whole CTA in the
+//     canonical K-major no-swizzle core-matrix layout, built once per column by screen5_tables_kernel,
+//   * R is split into two alpha halves with their own full/empty barriers so that the FP32 epilogue
+//     of one half overlaps the tensor work of the other half and of the next tile,
+//   * warp roles: warp 0 bulk-copy producer, warp 1 MMA issuer (one thread), warps 4-7 convert and
+//     square (thread = pixel), warps 8-15 epilogue (thread = pixel, 112 alphas each, accumulators in
+//     registers; setmaxnreg moves registers from the control warps to the epilogue warps).
+//
+// TMEM columns (DP = padded bands, N1 = DP rounded to 16, NA = padded alphas):
+//     [0, 2DP)            xh | xl          A of GEMM1
+//     [2DP, 2DP+N1)       Y, then zh       D of GEMM1, A of GEMM2
+//     [2DP+N1, 3DP+N1)    zl               A of GEMM2
+//     [3DP+N1, .. + NA)   R                D of GEMM2
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "cmf_common.cuh"
+#include "cmf_internal.h"
+
+namespace cmf {
+
+namespace {
+
+constexpr int kT5Threads = 512;
+constexpr int kT5Stages = 3;       // 64-row half tiles in flight
+constexpr int kT5HalfRows = 64;
+
+// ------------------------------------------------------------------ tcgen05 primitives
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// mbarrier wait that traps instead of hanging the GPU when a protocol error leaves it unsignalled
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+// D[tmem] (+)= A[tmem] . B[smem]^T, kind::tf32, issued by one thread for the CTA
+__device__ __forceinline__ void mma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, TF32 x TF32, K-major A and B, M = 128
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major, no swizzle: element (row, 16-byte
+// K chunk c) lives at start + (row % 8) * 16 + (row / 8) * SBO + c * LBO
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint32_t lo = ((addr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
+    const uint32_t hi = ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14);       // version 1 (Blackwell)
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(addr));
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(addr));
+}
+
+__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t tf32_bits(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// h(r) series, see k_screen.cu
+template <int M>
+__device__ __forceinline__ float h_series(float r, float u) {
+    float s1 = 1.0f, s2 = 1.0f / (float)(M + 1);
+#pragma unroll
+    for (int m = M; m >= 1; --m) {
+        s1 = fmaf(u, s1, 1.0f);
+        s2 = fmaf(u, s2, 1.0f / (float)m);
+    }
+    return u * fmaf(r, s1, -s2);
+}
+
+__device__ __forceinline__ float h_slow(float r, float u) {
+    const float au = fabsf(u);
+    return (au <= 0x1p-3f) ? h_series<9>(r, u)
+         : (au <= 0.25f)   ? log1pf(-u) + r * u / (1.0f - u)
+                           : __int_as_float(0x7fc00000);     // extreme outlier: poison -> exact FP64 search
+}
+
+// ------------------------------------------------------------------ shared-memory plan
+struct T5Plan {
+    int DP, N1, NA, KC;
+    uint32_t ph_off, pl_off, wh_off, wl_off, tab_bytes;      // B operand tables (one bulk copy)
+    uint32_t ring_off, mu_off, beta_off, bar_off, total;
+};
+
+__host__ __device__ inline T5Plan t5_plan(int NT, int NT16) {
+    T5Plan p;
+    p.DP = 8 * NT; p.N1 = (p.DP + 15) / 16 * 16; p.NA = 16 * NT16; p.KC = p.DP / 4;
+    const uint32_t pbytes = (uint32_t)p.KC * p.N1 * 16, wbytes = (uint32_t)p.KC * p.NA * 16;
+    p.ph_off = 0; p.pl_off = pbytes; p.wh_off = 2 * pbytes; p.wl_off = 2 * pbytes + wbytes;
+    p.tab_bytes = 2 * pbytes + 2 * wbytes;
+    p.ring_off = p.tab_bytes;
+    p.mu_off = p.ring_off + (uint32_t)kT5Stages * kT5HalfRows * p.DP * 4;
+    p.beta_off = p.mu_off + (uint32_t)p.DP * 8;
+    p.bar_off = (p.beta_off + (uint32_t)p.NA * 4 + 15u) & ~15u;
+    p.total = p.bar_off + 24 * 8;
+    return p;
+}
+
+enum { B_TAB = 0, B_XFULL = 1, B_XEMPTY = 4, B_XREADY = 7, B_G1 = 8, B_ZREADY = 9, B_RFULL = 10, B_REMPTY = 12,
+       B_COUNT = 14 };
+
+// ------------------------------------------------------------------ B operand tables
+// tab[s] = Ph | Pl | Wh | Wl, each [K chunk c][row][4]: P rows are eigen-directions j (K = band b),
+// W rows are alphas i (K = eigen-direction j); hi = tf32(v), lo = tf32(v - hi).
+__global__ void __launch_bounds__(256)
+    screen5_tables_kernel(const int* __restrict__ n_g, const int* __restrict__ nloo_g,
+                          const double* __restrict__ alphas, int A, int D, int NT, int NT16,
+                          const double* __restrict__ P_g, const double* __restrict__ lam_g,
+                          float* __restrict__ tab_g, float* __restrict__ betaf_g) {
+    const T5Plan p = t5_plan(NT, NT16);
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int n = n_g[s];
+    if (n < 2) return;
+    const int DP = p.DP;
+    float* tab = tab_g + (size_t)s * (p.tab_bytes / 4);
+    const double* P = P_g + (long long)s * DP * DP;
+    const double* lam = lam_g + (long long)s * DP;
+    for (int idx = tid; idx < p.KC * p.N1 * 4; idx += blockDim.x) {
+        const int e = idx & 3, j = (idx >> 2) % p.N1, c = (idx >> 2) / p.N1;
+        const int b = 4 * c + e;
+        const double v = (j < DP) ? P[b * DP + j] : 0.0;
+        const float hi = to_tf32((float)v);
+        tab[p.ph_off / 4 + idx] = hi;
+        tab[p.pl_off / 4 + idx] = to_tf32((float)(v - (double)hi));
+    }
+    const double dn = (double)(nloo_g ? nloo_g[s] : n);
+    for (int i = tid; i < p.NA; i += blockDim.x)
+        betaf_g[(long long)s * p.NA + i] = (i < A) ? (float)((1.0 - alphas[i]) / (dn - 1.0)) : 0.f;
+    for (int idx = tid; idx < p.KC * p.NA * 4; idx += blockDim.x) {
+        const int e = idx & 3, i = (idx >> 2) % p.NA, c = (idx >> 2) / p.NA;
+        const int j = 4 * c + e;
+        double w = 0.0;
+        if (j < D && i < A) {
+            const double al = alphas[i];
+            const double be = (1.0 - al) / (dn - 1.0);
+            w = 1.0 / (dn * be * lam[j] + al);
+        }
+        const float hi = to_tf32((float)w);
+        tab[p.wh_off / 4 + idx] = hi;
+        tab[p.wl_off / 4 + idx] = to_tf32((float)(w - (double)hi));
+    }
+}
+
+// ------------------------------------------------------------------ the screening kernel
+template <int NT, int NH16>
+__global__ void __launch_bounds__(kT5Threads, 1)
+    loo_screen5_kernel(const float* __restrict__ xt, const double* __restrict__ mu_g,
+                       const float* __restrict__ tab_g, const float* __restrict__ betaf_g,
+                       const int* __restrict__ n_g, int L, int NT16, int lines_per_chunk,
+                       double* __restrict__ fscreen) {
+    constexpr int DP = 8 * NT, N1 = (DP + 15) / 16 * 16;
+    constexpr uint32_t C_XH = 0, C_XL = DP, C_Y = 2 * DP, C_ZL = 2 * DP + N1, C_R = 3 * DP + N1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const T5Plan p = t5_plan(NT, NT16);
+    const int NA = p.NA;
+    const int nt_a = min(NH16, NT16), nt_b = NT16 - nt_a;       // 16-alpha tiles per half
+    const int NA_a = 16 * nt_a, NA_b = 16 * nt_b;
+
+    const int s = blockIdx.x, chunk = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double* out = fscreen + ((long long)s * gridDim.y + chunk) * NA;
+    if (n_g[s] < 2) return;                                      // nothing to search (K4 handles n < 2)
+    const int c_begin = chunk * lines_per_chunk;
+    const int c_end = min(L, c_begin + lines_per_chunk);
+    if (c_end <= c_begin) {                                      // empty tail chunk
+        for (int i = tid; i < NA; i += blockDim.x) out[i] = 0.0;
+        return;
+    }
+    const int nrows = c_end - c_begin;
+    const int ntiles = (nrows + 127) / 128;
+    const int nhalf = (nrows + kT5HalfRows - 1) / kT5HalfRows;
+
+    float* ring = reinterpret_cast<float*>(smem_raw + p.ring_off);
+    float2* mu2 = reinterpret_cast<float2*>(smem_raw + p.mu_off);
+    float* beta_s = reinterpret_cast<float*>(smem_raw + p.beta_off);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + p.bar_off);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+
+    if (tid == 0) {
+        mbar_init(&bars[B_TAB], 1);
+        for (int i = 0; i < kT5Stages; ++i) { mbar_init(&bars[B_XFULL + i], 1); mbar_init(&bars[B_XEMPTY + i], 2); }
+        mbar_init(&bars[B_XREADY], 128);
+        mbar_init(&bars[B_G1], 1);
+        mbar_init(&bars[B_ZREADY], 128);
+        mbar_init(&bars[B_RFULL], 1); mbar_init(&bars[B_RFULL + 1], 1);
+        mbar_init(&bars[B_REMPTY], 128); mbar_init(&bars[B_REMPTY + 1], 128);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < DP; i += blockDim.x) {
+        const double m = mu_g[(long long)s * DP + i];
+        const float mh = (float)m;
+        mu2[i] = make_float2(mh, (float)(m - (double)mh));
+    }
+    for (int i = tid; i < NA; i += blockDim.x) beta_s[i] = betaf_g[(long long)s * NA + i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int wg = warp >> 2;
+    if (wg == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 0 && lane == 0) {
+            // ---------------- producer: tables once, then 64-row half tiles through the ring
+            mbar_expect_tx(&bars[B_TAB], p.tab_bytes);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(tab_g) + (size_t)s * p.tab_bytes;
+            for (uint32_t off = 0; off < p.tab_bytes; off += 32768u) {
+                const uint32_t bytes = min(32768u, p.tab_bytes - off);
+                bulk_g2s(smem_raw + off, src + off, bytes, &bars[B_TAB]);
+            }
+            const float* col_base = xt + ((long long)s * L + c_begin) * DP;
+            for (int h = 0; h < nhalf; ++h) {
+                const int slot = h % kT5Stages, use = h / kT5Stages;
+                if (use > 0) mbar_wait_guard(&bars[B_XEMPTY + slot], (uint32_t)((use - 1) & 1));
+                const int rows = min(kT5HalfRows, nrows - h * kT5HalfRows);
+                const uint32_t bytes = (uint32_t)(rows * DP * sizeof(float));
+                mbar_expect_tx(&bars[B_XFULL + slot], bytes);
+                bulk_g2s(ring + slot * kT5HalfRows * DP, col_base + (long long)h * kT5HalfRows * DP, bytes,
+                         &bars[B_XFULL + slot]);
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ---------------- MMA issuer
+            const uint32_t sbase = smem_u32(smem_raw);
+            const uint32_t lbo1 = N1 * 16, lbo2 = (uint32_t)NA * 16;
+            const uint32_t id1 = idesc_tf32(N1), id2a = idesc_tf32(NA_a), id2b = idesc_tf32(NA_b > 0 ? NA_b : 16);
+            mbar_wait_guard(&bars[B_TAB], 0);
+            for (int t = 0; t < ntiles; ++t) {
+                const uint32_t ph = (uint32_t)(t & 1);
+                mbar_wait_guard(&bars[B_XREADY], ph);
+                tc_fence_after();
+#pragma unroll 1
+                for (int ks = 0; ks < NT; ++ks) {
+                    const uint64_t dh = smem_desc(sbase + p.ph_off + 2 * ks * lbo1, lbo1, 128);
+                    const uint64_t dl = smem_desc(sbase + p.pl_off + 2 * ks * lbo1, lbo1, 128);
+                    mma_ts_tf32(tmem + C_Y, tmem + C_XH + 8 * ks, dh, id1, ks > 0);
+                    mma_ts_tf32(tmem + C_Y, tmem + C_XL + 8 * ks, dh, id1, 1);
+                    mma_ts_tf32(tmem + C_Y, tmem + C_XH + 8 * ks, dl, id1, 1);
+                }
+                tc_commit(&bars[B_G1]);
+                mbar_wait_guard(&bars[B_ZREADY], ph);
+                if (t > 0) mbar_wait_guard(&bars[B_REMPTY], ph ^ 1u);
+                tc_fence_after();
+#pragma unroll 1
+                for (int ks = 0; ks < NT; ++ks) {
+                    const uint64_t dh = smem_desc(sbase + p.wh_off + 2 * ks * lbo2, lbo2, 128);
+                    const uint64_t dl = smem_desc(sbase + p.wl_off + 2 * ks * lbo2, lbo2, 128);
+                    mma_ts_tf32(tmem + C_R, tmem + C_Y + 8 * ks, dh, id2a, ks > 0);
+                    mma_ts_tf32(tmem + C_R, tmem + C_Y + 8 * ks, dl, id2a, 1);
+                    mma_ts_tf32(tmem + C_R, tmem + C_ZL + 8 * ks, dh, id2a, 1);
+                }
+                tc_commit(&bars[B_RFULL]);
+                if (NA_b > 0) {
+                    if (t > 0) { mbar_wait_guard(&bars[B_REMPTY + 1], ph ^ 1u); tc_fence_after(); }
+#pragma unroll 1
+                    for (int ks = 0; ks < NT; ++ks) {
+                        const uint64_t dh = smem_desc(sbase + p.wh_off + 2 * ks * lbo2 + NA_a * 16, lbo2, 128);
+                        const uint64_t dl = smem_desc(sbase + p.wl_off + 2 * ks * lbo2 + NA_a * 16, lbo2, 128);
+                        mma_ts_tf32(tmem + C_R + NA_a, tmem + C_Y + 8 * ks, dh, id2b, ks > 0);
+                        mma_ts_tf32(tmem + C_R + NA_a, tmem + C_Y + 8 * ks, dl, id2b, 1);
+                        mma_ts_tf32(tmem + C_R + NA_a, tmem + C_ZL + 8 * ks, dh, id2b, 1);
+                    }
+                    tc_commit(&bars[B_RFULL + 1]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (wg == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        // ---------------- convert (x -> xh|xl) and square (y -> zh|zl): thread = pixel = TMEM lane
+        const int q = warp & 3, row = 32 * q + lane, myhalf = q >> 1, rin = row & (kT5HalfRows - 1);
+        const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
+        auto convert = [&](int t) {
+            const int h = 2 * t + myhalf, slot = h % kT5Stages, use = h / kT5Stages;
+            const bool have = h < nhalf;
+            if (have) mbar_wait_guard(&bars[B_XFULL + slot], (uint32_t)(use & 1));
+            const bool row_ok = have && (128 * t + row < nrows);
+            const float4* src = reinterpret_cast<const float4*>(ring + (slot * kT5HalfRows + rin) * DP);
+#pragma unroll
+            for (int c = 0; c < NT; ++c) {
+                float x[8];
+                if (row_ok) {
+                    const float4 a = src[2 * c], b = src[2 * c + 1];
+                    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                }
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float2 m = mu2[8 * c + e];
+                    const float v = (row_ok && x[e] == x[e]) ? (x[e] - m.x) - m.y : 0.f;
+                    hi[e] = tf32_bits(v);
+                    lo[e] = tf32_bits(v - __uint_as_float(hi[e]));
+                }
+                tmem_st8(tl + C_XH + 8 * c, hi);
+                tmem_st8(tl + C_XL + 8 * c, lo);
+            }
+            tc_wait_st();
+            if (have) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[B_XEMPTY + slot]);
+            }
+            tc_fence_before();
+            mbar_arrive(&bars[B_XREADY]);
+        };
+        convert(0);
+        for (int t = 0; t < ntiles; ++t) {
+            mbar_wait_guard(&bars[B_G1], (uint32_t)(t & 1));
+            tc_fence_after();
+            uint32_t y[NT][8];
+#pragma unroll
+            for (int c = 0; c < NT; ++c) tmem_ld8(tl + C_Y + 8 * c, y[c]);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < NT; ++c) {
+                uint32_t lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float yv = __uint_as_float(y[c][e]);
+                    const float z = yv * yv;
+                    y[c][e] = tf32_bits(z);
+                    lo[e] = tf32_bits(z - __uint_as_float(y[c][e]));
+                }
+                tmem_st8(tl + C_Y + 8 * c, y[c]);
+                tmem_st8(tl + C_ZL + 8 * c, lo);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bars[B_ZREADY]);
+            if (t + 1 < ntiles) convert(t + 1);
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+        // ---------------- epilogue: thread = pixel, one half of the alphas, per-alpha sums in registers
+        const int q = warp & 3, half = (warp - 8) >> 2;
+        const int ntile = half ? nt_b : nt_a;
+        const int cb = half ? NA_a : 0;
+        const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16) + C_R + (uint32_t)cb;
+        float acc[NH16][16];
+#pragma unroll
+        for (int k = 0; k < NH16; ++k)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) acc[k][e] = 0.f;
+        if (ntile > 0) {
+            for (int t = 0; t < ntiles; ++t) {
+                mbar_wait_guard(&bars[B_RFULL + half], (uint32_t)(t & 1));
+                tc_fence_after();
+                uint32_t rbuf[2][16];
+                tmem_ld16(tl, rbuf[0]);
+#pragma unroll
+                for (int k = 0; k < NH16; ++k) {
+                    if (k < ntile) {
+                        tc_wait_ld();
+                        if (k + 1 < NH16 && k + 1 < ntile) tmem_ld16(tl + 16 * (k + 1), rbuf[(k + 1) & 1]);
+                        float r[16], u[16], umax = 0.f;
+                        const float4* bp = reinterpret_cast<const float4*>(beta_s + cb + 16 * k);
+#pragma unroll
+                        for (int v4 = 0; v4 < 4; ++v4) {
+                            const float4 b = bp[v4];
+                            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                r[4 * v4 + e] = __uint_as_float(rbuf[k & 1][4 * v4 + e]);
+                                u[4 * v4 + e] = bb[e] * r[4 * v4 + e];
+                                umax = fmaxf(umax, fabsf(u[4 * v4 + e]));
+                            }
+                        }
+                        if (!(umax == umax)) umax = 1.0f;                   // NaN -> slow path -> poison
+                        const unsigned big = __ballot_sync(0xffffffffu, umax > 0x1p-6f);
+                        const unsigned huge = __ballot_sync(0xffffffffu, umax > 0x1p-3f);
+                        if (big == 0u) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) acc[k][e] += h_series<4>(r[e], u[e]);
+                        } else if (huge == 0u) {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) acc[k][e] += h_series<9>(r[e], u[e]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) acc[k][e] += h_slow(r[e], u[e]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&bars[B_REMPTY + half]);
+            }
+        }
+        // every x tile has been consumed by now: the ring doubles as the reduction scratch [8 warps][NH16*16]
+        double* red = reinterpret_cast<double*>(ring) + (warp - 8) * (NH16 * 16);
+#pragma unroll
+        for (int k = 0; k < NH16; ++k)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                double v = (double)acc[k][e];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += shfl_xor_f64(v, o);
+                if (lane == 0) red[16 * k + e] = v;
+            }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+    const double* red = reinterpret_cast<const double*>(ring);
+    for (int i = tid; i < NA; i += blockDim.x) {
+        const int half = (i >= NA_a) ? 1 : 0, j = i - (half ? NA_a : 0);
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) a += red[(4 * half + w) * (NH16 * 16) + j];
+        out[i] = a;
+    }
+}
+
+// ------------------------------------------------------------------ self test (cmf_microbench kinds 20..23)
+// One 128 x N x K contraction with A written to TMEM by tcgen05.st and B in the canonical shared-memory
+// layout: checks the descriptor encoding, the TMEM A layout and the ld/st lane mapping against the host.
+__global__ void __launch_bounds__(128, 1)
+    tc5_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bt, int N, int K, int row_off,
+                        int swap_lbo_sbo, float* __restrict__ Dout) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int KC = K / 4, NB = N + row_off;                      // the table holds NB rows, the MMA uses rows row_off..
+    float* bs = reinterpret_cast<float*>(smem_raw);              // [KC][NB][4]
+    for (int idx = tid; idx < KC * NB * 4; idx += blockDim.x) {
+        const int e = idx & 3, n = (idx >> 2) % NB, c = (idx >> 2) / NB;
+        bs[idx] = Bt[n * K + 4 * c + e];
+    }
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t tl = tmem + ((uint32_t)(32 * warp) << 16);
+    for (int c = 0; c < K / 8; ++c) {
+        uint32_t v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __float_as_uint(A[tid * K + 8 * c + e]);
+        tmem_st8(tl + 8 * c, v);
+    }
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        const uint32_t lbo = (uint32_t)NB * 16, sbo = 128;
+        const uint32_t id = idesc_tf32(N);
+        for (int ks = 0; ks < K / 8; ++ks) {
+            const uint32_t addr = smem_u32(bs) + 2 * ks * lbo + row_off * 16;
+            const uint64_t d = swap_lbo_sbo ? smem_desc(addr, sbo, lbo) : smem_desc(addr, lbo, sbo);
+            mma_ts_tf32(tmem + 256, tmem + 8 * ks, d, id, ks > 0);
+        }
+        tc_commit(&bar);
+    }
+    mbar_wait_guard(&bar, 0);
+    tc_fence_after();
+    for (int c = 0; c < N / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld16(tl + 256 + 16 * c, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) Dout[tid * N + 16 * c + e] = __uint_as_float(v[e]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ launchers
+bool screen5_supported(const Dims& d) {
+    if (d.NT < 1 || d.NT > 9 || d.NT16 < 1 || d.NT16 > 14) return false;
+    const T5Plan p = t5_plan(d.NT, d.NT16);
+    if (3 * p.DP + p.N1 + p.NA > 512) return false;
+    // reduction scratch (8 warps x 112 doubles) reuses the ring
+    if ((size_t)kT5Stages * kT5HalfRows * p.DP * 4 < (size_t)8 * 7 * 16 * sizeof(double)) return false;
+    return p.total <= 227u * 1024u;
+}
+
+size_t screen5_table_floats(const Dims& d) { return t5_plan(d.NT, d.NT16).tab_bytes / 4; }
+
+int screen5_lines_per_chunk(const Dims& d, int nchunk) {
+    int lpc = (d.L + nchunk - 1) / nchunk;
+    return (lpc + 127) / 128 * 128;
+}
+
+template <int NT>
+static void launch_screen5_t(const Dims& d, const float* xt, const double* mu, const float* tab, const float* betaf,
+                             const int* n, int nchunk, double* fscreen, cudaStream_t st) {
+    const T5Plan p = t5_plan(d.NT, d.NT16);
+    cudaFuncSetAttribute(loo_screen5_kernel<NT, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);
+    dim3 grid(d.S, nchunk);
+    loo_screen5_kernel<NT, 7><<<grid, kT5Threads, p.total, st>>>(xt, mu, tab, betaf, n, d.L, d.NT16,
+                                                                 screen5_lines_per_chunk(d, nchunk), fscreen);
+}
+
+void launch_screen5(const Dims& d, const float* xt, const double* mu, const int* n, const int* nloo,
+                    const double* alphas, const double* P, const double* lam, float* tab, float* betaf,
+                    int nchunk, double* fscreen, cudaStream_t st) {
+    screen5_tables_kernel<<<d.S, 256, 0, st>>>(n, nloo, alphas, d.A, d.D, d.NT, d.NT16, P, lam, tab, betaf);
+    switch (d.NT) {
+#define CMF_CASE(k) case k: launch_screen5_t<k>(d, xt, mu, tab, betaf, n, nchunk, fscreen, st); break;
+        CMF_CASE(1) CMF_CASE(2) CMF_CASE(3) CMF_CASE(4) CMF_CASE(5) CMF_CASE(6) CMF_CASE(7) CMF_CASE(8) CMF_CASE(9)
+#undef CMF_CASE
+        default: break;
+    }
+}
+
+// max |D - A.B^T| of one tcgen05 TS-form contraction against the host; < 0 on a CUDA error
+double screen5_selftest(int N, int K, int row_off, int swap_lbo_sbo) {
+    const int NB = N + row_off;
+    std::vector<float> A(128 * K), B(NB * K), D(128 * N);
+    uint32_t seed = 12345u;
+    auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return (float)((int)((seed >> 16) & 127) - 64) / 64.0f; };
+    for (auto& v : A) v = rnd();
+    for (auto& v : B) v = rnd();
+    float *dA, *dB, *dD;
+    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dD, D.size() * 4);
+    cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(dD, 0xff, D.size() * 4);
+    const size_t smem = (size_t)(K / 4) * NB * 16;
+    cudaFuncSetAttribute(tc5_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc5_selftest_kernel<<<1, 128, smem>>>(dA, dB, N, K, row_off, swap_lbo_sbo, dD);
+    cudaError_t e = cudaDeviceSynchronize();
+    double err = -1.0;
+    if (e == cudaSuccess) {
+        cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+        err = 0.0;
+        for (int m = 0; m < 128; ++m)
+            for (int nn = 0; nn < N; ++nn) {
+                double ref = 0.0;
+                for (int k = 0; k < K; ++k) ref += (double)A[m * K + k] * (double)B[(nn + row_off) * K + k];
+                const double dv = fabs((double)D[m * N + nn] - ref);
+                if (!(dv <= err)) err = dv;
+            }
+    } else {
+        fprintf(stderr, "screen5_selftest: %s\n", cudaGetErrorString(e));
+    }
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+    return err;
+}
+
+}  // namespace cmf

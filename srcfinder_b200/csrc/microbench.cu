@@ -4,6 +4,7 @@
 
 #include "../../include/cmf_b200.h"
 #include "cmf_common.cuh"
+#include "cmf_internal.h"
 
 namespace {
 
@@ -250,6 +251,15 @@ extern "C" double cmf_microbench(int device, int kind, int iters) {
         const double sec = time_ms(e0, e1) * 1e-3 / iters;
         result = (kind == 4 ? 2.0 : 1.0) * (double)bytes / sec * 1e-9;   // GB/s
         cudaFree(in); cudaFree(flag); if (outp) cudaFree(outp);
+    }
+    else if (kind >= 20 && kind <= 25) {
+        // tcgen05 TS-form self test: max |D - A.B^T| (exact inputs, so 0 when the layouts are right)
+        if (kind == 20) result = cmf::screen5_selftest(80, 72, 0, 0);
+        else if (kind == 21) result = cmf::screen5_selftest(80, 72, 0, 1);
+        else if (kind == 22) result = cmf::screen5_selftest(96, 72, 112, 0);
+        else if (kind == 23) result = cmf::screen5_selftest(112, 72, 0, 0);
+        else if (kind == 24) result = cmf::screen5_selftest(72, 72, 0, 0);
+        else result = cmf::screen5_selftest(256, 8, 0, 0);
     }
     if (cudaGetLastError() != cudaSuccess) result = -1.0;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
