@@ -144,7 +144,8 @@ void fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* sel, const int* nloo
     mark(6);
     if (screen) {
         launch_select(d, ctx->fscreen, ctx->nchunk_screen, ctx->logdet, ctx->rsum, ctx->n, nloo, ctx->screen_tol,
-                      ctx->nll, ctx->sel_index, ctx->tile_mask, ctx->ncand, ctx->tol_col, st);
+                      ctx->nll, ctx->sel_index, ctx->tile_mask, ctx->ncand, ctx->tol_col,
+                      ctx->use_screen5 ? ctx->betaf : nullptr, st);
         ++ctx->launches;
     }
     mark(7);

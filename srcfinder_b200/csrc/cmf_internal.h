@@ -65,7 +65,8 @@ void launch_screen5(const Dims& d, const float* xt, const double* mu, const int*
 double screen5_selftest(int N, int K, int row_off, int swap_lbo_sbo);
 void launch_select(const Dims& d, const double* fscreen, int nchunk, const double* logdet, const double* rsum,
                    const int* n, const int* nloo, double tol, double* nll, int* sel_index,
-                   unsigned long long* tile_mask, int* ncand, double* tol_out, cudaStream_t st);
+                   unsigned long long* tile_mask, int* ncand, double* tol_out, const float* betaf_fold,
+                   cudaStream_t st);
 void launch_finalize(const Dims& d, const double* fpart, int nchunk, const double* logdet, const int* n,
                      const double* alphas, const double* P, const double* lam, const double* mu,
                      const double* abscf, int model, int reflectance, double scale, double* nll,

@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(128)
                   const int* __restrict__ nloo_g, int A, int AP, int AP16,
                   int D, int S, double tol, double* __restrict__ nll_g, int* __restrict__ sel_index,
                   unsigned long long* __restrict__ tile_mask, int* __restrict__ ncand_g,
-                  double* __restrict__ tol_g) {
+                  double* __restrict__ tol_g, const float* __restrict__ betaf_fold) {
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (s >= S) return;
@@ -339,6 +339,8 @@ __global__ void __launch_bounds__(128)
     for (int i = lane; i < A; i += 32) {
         double fs = 0.0;
         for (int c = 0; c < nchunk; ++c) fs += fscreen[((long long)s * nchunk + c) * AP16 + i];
+        // the tcgen05 pass sums h + u; sum_k u_k = beta sum_k r_k is the closed form (k_screen5.cu)
+        if (betaf_fold) fs -= (double)betaf_fold[(long long)s * AP16 + i] * rsum_g[(long long)s * AP + i];
         const double ld = logdet_g[(long long)s * AP + i];
         double v;
         if (ld < -744.4400719213812 || ld > 709.782712893384) v = inf;   // det under/overflow (:112-113)
@@ -438,9 +440,10 @@ void launch_screen(const Dims& d, const float* xt, const double* mu, const doubl
 
 void launch_select(const Dims& d, const double* fscreen, int nchunk, const double* logdet, const double* rsum,
                    const int* n, const int* nloo, double tol, double* nll, int* sel_index,
-                   unsigned long long* tile_mask, int* ncand, double* tol_out, cudaStream_t st) {
+                   unsigned long long* tile_mask, int* ncand, double* tol_out, const float* betaf_fold,
+                   cudaStream_t st) {
     select_kernel<<<(d.S + 3) / 4, 128, 0, st>>>(fscreen, nchunk, logdet, rsum, n, nloo, d.A, d.AP, d.AP16, d.D, d.S, tol,
-                                                 nll, sel_index, tile_mask, ncand, tol_out);
+                                                 nll, sel_index, tile_mask, ncand, tol_out, betaf_fold);
 }
 
 }  // namespace cmf

@@ -58,6 +58,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // mbarrier wait that traps instead of hanging the GPU when a protocol error leaves it unsignalled
 __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
         uint32_t ok;
         asm volatile(
@@ -116,36 +117,53 @@ __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) 
                  : "memory");
 }
 
-__device__ __forceinline__ uint32_t tf32_bits(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// FP32 -> TF32 on the integer pipe (cvt.rna.tf32.f32 issues on the 16-lane XU pipe and was the busiest
+// pipe of the first version): round-half-away on the 13 dropped bits for the hi part, truncation for the lo
+// part (its error is 2^-22 of the value).  Inputs are finite.
+__device__ __forceinline__ uint32_t tf32_round(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+__device__ __forceinline__ uint32_t tf32_trunc(float x) { return __float_as_uint(x) & 0xffffe000u; }
 
-// h(r) series, see k_screen.cu
-template <int M>
-__device__ __forceinline__ float h_series(float r, float u) {
-    float s1 = 1.0f, s2 = 1.0f / (float)(M + 1);
+// The epilogue sums g = h + u per alpha, where h = log(1-u) + r u/(1-u) and u = beta r (log q + r/q = r + h):
+//     g = sum_{k>=2} u^k (1/beta - 1/k)
+// sum_k u_k = beta sum_k r_k is known in closed form (rsum), so K3b subtracts it in FP64.  d_k = 1/beta - 1/k
+// are per-alpha constants: k = 2..5 come from a shared-memory table (terms to u^5: |u| <= 2^-6), k <= 10
+// (|u| <= 2^-3) are formed on the fly; anything larger is the rare out-of-line slow path.
+// Everything that is not the 5-term fast path, out of line so that the hot loop stays small: 10 terms while
+// |u| <= 2^-3 (u^11 < 2^-33), log1p and a division up to u = 1/4, poison beyond.
+__device__ __noinline__ void g_cold16(const float* __restrict__ rp, const float* __restrict__ beta,
+                                      const float4* __restrict__ dp, float* __restrict__ g) {
+    float r[16], u[16], umax = 0.f;
 #pragma unroll
-    for (int m = M; m >= 1; --m) {
-        s1 = fmaf(u, s1, 1.0f);
-        s2 = fmaf(u, s2, 1.0f / (float)m);
+    for (int e = 0; e < 16; ++e) { r[e] = rp[e]; u[e] = beta[e] * r[e]; umax = fmaxf(umax, fabsf(u[e])); }
+    if (!(umax == umax)) umax = 1.0f;
+    if (__ballot_sync(0xffffffffu, umax > 0x1p-3f) == 0u) {
+        float pz[16], binv[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { binv[e] = dp[e].x + 0.5f; pz[e] = binv[e] - 0.1f; }
+#pragma unroll 1
+        for (int kk = 9; kk >= 2; --kk) {
+            const float ik = 1.0f / (float)kk;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pz[e] = fmaf(pz[e], u[e], binv[e] - ik);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) g[e] = u[e] * u[e] * pz[e];
+    } else {
+#pragma unroll 1
+        for (int e = 0; e < 16; ++e) {
+            const float uu = beta[e] * rp[e], au = fabsf(uu);
+            // beyond u = 1/4 the term amplifies the TF32 error of r by u/(1-u) and more: such a pixel is an
+            // extreme outlier (x'G^-1 x > n/4); poison the sum so that the column is searched in FP64
+            g[e] = (au <= 0.25f) ? (log1pf(-uu) + rp[e] * uu / (1.0f - uu)) + uu : __int_as_float(0x7fc00000);
+        }
     }
-    return u * fmaf(r, s1, -s2);
-}
-
-__device__ __forceinline__ float h_slow(float r, float u) {
-    const float au = fabsf(u);
-    return (au <= 0x1p-3f) ? h_series<9>(r, u)
-         : (au <= 0.25f)   ? log1pf(-u) + r * u / (1.0f - u)
-                           : __int_as_float(0x7fc00000);     // extreme outlier: poison -> exact FP64 search
 }
 
 // ------------------------------------------------------------------ shared-memory plan
 struct T5Plan {
     int DP, N1, NA, KC;
     uint32_t ph_off, pl_off, wh_off, wl_off, tab_bytes;      // B operand tables (one bulk copy)
-    uint32_t ring_off, mu_off, beta_off, bar_off, total;
+    uint32_t ring_off, mu_off, beta_off, dtab_off, bar_off, total;
 };
 
 __host__ __device__ inline T5Plan t5_plan(int NT, int NT16) {
@@ -157,7 +175,8 @@ __host__ __device__ inline T5Plan t5_plan(int NT, int NT16) {
     p.ring_off = p.tab_bytes;
     p.mu_off = p.ring_off + (uint32_t)kT5Stages * kT5HalfRows * p.DP * 4;
     p.beta_off = p.mu_off + (uint32_t)p.DP * 8;
-    p.bar_off = (p.beta_off + (uint32_t)p.NA * 4 + 15u) & ~15u;
+    p.dtab_off = (p.beta_off + (uint32_t)p.NA * 4 + 15u) & ~15u;
+    p.bar_off = p.dtab_off + (uint32_t)p.NA * 16;
     p.total = p.bar_off + 24 * 8;
     return p;
 }
@@ -239,6 +258,7 @@ __global__ void __launch_bounds__(kT5Threads, 1)
     float* ring = reinterpret_cast<float*>(smem_raw + p.ring_off);
     float2* mu2 = reinterpret_cast<float2*>(smem_raw + p.mu_off);
     float* beta_s = reinterpret_cast<float*>(smem_raw + p.beta_off);
+    float4* dtab = reinterpret_cast<float4*>(smem_raw + p.dtab_off);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + p.bar_off);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
@@ -263,7 +283,14 @@ __global__ void __launch_bounds__(kT5Threads, 1)
         const float mh = (float)m;
         mu2[i] = make_float2(mh, (float)(m - (double)mh));
     }
-    for (int i = tid; i < NA; i += blockDim.x) beta_s[i] = betaf_g[(long long)s * NA + i];
+    for (int i = tid; i < NA; i += blockDim.x) {
+        const float b = betaf_g[(long long)s * NA + i];
+        const float binv = 1.0f / b;
+        beta_s[i] = b;
+        // beta == 0 (alpha == 1, padding): u == 0 and every term vanishes; keep the constants finite
+        dtab[i] = (b > 0.f) ? make_float4(binv - 0.5f, binv - 1.0f / 3.0f, binv - 0.25f, binv - 0.2f)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -341,63 +368,76 @@ __global__ void __launch_bounds__(kT5Threads, 1)
         // ---------------- convert (x -> xh|xl) and square (y -> zh|zl): thread = pixel = TMEM lane
         const int q = warp & 3, row = 32 * q + lane, myhalf = q >> 1, rin = row & (kT5HalfRows - 1);
         const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
-        auto convert = [&](int t) {
-            const int h = 2 * t + myhalf, slot = h % kT5Stages, use = h / kT5Stages;
-            const bool have = h < nhalf;
-            if (have) mbar_wait_guard(&bars[B_XFULL + slot], (uint32_t)(use & 1));
-            const bool row_ok = have && (128 * t + row < nrows);
-            const float4* src = reinterpret_cast<const float4*>(ring + (slot * kT5HalfRows + rin) * DP);
+        // loops stay rolled: one warp per scheduler runs this code, so its footprint has to sit in the
+        // instruction cache (the unrolled first version spent most of its time in instruction fetch)
+        auto square8 = [&](uint32_t (&y)[8], int c) {
+            uint32_t lo[8];
 #pragma unroll
-            for (int c = 0; c < NT; ++c) {
-                float x[8];
-                if (row_ok) {
-                    const float4 a = src[2 * c], b = src[2 * c + 1];
-                    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-                }
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float2 m = mu2[8 * c + e];
-                    const float v = (row_ok && x[e] == x[e]) ? (x[e] - m.x) - m.y : 0.f;
-                    hi[e] = tf32_bits(v);
-                    lo[e] = tf32_bits(v - __uint_as_float(hi[e]));
-                }
-                tmem_st8(tl + C_XH + 8 * c, hi);
-                tmem_st8(tl + C_XL + 8 * c, lo);
+            for (int e = 0; e < 8; ++e) {
+                const float yv = __uint_as_float(y[e]);
+                const float z = yv * yv;
+                y[e] = tf32_round(z);
+                lo[e] = tf32_trunc(z - __uint_as_float(y[e]));
             }
-            tc_wait_st();
-            if (have) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[B_XEMPTY + slot]);
-            }
-            tc_fence_before();
-            mbar_arrive(&bars[B_XREADY]);
+            tmem_st8(tl + C_Y + 8 * c, y);
+            tmem_st8(tl + C_ZL + 8 * c, lo);
         };
-        convert(0);
-        for (int t = 0; t < ntiles; ++t) {
-            mbar_wait_guard(&bars[B_G1], (uint32_t)(t & 1));
-            tc_fence_after();
-            uint32_t y[NT][8];
-#pragma unroll
-            for (int c = 0; c < NT; ++c) tmem_ld8(tl + C_Y + 8 * c, y[c]);
-            tc_wait_ld();
-#pragma unroll
-            for (int c = 0; c < NT; ++c) {
-                uint32_t lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float yv = __uint_as_float(y[c][e]);
-                    const float z = yv * yv;
-                    y[c][e] = tf32_bits(z);
-                    lo[e] = tf32_bits(z - __uint_as_float(y[c][e]));
+#pragma unroll 1
+        for (int t = 0; t <= ntiles; ++t) {
+            if (t > 0) {
+                // ---- y -> zh | zl of tile t-1
+                mbar_wait_guard(&bars[B_G1], (uint32_t)((t - 1) & 1));
+                tc_fence_after();
+                uint32_t ya[8], yb[8];
+                tmem_ld8(tl + C_Y, ya);
+#pragma unroll 1
+                for (int c = 0; c < NT; c += 2) {
+                    tc_wait_ld();
+                    if (c + 1 < NT) tmem_ld8(tl + C_Y + 8 * (c + 1), yb);
+                    square8(ya, c);
+                    if (c + 1 < NT) {
+                        tc_wait_ld();
+                        if (c + 2 < NT) tmem_ld8(tl + C_Y + 8 * (c + 2), ya);
+                        square8(yb, c + 1);
+                    }
                 }
-                tmem_st8(tl + C_Y + 8 * c, y[c]);
-                tmem_st8(tl + C_ZL + 8 * c, lo);
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(&bars[B_ZREADY]);
             }
-            tc_wait_st();
-            tc_fence_before();
-            mbar_arrive(&bars[B_ZREADY]);
-            if (t + 1 < ntiles) convert(t + 1);
+            if (t < ntiles) {
+                // ---- x -> xh | xl of tile t
+                const int h = 2 * t + myhalf, slot = h % kT5Stages, use = h / kT5Stages;
+                const bool have = h < nhalf;
+                if (have) mbar_wait_guard(&bars[B_XFULL + slot], (uint32_t)(use & 1));
+                const bool row_ok = have && (128 * t + row < nrows);
+                const float4* src = reinterpret_cast<const float4*>(ring + (slot * kT5HalfRows + rin) * DP);
+#pragma unroll 1
+                for (int c = 0; c < NT; ++c) {
+                    float x[8];
+                    {
+                        const float4 a = src[2 * c], b = src[2 * c + 1];    // stale but in-bounds when !row_ok
+                        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                    }
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float2 m = mu2[8 * c + e];
+                        const float v = (row_ok && x[e] == x[e]) ? (x[e] - m.x) - m.y : 0.f;
+                        hi[e] = tf32_round(v);
+                        lo[e] = tf32_trunc(v - __uint_as_float(hi[e]));
+                    }
+                    tmem_st8(tl + C_XH + 8 * c, hi);
+                    tmem_st8(tl + C_XL + 8 * c, lo);
+                }
+                tc_wait_st();
+                if (have) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars[B_XEMPTY + slot]);
+                }
+                tc_fence_before();
+                mbar_arrive(&bars[B_XREADY]);
+            }
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
@@ -437,16 +477,21 @@ __global__ void __launch_bounds__(kT5Threads, 1)
                         }
                         if (!(umax == umax)) umax = 1.0f;                   // NaN -> slow path -> poison
                         const unsigned big = __ballot_sync(0xffffffffu, umax > 0x1p-6f);
-                        const unsigned huge = __ballot_sync(0xffffffffu, umax > 0x1p-3f);
+                        const float4* dp = dtab + cb + 16 * k;
                         if (big == 0u) {
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) acc[k][e] += h_series<4>(r[e], u[e]);
-                        } else if (huge == 0u) {
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) acc[k][e] += h_series<9>(r[e], u[e]);
+                            for (int e = 0; e < 16; ++e) {
+                                const float4 d = dp[e];                     // d2..d5 of this alpha (broadcast)
+                                const float pz = fmaf(fmaf(fmaf(d.w, u[e], d.z), u[e], d.y), u[e], d.x);
+                                acc[k][e] = fmaf(u[e] * u[e], pz, acc[k][e]);
+                            }
                         } else {
+                            float g[16], rc[16];                // copies keep r itself in registers
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) acc[k][e] += h_slow(r[e], u[e]);
+                            for (int e = 0; e < 16; ++e) rc[e] = r[e];
+                            g_cold16(rc, beta_s + cb + 16 * k, dp, g);
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) acc[k][e] += g[e];
                         }
                     }
                 }
@@ -454,17 +499,26 @@ __global__ void __launch_bounds__(kT5Threads, 1)
                 mbar_arrive(&bars[B_REMPTY + half]);
             }
         }
-        // every x tile has been consumed by now: the ring doubles as the reduction scratch [8 warps][NH16*16]
+        // every x tile has been consumed by now: the ring doubles as the reduction scratch [8 warps][NH16*16].
+        // Butterfly with halving: after the five exchanges lane l holds the 32-lane total of value l.
         double* red = reinterpret_cast<double*>(ring) + (warp - 8) * (NH16 * 16);
 #pragma unroll
-        for (int k = 0; k < NH16; ++k)
+        for (int g0 = 0; g0 < NH16 * 16; g0 += 32) {
+            constexpr int kTot = NH16 * 16;
+            double v[32];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                double v = (double)acc[k][e];
+            for (int i = 0; i < 32; ++i) v[i] = (g0 + i < kTot) ? (double)acc[(g0 + i) >> 4][(g0 + i) & 15] : 0.0;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += shfl_xor_f64(v, o);
-                if (lane == 0) red[16 * k + e] = v;
+            for (int o = 16; o > 0; o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int i = 0; i < o; ++i) {
+                    const double send = up ? v[i] : v[i + o], keep = up ? v[i + o] : v[i];
+                    v[i] = keep + shfl_xor_f64(send, o);
+                }
             }
+            if (g0 + lane < kTot) red[g0 + lane] = v[0];
+        }
     }
     tc_fence_before();
     __syncthreads();
