@@ -289,20 +289,29 @@ def run_gpu(args):
         score_bytes = (4.0 * D + 8.0 + 1.0) * L * S            # one read of the slab + f64 score + mask byte
         score_ms = kt.get("score", float("nan"))
         traffic = load_traffic()
+        skern = eng.screen_kernel() or "loo_screen_kernel"
+        tc5 = skern == "loo_screen5_kernel"
+        DP = (D + 7) // 8 * 8
+        n1, na = ((DP + 15) // 16 * 16, 208) if tc5 else (DP, 208)
+        executed = 3.0 * (2.0 * DP * n1 + 2.0 * DP * na) * L * S / (screen_ms * 1e-3) / 1e12
+        pipe = ("tcgen05.mma kind::tf32 (SASS UTCMMA), accumulators in TMEM" if tc5 else
+                "mma.sync (SASS HMMA), whose measured ceiling in this run is %.0f TFLOP/s" % mma_peak)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world),
             "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
-            "roofline": {"kernel": "loo_screen_kernel", "bound": "tensor", "achieved": achieved, "peak": tf32_peak,
-                         "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic.get("loo_screen_kernel"),
-                         "peak_source": "%s: dense TF32 = half of MEASURED_PEAKS.json bf16_tflops (%s); the kernel "
-                                        "issues TF32 through mma.sync (SASS HMMA), whose measured ceiling in this run "
-                                        "is %.0f TFLOP/s, and executes 3 split products per algorithmic product"
-                                        % (src, peaks.get("bf16_tflops"), mma_peak),
-                         "flops_per_launch": flops, "executed_tflops": 3.0 * (2.0 * D * D + 2.0 * D * 208) * L * S
-                         / (screen_ms * 1e-3) / 1e12, "mma_sync_tf32_peak": mma_peak},
+            "roofline": {"kernel": skern, "bound": "tensor", "achieved": achieved, "peak": tf32_peak,
+                         "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic.get(skern),
+                         "peak_source": "%s: dense TF32 = half of MEASURED_PEAKS.json bf16_tflops (%s, burst; sustained "
+                                        "%s); the kernel issues TF32 through %s and executes 3 split products (hi*hi, "
+                                        "lo*hi, hi*lo) per algorithmic product, padded to N=%d/%d"
+                                        % (src, peaks.get("bf16_tflops"), peaks.get("bf16_tflops_sustained"), pipe,
+                                           n1, na),
+                         "flops_per_launch": flops, "executed_tflops": executed,
+                         "executed_frac": executed / tf32_peak, "mma_sync_tf32_peak": mma_peak,
+                         "share_of_step": screen_ms / max(sum(kt.values()), 1e-9)},
             "roofline_fp64": {"kernel": "gram_kernel", "bound": "tensor", "achieved": D * (D + 8.0) * L * S
                               / (kt.get("gram", float("nan")) * 1e-3) / 1e12, "peak": dmma_peak, "unit": "TFLOP/s",
                               "peak_source": "FP64 DMMA.8x8x4 rate measured in this run (cmf_microbench kind 0)",

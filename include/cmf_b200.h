@@ -134,6 +134,9 @@ const char* cmf_kernel_name(int i);
 int cmf_kernel_times(cmf_ctx* ctx, float* ms, int n);
 /* launches issued by the last cmf_run()/cmf_run_host() */
 int cmf_launch_count(const cmf_ctx* ctx);
+/* name of the __global__ function the alpha-search screening pass uses for this problem
+ * ("loo_screen5_kernel": tcgen05/TMEM, "loo_screen_kernel": mma.sync, "" if the problem is not screened) */
+const char* cmf_screen_kernel(const cmf_ctx* ctx);
 
 /* ---- pinned host memory helpers (for asynchronous uploads) ---- */
 void* cmf_host_alloc(size_t bytes);

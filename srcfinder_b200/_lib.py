@@ -13,7 +13,7 @@ SYMBOLS = [
     "cmf_create", "cmf_destroy", "cmf_last_error", "cmf_version", "cmf_set_stream", "cmf_set_problem",
     "cmf_upload_bil", "cmf_bind_device_slab", "cmf_set_labels", "cmf_run", "cmf_sync", "cmf_run_host", "cmf_download",
     "cmf_device_ptr", "cmf_output_bytes", "cmf_kernel_count", "cmf_kernel_name", "cmf_kernel_times",
-    "cmf_launch_count", "cmf_host_alloc", "cmf_host_free", "cmf_host_register", "cmf_host_unregister",
+    "cmf_launch_count", "cmf_screen_kernel", "cmf_host_alloc", "cmf_host_free", "cmf_host_register", "cmf_host_unregister",
     "cmf_microbench",
 ]
 
@@ -67,6 +67,7 @@ def load():
         "cmf_kernel_name": (C.c_char_p, [C.c_int]),
         "cmf_kernel_times": (C.c_int, [vp, C.POINTER(C.c_float), C.c_int]),
         "cmf_launch_count": (C.c_int, [vp]),
+        "cmf_screen_kernel": (C.c_char_p, [vp]),
         "cmf_host_alloc": (vp, [sz]),
         "cmf_host_free": (None, [vp]),
         "cmf_host_register": (C.c_int, [vp, sz]),

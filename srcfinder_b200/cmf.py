@@ -153,6 +153,10 @@ class ColumnwiseMF(object):
     def launch_count(self):
         return int(self._lib.cmf_launch_count(self._ctx))
 
+    def screen_kernel(self):
+        """Name of the kernel that screens the alpha search ('' when the problem is not screened)."""
+        return self._lib.cmf_screen_kernel(self._ctx).decode()
+
     def device_ptr(self, what):
         return self._lib.cmf_device_ptr(self._ctx, int(what))
 
