@@ -111,13 +111,17 @@ int cmf_set_labels(cmf_ctx* ctx, const int32_t* labels, int kmodes, int reject_m
 /* ---- compute: the whole column loop (:297-392) for every column, no host round trip ---- */
 enum {
     CMF_RUN_TIMING = 1,           /* bracket every kernel with CUDA events (see cmf_kernel_times) */
-    CMF_RUN_EXACT = 2             /* evaluate every alpha in FP64 (no tensor-core screening of the search) */
+    CMF_RUN_EXACT = 2,            /* evaluate every alpha in FP64 (no tensor-core screening of the search) */
+    CMF_RUN_ASYNC = 4             /* cmf_run_host: return once everything is enqueued; cmf_sync() completes it */
 };
 int cmf_run(cmf_ctx* ctx, uint32_t flags);
 int cmf_sync(cmf_ctx* ctx);
 
-/* Upload + run + download of scores / column statistics / alpha indices in one call; overlaps the
- * H2D copy with the first pass block by block.  Any output pointer may be NULL.  Synchronous. */
+/* Upload + run + download of scores / column statistics / alpha indices in one call.  The cube is copied in
+ * blocks of one Gram chunk and the repack and statistics passes chase the copies, so only the factorisation,
+ * alpha search and scoring remain once the last block has landed.  Any output pointer may be NULL.
+ * Synchronous unless CMF_RUN_ASYNC is set (pinned buffers; outputs are valid after cmf_sync()): two contexts
+ * used alternately keep the PCIe link busy while the previous flightline is still being scored. */
 int cmf_run_host(cmf_ctx* ctx, const float* host_cube, double* mf_out, double* colstats_out,
                  int32_t* alpha_index_out, uint32_t flags);
 

@@ -21,6 +21,7 @@ OUT_MF, OUT_MASK, OUT_COLSTATS, OUT_ALPHA_INDEX, OUT_NLL, OUT_MU, OUT_WEIGHTS, O
     OUT_EIGVALS, OUT_SWEEPS, OUT_NCAND, OUT_SCREEN_TOL, OUT_CLUSTER_ID, OUT_ALPHA_IMAGE, OUT_MODE_LIST = range(16)
 RUN_TIMING = 1
 RUN_EXACT = 2
+RUN_ASYNC = 4
 MODEL_LOOSHRINKAGE, MODEL_EMPIRICAL = 0, 1
 COL_EMPTY, COL_DEGENERATE, COL_SINGULAR, COL_NOCONVERGE, COL_ALLINF = 1, 2, 4, 8, 16
 

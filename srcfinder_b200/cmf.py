@@ -135,12 +135,13 @@ class ColumnwiseMF(object):
     def sync(self):
         self._check(self._lib.cmf_sync(self._ctx))
 
-    def run_host(self, host_ptr, mf_out=None, colstats_out=None, alpha_out=None):
-        """End-to-end call on a host cube pointer (int address): H2D + all kernels + D2H, synchronous."""
+    def run_host(self, host_ptr, mf_out=None, colstats_out=None, alpha_out=None, wait=True):
+        """End-to-end call on a host cube pointer (int address): H2D + all kernels + D2H.  ``wait=False``
+        returns as soon as the work is enqueued (pinned buffers); ``sync()`` then completes it."""
         def addr(a):
             return C.c_void_p(None if a is None else int(a))
         self._check(self._lib.cmf_run_host(self._ctx, C.c_void_p(int(host_ptr)), addr(mf_out),
-                                           addr(colstats_out), addr(alpha_out), 0))
+                                           addr(colstats_out), addr(alpha_out), 0 if wait else _lib.RUN_ASYNC))
 
     def kernel_times(self):
         n = self._lib.cmf_kernel_count()

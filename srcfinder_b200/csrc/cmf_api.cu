@@ -71,6 +71,8 @@ struct cmf_ctx {
     double screen_tol = 2.0e-5;   // relative to the screened part of nll; measured error is <= 2.5e-6
     int nchunk_screen = 1;
     int nsplit = 1, lps = 8, nchunk_gram = 1, nchunk_loo = 1, nlanes = 1, score_lpc = 0;
+    int lpc_gram = 16, spc = 1;   // lines per Gram chunk = spc repack splits = one upload block of cmf_run_host
+    double* ctr = nullptr;        // pilot centre of the Gram pass: column mean over the first Gram chunk
 
     cudaEvent_t ev[K_COUNT + 1] = {};              // scratch set (ordering events, untimed runs)
     std::vector<std::vector<cudaEvent_t>> ev_sets;  // one set of K_COUNT+1 events per timed run
@@ -115,23 +117,35 @@ cudaError_t dalloc(cmf_ctx* c, T** p, size_t count) {
 // pixels (sel == NULL: every valid pixel), factorisation, alpha search, weights, scores.  `mark` records
 // the per-kernel timing events of an unlabelled run.
 template <class Mark>
-void fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* sel, const int* nloo, Mark mark) {
+void fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* sel, const int* nloo, Mark mark, bool chased = false) {
     const Dims& d = ctx->d;
     cudaStream_t st = ctx->stream;
-    launch_mean(d, ctx->colsum_part, ctx->colcnt_part, ctx->nsplit, ctx->mu, ctx->n, st);
-    mark(2);
-    launch_gram(d, ctx->xt, ctx->mu, ctx->nchunk_gram, ctx->gram_part, st);
-    mark(3);
+    // Unimodal passes centre the Gram products on a pilot point (the mean of the first Gram chunk) so that
+    // cmf_run_host can run the statistics chunk by chunk behind the upload; K2 removes the offset exactly.
+    // Both entry points do the same arithmetic, so their results are bitwise identical.
+    const bool pilot = sel == nullptr;
+    if (!chased) {
+        if (pilot) launch_mean(d, ctx->colsum_part, ctx->colcnt_part, ctx->spc, ctx->ctr, nullptr, st);
+        launch_mean(d, ctx->colsum_part, ctx->colcnt_part, ctx->nsplit, ctx->mu, ctx->n, st);
+        mark(2);
+        launch_gram(d, ctx->xt, pilot ? ctx->ctr : ctx->mu, ctx->nchunk_gram, ctx->lpc_gram, 0, ctx->nchunk_gram,
+                    ctx->gram_part, st);
+        mark(3);
+        ctx->launches += pilot ? 3 : 2;
+    } else {
+        launch_mean(d, ctx->colsum_part, ctx->colcnt_part, ctx->nsplit, ctx->mu, ctx->n, st);
+        ++ctx->launches;
+    }
     const bool loo = ctx->model == CMF_MODEL_LOOSHRINKAGE;
     const bool screen = loo && ctx->can_screen && !exact;
-    launch_eigen(d, ctx->gram_part, ctx->nchunk_gram, ctx->n, ctx->P, ctx->lam, ctx->slogT, ctx->status,
-                 ctx->sweeps, ctx->eigen_method, st);
+    launch_eigen(d, ctx->gram_part, ctx->nchunk_gram, ctx->n, ctx->mu, pilot ? ctx->ctr : nullptr, ctx->P, ctx->lam,
+                 ctx->slogT, ctx->status, ctx->sweeps, ctx->eigen_method, st);
     mark(4);
     launch_tables(d, ctx->n, nloo, ctx->alphas_d, ctx->model, ctx->P, ctx->lam, ctx->slogT, ctx->Pf, ctx->Wf,
                   ctx->logdet, ctx->beta, (screen && !ctx->use_screen5) ? ctx->Ws : nullptr, ctx->betaf, ctx->rsum,
                   (screen && !ctx->use_screen5) ? ctx->Ps : nullptr, st);
     mark(5);
-    ctx->launches += 4;
+    ctx->launches += 2;
     if (screen && ctx->use_screen5) {
         launch_screen5(d, ctx->xt, ctx->mu, ctx->n, nloo, ctx->alphas_d, ctx->P, ctx->lam, ctx->tab5, ctx->betaf,
                        ctx->nchunk_screen, ctx->fscreen, st);
@@ -191,7 +205,9 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
     if (timing && modes) cudaEventRecord(evs[0], st);
     mark(0);
     // ---- pass over every valid pixel: validity mask, column-major copy, column sums
+    const bool chased = blocks_ready != nullptr && !modes;
     if (blocks_ready) {
+        // one block = one Gram chunk: its repack and (unimodal) its Gram partial run as soon as its copy lands
         int line = 0;
         for (size_t b = 0; b < blocks_ready->size(); ++b) {
             const int lim = std::min(d.L, line + lines_per_block);
@@ -199,6 +215,15 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
             launch_repack(d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, line,
                           lim, nullptr, 1, st);
             ++ctx->launches;
+            if (chased) {
+                if (b == 0) {
+                    launch_mean(d, ctx->colsum_part, ctx->colcnt_part, ctx->spc, ctx->ctr, nullptr, st);
+                    ++ctx->launches;
+                }
+                launch_gram(d, ctx->xt, ctx->ctr, ctx->nchunk_gram, ctx->lpc_gram, (int)b, (int)b + 1,
+                            ctx->gram_part, st);
+                ++ctx->launches;
+            }
             line = lim;
         }
     } else {
@@ -208,7 +233,7 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
     }
     mark(1);
     if (!modes) {
-        fit_and_score(ctx, exact, nullptr, nullptr, mark);
+        fit_and_score(ctx, exact, nullptr, nullptr, mark, chased);
         launch_colstats(d, ctx->stat_part, ctx->nlanes, ctx->n, ctx->nodata, ctx->colstats, st);
         ++ctx->launches;
         mark(11);
@@ -368,7 +393,13 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     ctx->nsplit = repack_nsplit(d);
     ctx->lps = repack_lines_per_split(d, ctx->nsplit);
     ctx->nsplit = (d.L + ctx->lps - 1) / ctx->lps;
-    ctx->nchunk_gram = pick_chunks(d.S, d.L, 256, ctx->sm_count, 1);
+    {   // Gram chunks are whole repack splits (and upload blocks of cmf_run_host are whole Gram chunks)
+        const int want = pick_chunks(d.S, d.L, 256, ctx->sm_count, 1);
+        const int lpc0 = (d.L + want - 1) / want;
+        ctx->spc = std::max(1, (lpc0 + ctx->lps / 2) / ctx->lps);
+        ctx->lpc_gram = ctx->spc * ctx->lps;
+        ctx->nchunk_gram = (d.L + ctx->lpc_gram - 1) / ctx->lpc_gram;
+    }
     ctx->nchunk_loo = pick_chunks(d.S, d.L, 128, ctx->sm_count, 1);
     ctx->nlanes = score_plan(d, ctx->sm_count, &ctx->score_lpc);
     ctx->nchunk_screen = ctx->nchunk_loo;
@@ -389,6 +420,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     A_(dalloc(ctx, &ctx->colsum_part, (size_t)ctx->nsplit * d.S * d.DP));
     A_(dalloc(ctx, &ctx->colcnt_part, (size_t)ctx->nsplit * d.S));
     A_(dalloc(ctx, &ctx->mu, (size_t)d.S * d.DP));
+    A_(dalloc(ctx, &ctx->ctr, (size_t)d.S * d.DP));
     A_(dalloc(ctx, &ctx->n, (size_t)d.S));
     A_(dalloc(ctx, &ctx->gram_part, gram_part_elems(d, ctx->nchunk_gram)));
     A_(dalloc(ctx, &ctx->P, (size_t)d.S * d.DP * d.DP));
@@ -525,10 +557,9 @@ int cmf_run_host(cmf_ctx* ctx, const float* host_cube, double* mf_out, double* c
     int rc = ensure_own_slab(ctx);
     if (rc) return rc;
     const Dims& d = ctx->d;
-    // upload in blocks of whole repack splits on the copy stream; the repack pass chases the copies
-    const int splits_per_block = std::max(1, (ctx->nsplit + 7) / 8);
-    const int lines_per_block = splits_per_block * ctx->lps;
-    const int nblocks = (d.L + lines_per_block - 1) / lines_per_block;
+    // upload in blocks of one Gram chunk on the copy stream; the repack and Gram passes chase the copies
+    const int lines_per_block = ctx->lpc_gram;
+    const int nblocks = ctx->nchunk_gram;
     while ((int)ctx->blk_ev.size() < nblocks) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -559,8 +590,13 @@ int cmf_run_host(cmf_ctx* ctx, const float* host_cube, double* mf_out, double* c
     if (alpha_index_out)
         CK(cudaMemcpyAsync(alpha_index_out, ctx->mindex, (size_t)d.S * sizeof(int), cudaMemcpyDeviceToHost,
                            ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (!(flags & CMF_RUN_ASYNC)) CK(cudaStreamSynchronize(ctx->stream));
     return CMF_OK;
+}
+
+const char* cmf_screen_kernel(const cmf_ctx* ctx) {
+    if (!ctx || !ctx->have_problem || !ctx->can_screen || ctx->model != CMF_MODEL_LOOSHRINKAGE) return "";
+    return ctx->use_screen5 ? "loo_screen5_kernel" : "loo_screen_kernel";
 }
 
 size_t cmf_output_bytes(const cmf_ctx* ctx, int what) {

@@ -42,10 +42,12 @@ void launch_repack(const Dims& d, const float* slab, float* xt, uint8_t* mask, d
 int repack_lines_per_split(const Dims& d, int nsplit);
 void launch_mean(const Dims& d, const double* colsum_part, const int* colcnt_part, int nsplit,
                  double* mu, int* n, cudaStream_t st);
-void launch_gram(const Dims& d, const float* xt, const double* mu, int nchunk, double* gram_part,
-                 cudaStream_t st);
-void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, double* P, double* lam,
-                  double* slogT, int* status, int* sweeps, int method, cudaStream_t st);
+void launch_gram(const Dims& d, const float* xt, const double* ctr, int nchunk, int lpc, int chunk_lo,
+                 int chunk_hi, double* gram_part, cudaStream_t st);
+// ctr != NULL: the Gram partials are centred on ctr, the rank-one term n (mu-ctr)(mu-ctr)^T is removed here
+void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, const double* mu,
+                  const double* ctr, double* P, double* lam, double* slogT, int* status, int* sweeps, int method,
+                  cudaStream_t st);
 void launch_tables(const Dims& d, const int* n, const int* nloo, const double* alphas, int model, const double* P,
                    const double* lam, const double* slogT, double* Pf, double* Wf, double* logdet, double* beta,
                    float* Ws, float* betaf, double* rsum, float* Ps, cudaStream_t st);

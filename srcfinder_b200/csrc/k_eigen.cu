@@ -28,9 +28,17 @@ __device__ __forceinline__ void tri_unrank(int t, int& i, int& j) {
     j = t - ii * (ii + 1) / 2;
 }
 
+// sum_l (x-c)(x-c)^T = sum_l (x-mu)(x-mu)^T + n (mu-c)(mu-c)^T: the term the pilot-centred Gram pass leaves in
+__device__ __forceinline__ double pilot_term(const double* __restrict__ mu, const double* __restrict__ ctr,
+                                             long long base, int row, int col, int n) {
+    const double dr = mu[base + row] - ctr[base + row], dc = mu[base + col] - ctr[base + col];
+    return (double)n * dr * dc;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(512)
     eigen_kernel(const double* __restrict__ gram_part, int nchunk, const int* __restrict__ n_g, int D,
+        const double* __restrict__ mu_g, const double* __restrict__ ctr_g,
                  double* __restrict__ P_g, double* __restrict__ lam_g, double* __restrict__ slogT_g,
                  int* __restrict__ status_g, int* __restrict__ sweeps_g) {
     constexpr int DP = 8 * NT, LD = DP + 1, NTRI = NT * (NT + 1) / 2;
@@ -69,8 +77,9 @@ __global__ void __launch_bounds__(512)
         tri_unrank(t, ti, tj);
         double v = 0.0;
         for (int c = 0; c < nchunk; ++c) v += gram_part[((long long)s * nchunk + c) * NTRI * 64 + idx];
-        v *= inv_nm1;
         const int row = 8 * ti + (lane >> 2), col = 8 * tj + 2 * (lane & 3) + e;
+        if (ctr_g != nullptr) v -= pilot_term(mu_g, ctr_g, (long long)s * DP, row, col, n);
+        v *= inv_nm1;
         Am[row * LD + col] = v;
         if (ti != tj) Am[col * LD + row] = v;
     }
@@ -209,6 +218,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 template <int NT>
 __global__ void __launch_bounds__(kQlThreads)
     eigen_ql_kernel(const double* __restrict__ gram_part, int nchunk, const int* __restrict__ n_g, int D,
+        const double* __restrict__ mu_g, const double* __restrict__ ctr_g,
                     double* __restrict__ P_g, double* __restrict__ lam_g, double* __restrict__ slogT_g,
                     int* __restrict__ status_g, int* __restrict__ sweeps_g) {
     constexpr int DP = 8 * NT, LD = DP + 1, NTRI = NT * (NT + 1) / 2;
@@ -244,8 +254,9 @@ __global__ void __launch_bounds__(kQlThreads)
         tri_unrank(t, ti, tj);
         double v = 0.0;
         for (int c = 0; c < nchunk; ++c) v += gram_part[((long long)s * nchunk + c) * NTRI * 64 + idx];
-        v *= inv_nm1;
         const int row = 8 * ti + (ln >> 2), col = 8 * tj + 2 * (ln & 3) + ee;
+        if (ctr_g != nullptr) v -= pilot_term(mu_g, ctr_g, (long long)s * DP, row, col, n);
+        v *= inv_nm1;
         a[row * LD + col] = v;
         if (ti != tj) a[col * LD + row] = v;
     }
@@ -684,26 +695,28 @@ __global__ void __launch_bounds__(256)
 
 // ---------------------------------------------------------------------------------------- launchers
 template <int NT>
-static void launch_eigen_t(const Dims& d, const double* gram_part, int nchunk, const int* n, double* P,
-                           double* lam, double* slogT, int* status, int* sweeps, int method, cudaStream_t st) {
+static void launch_eigen_t(const Dims& d, const double* gram_part, int nchunk, const int* n, const double* mu,
+                           const double* ctr, double* P, double* lam, double* slogT, int* status, int* sweeps,
+                           int method, cudaStream_t st) {
     constexpr int DP = 8 * NT, LD = DP + 1;
     if (method == 1) {
         const size_t smem = (size_t)(2 * DP * LD + 2 * DP + 2 * (DP / 2 + 1)) * sizeof(double);
         cudaFuncSetAttribute(eigen_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        eigen_kernel<NT><<<d.S, 512, smem, st>>>(gram_part, nchunk, n, d.D, P, lam, slogT, status, sweeps);
+        eigen_kernel<NT><<<d.S, 512, smem, st>>>(gram_part, nchunk, n, d.D, mu, ctr, P, lam, slogT, status, sweeps);
     } else {
         const size_t smem = (size_t)(DP * LD + 5 * DP + 8) * sizeof(double);
         cudaFuncSetAttribute(eigen_ql_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        eigen_ql_kernel<NT><<<d.S, kQlThreads, smem, st>>>(gram_part, nchunk, n, d.D, P, lam, slogT, status, sweeps);
+        eigen_ql_kernel<NT><<<d.S, kQlThreads, smem, st>>>(gram_part, nchunk, n, d.D, mu, ctr, P, lam, slogT, status, sweeps);
     }
 }
 
 // method: 0 = Householder + implicit QL (default), 1 = cyclic Jacobi (cross-check)
-void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, double* P, double* lam,
-                  double* slogT, int* status, int* sweeps, int method, cudaStream_t st) {
+void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, const double* mu,
+                  const double* ctr, double* P, double* lam, double* slogT, int* status, int* sweeps, int method,
+                  cudaStream_t st) {
     switch (d.NT) {
 #define CMF_CASE(k) \
-    case k: launch_eigen_t<k>(d, gram_part, nchunk, n, P, lam, slogT, status, sweeps, method, st); break;
+    case k: launch_eigen_t<k>(d, gram_part, nchunk, n, mu, ctr, P, lam, slogT, status, sweeps, method, st); break;
         CMF_CASE(1) CMF_CASE(2) CMF_CASE(3) CMF_CASE(4) CMF_CASE(5) CMF_CASE(6)
         CMF_CASE(7) CMF_CASE(8) CMF_CASE(9) CMF_CASE(10) CMF_CASE(11) CMF_CASE(12)
 #undef CMF_CASE

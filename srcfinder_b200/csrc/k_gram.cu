@@ -1,4 +1,5 @@
-// K1: per-column centred Gram matrix  G = sum_l (x_l - mu)(x_l - mu)^T  on the FP64 tensor path.
+// K1: per-column centred Gram matrix  G = sum_l (x_l - c)(x_l - c)^T  on the FP64 tensor path (c = column mean,
+// or a pilot centre near it whose offset K2 removes exactly: sum (x-c)(x-c)^T - n (mu-c)(mu-c)^T).
 //
 // Replaces numpy.cov in the reference (cmf/robust_mf.py:52-70, called at :98 and :130).  Precision
 // scheme: FP32 radiances converted to FP64, mean removed in FP64, products and accumulation in
@@ -105,7 +106,7 @@ __device__ __forceinline__ void gram_warp(const float* __restrict__ col_base, co
 template <int NT>
 __global__ void __launch_bounds__(kGramWarps * 32, 1)
     gram_kernel(const float* __restrict__ xt, const double* __restrict__ mu_g, int L, int lines_per_chunk,
-                double* __restrict__ gram_part) {
+                int chunk_lo, int nchunk, double* __restrict__ gram_part) {
     constexpr int DP = 8 * NT, TL = kGramTL, NS = kGramNS, NTRI = NT * (NT + 1) / 2;
     constexpr int NROLE = (NT > 9) ? 2 : 1;
     constexpr int RSPLIT = (NT > 9) ? 8 : NT;   // role 0: tile rows [0,RSPLIT), role 1: [RSPLIT,NT)
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kGramWarps * 32, 1)
     double* mu_s = red + NTRI * 64;                                       // [DP]
     uint64_t* bars = reinterpret_cast<uint64_t*>(mu_s + DP);              // [warps][NS]
 
-    const int s = blockIdx.x, chunk = blockIdx.y;
+    const int s = blockIdx.x, chunk = chunk_lo + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c_begin = chunk * lines_per_chunk;
     const int c_end = min(L, c_begin + lines_per_chunk);
@@ -146,29 +147,31 @@ __global__ void __launch_bounds__(kGramWarps * 32, 1)
                                       warp, lane);
     }
     __syncthreads();
-    double* out = gram_part + ((long long)s * gridDim.y + chunk) * NTRI * 64;
+    double* out = gram_part + ((long long)s * nchunk + chunk) * NTRI * 64;
     for (int i = threadIdx.x; i < NTRI * 64; i += blockDim.x) out[i] = red[i];
 }
 
 size_t gram_part_elems(const Dims& d, int nchunk) { return (size_t)d.S * nchunk * ntri(d.NT) * 64; }
 
 template <int NT>
-static void launch_gram_t(const Dims& d, const float* xt, const double* mu, int nchunk, double* gram_part,
-                          cudaStream_t st) {
+static void launch_gram_t(const Dims& d, const float* xt, const double* mu, int nchunk, int lpc, int chunk_lo,
+                          int chunk_hi, double* gram_part, cudaStream_t st) {
     constexpr int DP = 8 * NT, NTRI = NT * (NT + 1) / 2;
     const size_t smem = (size_t)kGramWarps * kGramNS * kGramTL * DP * sizeof(float) +
                         (size_t)(NTRI * 64 + DP) * sizeof(double) + kGramWarps * kGramNS * sizeof(uint64_t);
     cudaFuncSetAttribute(gram_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int lpc = (d.L + nchunk - 1) / nchunk;
-    lpc = (lpc + kGramTL - 1) / kGramTL * kGramTL;
-    dim3 grid(d.S, nchunk);
-    gram_kernel<NT><<<grid, kGramWarps * 32, smem, st>>>(xt, mu, d.L, lpc, gram_part);
+    if (chunk_hi <= chunk_lo) return;
+    dim3 grid(d.S, chunk_hi - chunk_lo);
+    gram_kernel<NT><<<grid, kGramWarps * 32, smem, st>>>(xt, mu, d.L, lpc, chunk_lo, nchunk, gram_part);
 }
 
-void launch_gram(const Dims& d, const float* xt, const double* mu, int nchunk, double* gram_part,
-                 cudaStream_t st) {
+// Chunks [chunk_lo, chunk_hi) of `nchunk` chunks of `lpc` lines each (lpc a multiple of the Gram tile);
+// `ctr` is the point the products are centred on (the column mean, or the pilot centre of the chased pass).
+void launch_gram(const Dims& d, const float* xt, const double* ctr, int nchunk, int lpc, int chunk_lo,
+                 int chunk_hi, double* gram_part, cudaStream_t st) {
+    const double* mu = ctr;
     switch (d.NT) {
-#define CMF_CASE(n) case n: launch_gram_t<n>(d, xt, mu, nchunk, gram_part, st); break;
+#define CMF_CASE(n) case n: launch_gram_t<n>(d, xt, mu, nchunk, lpc, chunk_lo, chunk_hi, gram_part, st); break;
         CMF_CASE(1) CMF_CASE(2) CMF_CASE(3) CMF_CASE(4) CMF_CASE(5) CMF_CASE(6)
         CMF_CASE(7) CMF_CASE(8) CMF_CASE(9) CMF_CASE(10) CMF_CASE(11) CMF_CASE(12)
 #undef CMF_CASE

@@ -180,6 +180,8 @@ __global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ s
 }
 
 // ---------------------------------------------------------------------------------------- K0b
+// Splits [0, nsplit) give the column mean; the same kernel over the first `nsplit` = pilot splits gives the
+// pilot centre of the Gram pass (n == NULL: the count is not stored).
 __global__ void mean_kernel(const double* __restrict__ colsum_part, const int* __restrict__ colcnt_part,
                             int nsplit, int S, int DP, double* __restrict__ mu, int* __restrict__ n) {
     const int s = blockIdx.x;
@@ -190,7 +192,7 @@ __global__ void mean_kernel(const double* __restrict__ colsum_part, const int* _
         for (int k = 0; k < nsplit; ++k) a += colsum_part[((long long)k * S + s) * DP + b];
         mu[(long long)s * DP + b] = cnt > 0 ? a / (double)cnt : 0.0;   // numpy mean: sum / n
     }
-    if (threadIdx.x == 0) n[s] = cnt;
+    if (threadIdx.x == 0 && n != nullptr) n[s] = cnt;
 }
 
 // ---------------------------------------------------------------------------------------- K5
@@ -474,7 +476,7 @@ static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t
 
 int repack_lines_per_split(const Dims& d, int nsplit) {
     int lps = (d.L + nsplit - 1) / nsplit;
-    return (lps + kRepackLT - 1) / kRepackLT * kRepackLT;
+    return (lps + kGramTL - 1) / kGramTL * kGramTL;    // Gram chunks are whole splits made of whole Gram tiles
 }
 
 // Repack lines [line_base, line_limit); line_base must be a multiple of lines-per-split so that the

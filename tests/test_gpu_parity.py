@@ -239,6 +239,36 @@ def test_device_resident_full_cube_and_run_host():
         assert eng.launch_count() >= 8
 
 
+def test_async_host_calls_on_two_contexts():
+    """cmf_run_host(CMF_RUN_ASYNC) on two contexts used alternately (the streaming mode bench.py's e2e leg times)
+    returns the same bits as the synchronous call."""
+    import torch
+    cubes = [synth.make_cube(480, 10, seed=71 + i, bad_pixels=bool(i)) for i in range(3)]
+    active = [351, 422]
+    ab = _abscf(active)
+    L, B, S = cubes[0].shape
+    pinned = [torch.from_numpy(c).pin_memory() for c in cubes]
+    want = []
+    with ColumnwiseMF(L, B, S, active, ab) as eng:
+        for c in cubes:
+            mf = np.empty((L, S)); ai = np.empty(S, dtype=np.int32)
+            eng.run_host(c.ctypes.data, mf.ctypes.data, None, ai.ctypes.data)
+            want.append((mf, ai))
+    engs = [ColumnwiseMF(L, B, S, active, ab) for _ in range(2)]
+    outs = [(torch.empty((L, S), dtype=torch.float64).pin_memory(), torch.empty(S, dtype=torch.int32).pin_memory())
+            for _ in range(3)]
+    for i in range(3):
+        e = engs[i % 2]
+        e.sync()
+        e.run_host(pinned[i].data_ptr(), outs[i][0].data_ptr(), None, outs[i][1].data_ptr(), wait=False)
+    for e in engs:
+        e.sync()
+        e.close()
+    for (mf, ai), (gmf, gai) in zip(want, outs):
+        assert np.array_equal(gmf.numpy(), mf, equal_nan=True)
+        assert np.array_equal(gai.numpy(), ai)
+
+
 def test_error_paths():
     from srcfinder_b200 import CmfError
     ab = _abscf([351, 422])
