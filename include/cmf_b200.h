@@ -66,7 +66,10 @@ enum {
                                                   selection is exact while the screening error stays below half of it */
     CMF_OUT_CLUSTER_ID = 13,  /* int16  [L][S]   _bgmeta band 0 (:327): cluster label, negated when rejected; labelled runs */
     CMF_OUT_ALPHA_IMAGE = 14, /* int16  [L][S]   _bgmeta band 1 (:365): alpha index of the mode that scored the pixel */
-    CMF_OUT_MODE_LIST = 15    /* int8   [S][32]  the column's mode list (bgulab, :313-332); 127 = past the end */
+    CMF_OUT_MODE_LIST = 15,   /* int8   [S][32]  the column's mode list (bgulab, :313-332); 127 = past the end */
+    CMF_OUT_LABELS = 16,      /* int32  [L][S]   cluster labels in use (given by cmf_set_labels or found by cmf_set_clustering) */
+    CMF_OUT_PCA = 17,         /* double [S][L][pcadim] projections the on-device k-means partitioned (:311) */
+    CMF_OUT_KMEANS_ITERS = 18 /* int32  [S]      reassignment passes the k-means needed */
 };
 
 typedef struct cmf_problem {
@@ -107,6 +110,20 @@ int cmf_bind_device_slab(cmf_ctx* ctx, const float* dev_slab, int64_t line_pitch
  * per-mode fits with n = the column's valid count (:355-356), the overwrite order (:339-386), the inlier
  * statistics (:388-391) -- runs on the device.  labels == NULL returns to the unimodal path.  Host pointer. */
 int cmf_set_labels(cmf_ctx* ctx, const int32_t* labels, int kmodes, int reject_min);
+
+/* The same, with the partition found on the device (:308-313): the column's valid pixels are projected on the
+ * `pcadim` leading eigenvectors of the column covariance and partitioned by a k-means with `kmodes` clusters.
+ * The reference's MiniBatchKMeans is unseeded, so its partition is not reproducible; this one is deterministic
+ * (rule in csrc/k_cluster.cu, restated in oracle/cluster_oracle.py): components by descending eigenvalue, signed
+ * so that v . mu >= 0; projections quantised to 2^-24 of the column's range and cluster sums kept in 64-bit
+ * integers; initial partition = kmodes equal-count slices of component 1; at most max_iter (<= 0: 100) Lloyd
+ * iterations.  kmodes <= 1 returns to the unimodal path.  CMF_OUT_LABELS returns the labels found. */
+int cmf_set_clustering(cmf_ctx* ctx, int kmodes, int pcadim, int reject_min, int max_iter);
+
+/* -f (:161, :358): in a labelled / clustered looshrinkage run the shrinkage target of every mode fit is the
+ * covariance of the whole column instead of diag(S) (looshrinkage's I_reg, :100, :131).  On the device this is a
+ * Cholesky whitening ahead of the same eigen-solve.  No effect on unimodal runs (the reference tests bgmodes > 1). */
+int cmf_set_regfull(cmf_ctx* ctx, int enable);
 
 /* ---- compute: the whole column loop (:297-392) for every column, no host round trip ---- */
 enum {

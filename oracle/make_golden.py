@@ -55,6 +55,11 @@ CASES = [
          lib="ang_ch4_unit.txt", np_seed=5, bright_lines=(100, 140)),
     dict(name="modes_k2_600x3", L=600, S=3, seed=22, kw={}, flags=["-k", "2", "-m"], lib="ang_ch4_unit.txt",
          np_seed=7),
+    # -f: every mode fit is regularised with the covariance of the whole column (:358, looshrinkage's I_reg)
+    dict(name="modes_k3rf_900x4", L=900, S=4, seed=23, kw=dict(bad_pixels=True),
+         flags=["-k", "3", "-r", "-f", "-m"], lib="ang_ch4_unit.txt", np_seed=9, bright_lines=(300, 340)),
+    dict(name="modes_k2f_500x3", L=500, S=3, seed=24, kw={}, flags=["-k", "2", "-f", "-m"],
+         lib="ang_ch4_unit.txt", np_seed=11),
 ]
 
 

@@ -114,6 +114,27 @@ class ColumnwiseMF(object):
         self._check(self._lib.cmf_set_labels(self._ctx, C.c_void_p(lab.ctypes.data), k, int(reject_min)))
         self._labelled = True
 
+    def set_clustering(self, kmodes, pcadim=6, reject_min=0, max_iter=100):
+        """Partition every column on the device (PCA + k-means, cmf/robust_mf.py:308-313; deterministic rule in
+        csrc/k_cluster.cu).  ``kmodes`` <= 1 returns to the unimodal path."""
+        self._check(self._lib.cmf_set_clustering(self._ctx, int(kmodes), int(pcadim), int(reject_min), int(max_iter)))
+        self._labelled = int(kmodes) > 1
+        self.pcadim = int(pcadim)
+
+    def set_regfull(self, enable=True):
+        """``-f``: regularise every mode fit with the covariance of the whole column (cmf/robust_mf.py:358)."""
+        self._check(self._lib.cmf_set_regfull(self._ctx, 1 if enable else 0))
+
+    def labels(self):
+        return self._get(_lib.OUT_LABELS, np.int32, (self.L, self.S))
+
+    def pca(self):
+        """(S, L, pcadim) projections the on-device k-means partitioned (0 for invalid pixels)."""
+        return self._get(_lib.OUT_PCA, np.float64, (self.S, self.L, self.pcadim))
+
+    def kmeans_iters(self):
+        return self._get(_lib.OUT_KMEANS_ITERS, np.int32, (self.S,))
+
     def cluster_id(self):
         return self._get(_lib.OUT_CLUSTER_ID, np.int16, (self.L, self.S))
 
@@ -217,7 +238,8 @@ class ColumnwiseMF(object):
 
 
 def cmf_cube(cube_lbs, abscf, active, model="looshrinkage", reflectance=False, alphas=None,
-             nodata=-9999.0, device=0, exact=False, labels=None, reject_min=0):
+             nodata=-9999.0, device=0, exact=False, labels=None, reject_min=0, regfull=False, kmodes=1,
+             pcadim=6):
     """One-shot convenience: same inputs/outputs as the oracle's ``cmf_cube`` (for parity tests)."""
     L, B, S = cube_lbs.shape
     with ColumnwiseMF(L, B, S, active, abscf, model=model, reflectance=reflectance, alphas=alphas,
@@ -225,10 +247,16 @@ def cmf_cube(cube_lbs, abscf, active, model="looshrinkage", reflectance=False, a
         eng.upload(cube_lbs)
         if labels is not None:
             eng.set_labels(labels, reject_min=reject_min)
+        elif kmodes > 1:
+            eng.set_clustering(kmodes, pcadim=pcadim, reject_min=reject_min)
+        if regfull:
+            eng.set_regfull(True)
         eng.run(exact=exact)
         res = eng.results()
-        if labels is not None:
+        if labels is not None or kmodes > 1:
             res["cluster_id"], res["alpha_image"] = eng.cluster_id(), eng.alpha_image()
+        if labels is None and kmodes > 1:
+            res["labels"], res["pca"], res["kmeans_iters"] = eng.labels(), eng.pca(), eng.kmeans_iters()
         if model == "looshrinkage":
             res["nll"] = eng.nll()
         return res

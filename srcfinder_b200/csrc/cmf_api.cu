@@ -67,6 +67,12 @@ struct cmf_ctx {
     int *nentries = nullptr, *nuse = nullptr;
     uint8_t *sel = nullptr, *inlier = nullptr;
     int16_t *cluster_img = nullptr, *alpha_img = nullptr;
+    // on-device partition (cmf_set_clustering) and the -f regulariser (cmf_set_regfull)
+    bool auto_cluster = false, regfull = false;
+    int pcadim = 6, km_max_iter = 100, y_pd = 0;
+    double *gram_full = nullptr, *vtop = nullptr, *ypca = nullptr;
+    int *pick = nullptr, *km_iters = nullptr;
+    uint8_t* lab8 = nullptr;
     bool can_screen = false;
     double screen_tol = 2.0e-5;   // relative to the screened part of nll; measured error is <= 2.5e-6
     int nchunk_screen = 1;
@@ -138,8 +144,11 @@ void fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* sel, const int* nloo
     }
     const bool loo = ctx->model == CMF_MODEL_LOOSHRINKAGE;
     const bool screen = loo && ctx->can_screen && !exact;
+    // -f: the shrinkage target of a mode fit is the covariance of the whole column (:100, :358)
+    const bool full_target = sel != nullptr && ctx->regfull && ctx->model == CMF_MODEL_LOOSHRINKAGE;
     launch_eigen(d, ctx->gram_part, ctx->nchunk_gram, ctx->n, ctx->mu, pilot ? ctx->ctr : nullptr, ctx->P, ctx->lam,
-                 ctx->slogT, ctx->status, ctx->sweeps, ctx->eigen_method, st);
+                 ctx->slogT, ctx->status, ctx->sweeps, ctx->eigen_method, st, full_target ? 2 : 0,
+                 full_target ? ctx->gram_full : nullptr, full_target ? ctx->nuse : nullptr);
     mark(4);
     launch_tables(d, ctx->n, nloo, ctx->alphas_d, ctx->model, ctx->P, ctx->lam, ctx->slogT, ctx->Pf, ctx->Wf,
                   ctx->logdet, ctx->beta, (screen && !ctx->use_screen5) ? ctx->Ws : nullptr, ctx->betaf, ctx->rsum,
@@ -199,7 +208,7 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
         evs = ctx->ev_sets[ctx->timed_runs].data();
         ++ctx->timed_runs;
     }
-    const bool modes = ctx->have_labels;
+    const bool modes = ctx->have_labels || ctx->auto_cluster;
     auto mark = [&](int i) { if (timing && !modes) cudaEventRecord(evs[i], st); };
     auto no_mark = [](int) {};
     if (timing && modes) cudaEventRecord(evs[0], st);
@@ -241,6 +250,19 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
         // ---- background modes (cmf/robust_mf.py:306-344): one fit-and-score pass per mode-list entry
         const size_t LS = (size_t)d.L * d.S;
         launch_mean(d, ctx->colsum_part, ctx->colcnt_part, ctx->nsplit, ctx->mu, ctx->nuse, st);   // nuse (:302)
+        if (ctx->auto_cluster || ctx->regfull) {
+            // scatter of the whole column about its mean: the PCA basis (:310) and the -f target (:358)
+            launch_gram(d, ctx->xt, ctx->mu, ctx->nchunk_gram, ctx->lpc_gram, 0, ctx->nchunk_gram, ctx->gram_full, st);
+            ++ctx->launches;
+        }
+        if (ctx->auto_cluster) {
+            launch_eigen(d, ctx->gram_full, ctx->nchunk_gram, ctx->nuse, ctx->mu, nullptr, ctx->P, ctx->lam, ctx->slogT,
+                         ctx->status, ctx->sweeps, 0, st, 1);
+            launch_pca_kmeans(d, ctx->xt, ctx->mask, ctx->mu, ctx->nuse, ctx->P, ctx->lam, ctx->pcadim, ctx->kmodes,
+                              ctx->km_max_iter, ctx->pick, ctx->vtop, ctx->ypca, ctx->lab8, ctx->labels_d,
+                              ctx->km_iters, st);
+            ctx->launches += 4;
+        }
         launch_modes(d, ctx->labels_d, ctx->mask, ctx->reject_min, ctx->entries, ctx->rejmask, ctx->nentries, st);
         launch_fill_f64(ctx->mf, (long long)LS, ctx->nodata, st);
         CK(cudaMemsetAsync(ctx->alpha_img, 0, LS * sizeof(int16_t), st));
@@ -277,6 +299,27 @@ int ensure_own_slab(cmf_ctx* ctx) {
     return CMF_OK;
 }
 
+int ensure_mode_buffers(cmf_ctx* ctx) {
+    if (ctx->labels_d) return CMF_OK;
+    const size_t LS = (size_t)ctx->d.L * ctx->d.S;
+    cudaError_t e = cudaSuccess;
+    auto A_ = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    A_(dalloc(ctx, &ctx->labels_d, LS));
+    A_(dalloc(ctx, &ctx->sel, LS));
+    A_(dalloc(ctx, &ctx->inlier, LS));
+    A_(dalloc(ctx, &ctx->cluster_img, LS));
+    A_(dalloc(ctx, &ctx->alpha_img, LS));
+    if (e != cudaSuccess) return fail(ctx, CMF_E_NOMEM, std::string("label buffers: ") + cudaGetErrorString(e));
+    return CMF_OK;
+}
+
+int ensure_full_gram(cmf_ctx* ctx) {
+    if (ctx->gram_full) return CMF_OK;
+    if (dalloc(ctx, &ctx->gram_full, gram_part_elems(ctx->d, ctx->nchunk_gram)) != cudaSuccess)
+        return fail(ctx, CMF_E_NOMEM, "full-column Gram buffer");
+    return CMF_OK;
+}
+
 struct OutDesc { void* ptr; size_t bytes; };
 
 OutDesc out_desc(const cmf_ctx* c, int what) {
@@ -296,9 +339,12 @@ OutDesc out_desc(const cmf_ctx* c, int what) {
         case CMF_OUT_SWEEPS: return {c->sweeps, (size_t)d.S * sizeof(int)};
         case CMF_OUT_NCAND: return {c->ncand, (size_t)d.S * sizeof(int)};
         case CMF_OUT_SCREEN_TOL: return {c->tol_col, (size_t)d.S * sizeof(double)};
-        case CMF_OUT_CLUSTER_ID: return {c->cluster_img, c->have_labels ? LS * sizeof(int16_t) : 0};
-        case CMF_OUT_ALPHA_IMAGE: return {c->alpha_img, c->have_labels ? LS * sizeof(int16_t) : 0};
+        case CMF_OUT_CLUSTER_ID: return {c->cluster_img, c->cluster_img ? LS * sizeof(int16_t) : 0};
+        case CMF_OUT_ALPHA_IMAGE: return {c->alpha_img, c->alpha_img ? LS * sizeof(int16_t) : 0};
         case CMF_OUT_MODE_LIST: return {c->entries, (size_t)d.S * kMaxLabels};
+        case CMF_OUT_LABELS: return {c->labels_d, c->labels_d ? LS * sizeof(int32_t) : 0};
+        case CMF_OUT_PCA: return {c->ypca, c->auto_cluster ? LS * c->pcadim * sizeof(double) : 0};
+        case CMF_OUT_KMEANS_ITERS: return {c->km_iters, c->auto_cluster ? (size_t)d.S * sizeof(int) : 0};
         default: return {nullptr, 0};
     }
 }
@@ -380,6 +426,9 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     ctx->have_labels = false;
     ctx->labels_d = nullptr; ctx->sel = nullptr; ctx->inlier = nullptr; ctx->cluster_img = nullptr;
     ctx->alpha_img = nullptr;
+    ctx->auto_cluster = false; ctx->regfull = false; ctx->y_pd = 0;
+    ctx->gram_full = nullptr; ctx->vtop = nullptr; ctx->ypca = nullptr; ctx->pick = nullptr;
+    ctx->km_iters = nullptr; ctx->lab8 = nullptr;
     Dims& d = ctx->d;
     d.L = p->lines; d.S = p->samples; d.D = D; d.NT = NT; d.DP = 8 * NT;
     d.A = loo ? p->num_alphas : 1;
@@ -510,28 +559,69 @@ int cmf_set_labels(cmf_ctx* ctx, const int32_t* labels, int kmodes, int reject_m
     if (!ctx) return CMF_E_ARG;
     if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_set_labels before cmf_set_problem");
     CK(cudaSetDevice(ctx->device));
-    if (labels == nullptr) { ctx->have_labels = false; return CMF_OK; }
+    if (labels == nullptr) { ctx->have_labels = false; ctx->auto_cluster = false; return CMF_OK; }
     if (kmodes < 1 || kmodes > kMaxLabels) return fail(ctx, CMF_E_ARG, "kmodes must be 1..32");
     const Dims& d = ctx->d;
     const size_t LS = (size_t)d.L * d.S;
     for (size_t i = 0; i < LS; ++i)
         if (labels[i] < 0 || labels[i] >= kmodes)
             return fail(ctx, CMF_E_ARG, "labels must lie in 0..kmodes-1 (rejection is derived on the device)");
-    if (!ctx->labels_d) {
-        cudaError_t e = cudaSuccess;
-        auto A_ = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-        A_(dalloc(ctx, &ctx->labels_d, LS));
-        A_(dalloc(ctx, &ctx->sel, LS));
-        A_(dalloc(ctx, &ctx->inlier, LS));
-        A_(dalloc(ctx, &ctx->cluster_img, LS));
-        A_(dalloc(ctx, &ctx->alpha_img, LS));
-        if (e != cudaSuccess) return fail(ctx, CMF_E_NOMEM, std::string("label buffers: ") + cudaGetErrorString(e));
-    }
+    int rc = ensure_mode_buffers(ctx);
+    if (rc) return rc;
+    ctx->auto_cluster = false;
     CK(cudaMemcpyAsync(ctx->labels_d, labels, LS * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->kmodes = kmodes;
     ctx->reject_min = reject_min > 0 ? reject_min : 0;
     ctx->have_labels = true;
+    return CMF_OK;
+}
+
+int cmf_set_clustering(cmf_ctx* ctx, int kmodes, int pcadim, int reject_min, int max_iter) {
+    if (!ctx) return CMF_E_ARG;
+    if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_set_clustering before cmf_set_problem");
+    CK(cudaSetDevice(ctx->device));
+    if (kmodes <= 1) { ctx->auto_cluster = false; ctx->have_labels = false; return CMF_OK; }
+    if (kmodes > kMaxLabels) return fail(ctx, CMF_E_ARG, "kmodes must be 1..32");
+    const Dims& d = ctx->d;
+    if (pcadim < 1 || pcadim > kMaxPcaDim || pcadim > d.D)
+        return fail(ctx, CMF_E_ARG, "pcadim must be 1..min(16, active bands)");
+    int rc = ensure_mode_buffers(ctx);
+    if (rc) return rc;
+    rc = ensure_full_gram(ctx);
+    if (rc) return rc;
+    const size_t LS = (size_t)d.L * d.S;
+    if (ctx->y_pd < pcadim) {      // (re)allocate the projection buffer; smaller requests reuse it
+        cudaError_t e = cudaSuccess;
+        auto A_ = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+        A_(dalloc(ctx, &ctx->ypca, LS * pcadim));
+        if (!ctx->lab8) {
+            A_(dalloc(ctx, &ctx->lab8, LS));
+            A_(dalloc(ctx, &ctx->pick, (size_t)d.S * kMaxPcaDim));
+            A_(dalloc(ctx, &ctx->vtop, (size_t)d.S * d.DP * kMaxPcaDim));
+            A_(dalloc(ctx, &ctx->km_iters, (size_t)d.S));
+        }
+        if (e != cudaSuccess) return fail(ctx, CMF_E_NOMEM, std::string("clustering buffers: ") + cudaGetErrorString(e));
+        ctx->y_pd = pcadim;
+    }
+    ctx->kmodes = kmodes;
+    ctx->pcadim = pcadim;
+    ctx->reject_min = reject_min > 0 ? reject_min : 0;
+    ctx->km_max_iter = max_iter > 0 ? max_iter : 100;
+    ctx->auto_cluster = true;
+    ctx->have_labels = false;
+    return CMF_OK;
+}
+
+int cmf_set_regfull(cmf_ctx* ctx, int enable) {
+    if (!ctx) return CMF_E_ARG;
+    if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_set_regfull before cmf_set_problem");
+    CK(cudaSetDevice(ctx->device));
+    if (enable) {
+        int rc = ensure_full_gram(ctx);
+        if (rc) return rc;
+    }
+    ctx->regfull = enable != 0;
     return CMF_OK;
 }
 

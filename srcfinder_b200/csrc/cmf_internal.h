@@ -14,6 +14,7 @@ constexpr int kLooMT = 2;           // 8-pixel m-tiles per LOO pass
 constexpr int kScoreLines = 8;      // lines per thread in the scoring pass (scalar kernel)
 constexpr int kMaxLabels = 32;      // background-mode labels are 0 .. kMaxLabels-1
 constexpr int kModeNone = 127;      // mode-list slot past the end of a column's list
+constexpr int kMaxPcaDim = 16;      // --pcadim upper bound of the on-device partition
 
 // column status bits (per cross-track column)
 enum : int {
@@ -47,7 +48,7 @@ void launch_gram(const Dims& d, const float* xt, const double* ctr, int nchunk, 
 // ctr != NULL: the Gram partials are centred on ctr, the rank-one term n (mu-ctr)(mu-ctr)^T is removed here
 void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, const double* mu,
                   const double* ctr, double* P, double* lam, double* slogT, int* status, int* sweeps, int method,
-                  cudaStream_t st);
+                  cudaStream_t st, int target = 0, const double* gramT_part = nullptr, const int* nT = nullptr);
 void launch_tables(const Dims& d, const int* n, const int* nloo, const double* alphas, int model, const double* P,
                    const double* lam, const double* slogT, double* Pf, double* Wf, double* logdet, double* beta,
                    float* Ws, float* betaf, double* rsum, float* Ps, cudaStream_t st);
@@ -83,6 +84,10 @@ void launch_members(const Dims& d, const int32_t* labels, const uint8_t* mask, i
                     const uint32_t* rejmask, uint8_t* sel, int16_t* cluster_img, uint8_t* inlier,
                     cudaStream_t st);
 void launch_fill_f64(double* p, long long n, double v, cudaStream_t st);
+// PCA projection (P, lam = eigenvectors / eigenvalues of the column covariance, launch_eigen target 1) + k-means
+void launch_pca_kmeans(const Dims& d, const float* xt, const uint8_t* mask, const double* mu, const int* n,
+                       const double* P, const double* lam, int pcadim, int k, int max_iter, int* pick,
+                       double* vtop, double* y, uint8_t* lab8, int32_t* labels, int* iters, cudaStream_t st);
 void launch_colstats_modes(const Dims& d, const double* mf, const uint8_t* inlier, const int* nuse,
                            double nodata, double* colstats, cudaStream_t st);
 int score_plan(const Dims& d, int sm_count, int* lines_per_cta);

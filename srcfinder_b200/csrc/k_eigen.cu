@@ -215,12 +215,21 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return t;
 }
 
-template <int NT>
+// MODE selects the shrinkage target T the column covariance S is whitened with before the eigen-solve:
+//   kEigDiag  T = diag(S) (the default target, :100): R = T^-1/2 S T^-1/2, P = T^-1/2 V
+//   kEigNone  T = I: plain eigenvectors of the covariance (the PCA of the multimodal partition, :310-311)
+//   kEigFull  T = covariance of the whole column (-f, :100 with I_reg, :358): T = L L^T (Cholesky in shared
+//             memory), R = L^-1 S L^-T, P = L^-T V, log det T = 2 sum log L_jj.  Every downstream formula
+//             (G_alpha^-1 = P (n beta Lam + alpha)^-1 P^T, C^-1 = P ((1-alpha) Lam + alpha)^-1 P^T) is unchanged.
+enum { kEigDiag = 0, kEigNone = 1, kEigFull = 2 };
+
+template <int NT, int MODE>
 __global__ void __launch_bounds__(kQlThreads)
     eigen_ql_kernel(const double* __restrict__ gram_part, int nchunk, const int* __restrict__ n_g, int D,
         const double* __restrict__ mu_g, const double* __restrict__ ctr_g,
                     double* __restrict__ P_g, double* __restrict__ lam_g, double* __restrict__ slogT_g,
-                    int* __restrict__ status_g, int* __restrict__ sweeps_g) {
+                    int* __restrict__ status_g, int* __restrict__ sweeps_g,
+                    const double* __restrict__ gramT_part, const int* __restrict__ nT_g) {
     constexpr int DP = 8 * NT, LD = DP + 1, NTRI = NT * (NT + 1) / 2;
     extern __shared__ double sm[];
     double* a = sm;                  // [DP][LD]  correlation matrix -> Householder vectors -> eigenvectors
@@ -229,7 +238,8 @@ __global__ void __launch_bounds__(kQlThreads)
     double* e = d + DP;              // [DP]      off-diagonal
     double* cs = e + DP;             // [2*DP]    rotation (c, s) pairs of one QL iteration
     double* red = cs + 2 * DP;       // [8]       reduction scratch / broadcast
-    __shared__ int sh_m, sh_cnt, sh_flag;
+    double* tl = red + 8;            // [DP][LD]  kEigFull only: T -> its Cholesky factor L (lower)
+    __shared__ int sh_m, sh_cnt, sh_flag, sh_bad;
 
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kQlThreads / 32;
@@ -261,25 +271,104 @@ __global__ void __launch_bounds__(kQlThreads)
         if (ti != tj) a[col * LD + row] = v;
     }
     __syncthreads();
-    if (tid < DP) {
-        const double t0 = (tid < D) ? a[tid * LD + tid] : 0.0;
-        dinv[tid] = (t0 > 0.0) ? 1.0 / sqrt(t0) : 0.0;
+    if (MODE == kEigDiag) {
+        if (tid < DP) {
+            const double t0 = (tid < D) ? a[tid * LD + tid] : 0.0;
+            dinv[tid] = (t0 > 0.0) ? 1.0 / sqrt(t0) : 0.0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double acc = 0.0;
+            for (int b = 0; b < D; ++b) acc += log(1.0e4 * a[b * LD + b]);   // log det of the scaled T (:94-99)
+            slogT_g[s] = acc;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < DP * DP; idx += blockDim.x) {
+            const int r = idx / DP, c = idx % DP;
+            double v = a[r * LD + c] * dinv[r] * dinv[c];
+            if (r == c) v = (r < D && dinv[r] > 0.0) ? 1.0 : 0.0;
+            if (r >= D || c >= D) v = 0.0;
+            a[r * LD + c] = v;
+        }
+        __syncthreads();
+    } else if (MODE == kEigNone) {
+        if (tid < DP) dinv[tid] = (tid < D) ? 1.0 : 0.0;
+        if (tid == 0) slogT_g[s] = 0.0;
+        for (int idx = tid; idx < DP * DP; idx += blockDim.x) {
+            const int r = idx / DP, c = idx % DP;
+            if (r >= D || c >= D) a[r * LD + c] = 0.0;
+        }
+        __syncthreads();
+    } else {
+        // ---- T = covariance of the whole column from its own Gram partials (centred on the column mean)
+        const int nT = nT_g[s];
+        const double inv_nT = 1.0 / (double)(nT - 1);
+        for (int idx = tid; idx < NTRI * 64; idx += blockDim.x) {
+            const int t = idx >> 6, within = idx & 63;
+            const int ln = within >> 1, ee = within & 1;
+            int ti, tj;
+            tri_unrank(t, ti, tj);
+            double v = 0.0;
+            for (int c = 0; c < nchunk; ++c) v += gramT_part[((long long)s * nchunk + c) * NTRI * 64 + idx];
+            const int row = 8 * ti + (ln >> 2), col = 8 * tj + 2 * (ln & 3) + ee;
+            v *= inv_nT;
+            tl[row * LD + col] = v;
+            if (ti != tj) tl[col * LD + row] = v;
+        }
+        if (tid == 0) sh_bad = 0;
+        __syncthreads();
+        // right-looking Cholesky, lower triangle in place
+        for (int j = 0; j < D; ++j) {
+            const double piv = tl[j * LD + j];
+            __syncthreads();
+            if (!(piv > 0.0)) { if (tid == 0) sh_bad = 1; break; }
+            const double ljj = sqrt(piv);
+            for (int i = j + tid; i < D; i += blockDim.x) tl[i * LD + j] = (i == j) ? ljj : tl[i * LD + j] / ljj;
+            __syncthreads();
+            for (int i = j + 1 + warp; i < D; i += NW) {
+                const double lij = tl[i * LD + j];
+                for (int k = j + 1 + lane; k <= i; k += 32) tl[i * LD + k] -= lij * tl[k * LD + j];
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        if (sh_bad) {   // T not positive definite: no usable factor, report the mode as singular (:371-374)
+            for (int i = tid; i < DP * DP; i += blockDim.x) Pout[i] = 0.0;
+            for (int i = tid; i < DP; i += blockDim.x) lam_g[(long long)s * DP + i] = 0.0;
+            if (tid == 0) { status_g[s] = kStatusSingular; sweeps_g[s] = 0; slogT_g[s] = 0.0; }
+            return;
+        }
+        if (tid == 0) {
+            double acc = (double)D * log(1.0e4);                            // the x100 scaling of I_reg (:100)
+            for (int b = 0; b < D; ++b) acc += 2.0 * log(tl[b * LD + b]);
+            slogT_g[s] = acc;
+        }
+        if (tid < DP) dinv[tid] = (tid < D) ? 1.0 : 0.0;
+        // X = L^-1 S (forward substitution, one column of S per thread), then R = X L^-T = (L^-1 X^T)^T
+        for (int c = tid; c < D; c += blockDim.x) {
+            for (int i = 0; i < D; ++i) {
+                double v = a[i * LD + c];
+                for (int k = 0; k < i; ++k) v -= tl[i * LD + k] * a[k * LD + c];
+                a[i * LD + c] = v / tl[i * LD + i];
+            }
+        }
+        __syncthreads();
+        // rows of X are independent: thread r owns row r; strided by LD so the accesses do not conflict
+        for (int r = tid; r < D; r += blockDim.x) {
+            for (int i = 0; i < D; ++i) {
+                double v = a[r * LD + i];
+                for (int k = 0; k < i; ++k) v -= tl[i * LD + k] * a[r * LD + k];
+                a[r * LD + i] = v / tl[i * LD + i];
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < DP * DP; idx += blockDim.x) {
+            const int r = idx / DP, c = idx % DP;
+            if (r >= D || c >= D) a[r * LD + c] = 0.0;
+            else if (c < r) a[r * LD + c] = 0.5 * (a[r * LD + c] + a[c * LD + r]);   // tred2 reads the lower triangle
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    if (tid == 0) {
-        double acc = 0.0;
-        for (int b = 0; b < D; ++b) acc += log(1.0e4 * a[b * LD + b]);   // log det of the scaled T (:94-99)
-        slogT_g[s] = acc;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < DP * DP; idx += blockDim.x) {
-        const int r = idx / DP, c = idx % DP;
-        double v = a[r * LD + c] * dinv[r] * dinv[c];
-        if (r == c) v = (r < D && dinv[r] > 0.0) ? 1.0 : 0.0;
-        if (r >= D || c >= D) v = 0.0;
-        a[r * LD + c] = v;
-    }
-    __syncthreads();
 
     // ---- tred2: reduce to tridiagonal form, lower triangle, rows n-1 .. 1
     for (int i = D - 1; i >= 1; --i) {
@@ -429,6 +518,18 @@ __global__ void __launch_bounds__(kQlThreads)
     if (tid == 0) {
         status_g[s] = sh_flag ? kStatusNoConverge : kStatusOk;
         sweeps_g[s] = total_iter;
+    }
+    if (MODE == kEigFull) {
+        // P = L^-T V: back substitution, one eigenvector (column of a) per thread
+        __syncthreads();
+        for (int j = tid; j < D; j += blockDim.x) {
+            for (int b = D - 1; b >= 0; --b) {
+                double v = a[b * LD + j];
+                for (int k = b + 1; k < D; ++k) v -= tl[k * LD + b] * a[k * LD + j];
+                a[b * LD + j] = v / tl[b * LD + b];
+            }
+        }
+        __syncthreads();
     }
     for (int idx = tid; idx < DP * DP; idx += blockDim.x) {
         const int b = idx / DP, j = idx % DP;
@@ -595,7 +696,7 @@ __global__ void __launch_bounds__(256)
         return;
     }
 
-    if (tid == 0) singular = 0;
+    if (tid == 0) singular = (status_g[s] & kStatusSingular) ? 1 : 0;   // set by K2 when -f finds T not positive definite
     if (model == 0) {
         // screened run (K3a/K3b): sel >= 0 index decided by the screen, -1 all inf, -2 exact values of the
         // tiles in `tmask` decide; alphas outside the mask keep the screened nll (never the minimum).
@@ -697,26 +798,39 @@ __global__ void __launch_bounds__(256)
 template <int NT>
 static void launch_eigen_t(const Dims& d, const double* gram_part, int nchunk, const int* n, const double* mu,
                            const double* ctr, double* P, double* lam, double* slogT, int* status, int* sweeps,
-                           int method, cudaStream_t st) {
+                           int method, int target, const double* gramT_part, const int* nT, cudaStream_t st) {
     constexpr int DP = 8 * NT, LD = DP + 1;
-    if (method == 1) {
+    if (target == kEigNone) {
+        const size_t smem = (size_t)(DP * LD + 5 * DP + 8) * sizeof(double);
+        cudaFuncSetAttribute(eigen_ql_kernel<NT, kEigNone>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        eigen_ql_kernel<NT, kEigNone><<<d.S, kQlThreads, smem, st>>>(gram_part, nchunk, n, d.D, mu, ctr, P, lam, slogT,
+                                                                    status, sweeps, nullptr, nullptr);
+    } else if (target == kEigFull) {
+        const size_t smem = (size_t)(2 * DP * LD + 5 * DP + 8) * sizeof(double);
+        cudaFuncSetAttribute(eigen_ql_kernel<NT, kEigFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        eigen_ql_kernel<NT, kEigFull><<<d.S, kQlThreads, smem, st>>>(gram_part, nchunk, n, d.D, mu, ctr, P, lam, slogT,
+                                                                    status, sweeps, gramT_part, nT);
+    } else if (method == 1) {
         const size_t smem = (size_t)(2 * DP * LD + 2 * DP + 2 * (DP / 2 + 1)) * sizeof(double);
         cudaFuncSetAttribute(eigen_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         eigen_kernel<NT><<<d.S, 512, smem, st>>>(gram_part, nchunk, n, d.D, mu, ctr, P, lam, slogT, status, sweeps);
     } else {
         const size_t smem = (size_t)(DP * LD + 5 * DP + 8) * sizeof(double);
-        cudaFuncSetAttribute(eigen_ql_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        eigen_ql_kernel<NT><<<d.S, kQlThreads, smem, st>>>(gram_part, nchunk, n, d.D, mu, ctr, P, lam, slogT, status, sweeps);
+        cudaFuncSetAttribute(eigen_ql_kernel<NT, kEigDiag>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        eigen_ql_kernel<NT, kEigDiag><<<d.S, kQlThreads, smem, st>>>(gram_part, nchunk, n, d.D, mu, ctr, P, lam, slogT,
+                                                                    status, sweeps, nullptr, nullptr);
     }
 }
 
 // method: 0 = Householder + implicit QL (default), 1 = cyclic Jacobi (cross-check)
+// target: 0 = diag(S) (default shrinkage target), 1 = none (PCA), 2 = full-column covariance from gramT_part / nT (-f)
 void launch_eigen(const Dims& d, const double* gram_part, int nchunk, const int* n, const double* mu,
                   const double* ctr, double* P, double* lam, double* slogT, int* status, int* sweeps, int method,
-                  cudaStream_t st) {
+                  cudaStream_t st, int target, const double* gramT_part, const int* nT) {
     switch (d.NT) {
 #define CMF_CASE(k) \
-    case k: launch_eigen_t<k>(d, gram_part, nchunk, n, mu, ctr, P, lam, slogT, status, sweeps, method, st); break;
+    case k: launch_eigen_t<k>(d, gram_part, nchunk, n, mu, ctr, P, lam, slogT, status, sweeps, method, target, \
+                              gramT_part, nT, st); break;
         CMF_CASE(1) CMF_CASE(2) CMF_CASE(3) CMF_CASE(4) CMF_CASE(5) CMF_CASE(6)
         CMF_CASE(7) CMF_CASE(8) CMF_CASE(9) CMF_CASE(10) CMF_CASE(11) CMF_CASE(12)
 #undef CMF_CASE

@@ -91,9 +91,9 @@ def run(args, log=print):
     if active is None:
         log("could not set active range")
         return 0                                                             # sys.exit(0), :193-194
-    if args.kmeans > 1:
-        raise CmfError("multimodal background (-k > 1) is not available in this build: the reference's "
-                       "MiniBatchKMeans is unseeded (:312); pass labels through the C ABI instead")
+    if args.kmeans > 32:
+        raise CmfError("at most 32 background modes are supported")
+    bgminsamp = int((active[1] - active[0]) * 1.2)                           # :200
     if args.model not in ("looshrinkage", "empirical"):
         raise CmfError("unknown model %r" % args.model)
     log('started processing input file: "%s"' % infile)
@@ -136,11 +136,19 @@ def run(args, log=print):
     with ColumnwiseMF(L, B, S, active, abscf, model=args.model, reflectance=args.reflectance,
                       alphas=alpha_grid(), nodata=nodata, device=args.device) as eng:
         eng.upload(cube)
+        if args.kmeans > 1:
+            # PCA + k-means partition on the device (:306-313; deterministic, the reference's is unseeded),
+            # rejection of small clusters (-r, :316-324) and the full-column regulariser (-f, :358)
+            eng.set_clustering(args.kmeans, pcadim=args.pcadim, reject_min=bgminsamp if args.reject else 0)
+            if args.full and args.model == "looshrinkage":
+                eng.set_regfull(True)
         eng.run()
         mf = eng.mf()
         colstats = eng.colstats()
         aidx = eng.alpha_index()
         mask = eng.mask() if args.metadata else None
+        if args.metadata and args.kmeans > 1:
+            cluster_img, alpha_img = eng.cluster_id(), eng.alpha_image()
     out[:, :, -1] = mf
     done = colstats[0] != nodata          # columns with no valid pixel are skipped entirely (:303-304)
     if len(rgb) == 3:
@@ -157,7 +165,11 @@ def run(args, log=print):
         bgmeta["alphas"] = "{%s}" % (str(alpha_grid())[1:-1])
         bgmeta["band names"] = "{cluster_id, alpha_index}"
         bg = envi.create_image(outfile + "_bgmeta", bgmeta)
-        if args.model == "looshrinkage":
+        if args.kmeans > 1:
+            bg[:, :, 0] = np.where(mask, cluster_img, 0)                          # :327
+            if args.model == "looshrinkage":
+                bg[:, :, 1] = np.where(mask, alpha_img, 0)                        # :365
+        elif args.model == "looshrinkage":
             bg[:, :, 1] = np.where(mask, aidx[None, :].astype(np.int16), 0)       # :365
         bg.flush()
     log("Saving column stats to %s" % colcsv)

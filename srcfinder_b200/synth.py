@@ -122,7 +122,7 @@ def make_cube(lines, samples, bands=425, seed=1, lib=None, plume=True, bad_pixel
 
 
 def make_slab_torch(lines, samples, band_lo, band_hi, device, seed=2, lib=None, plume=True,
-                    noise=0.004, dtype=None, chunk_lines=1024, out=None):
+                    noise=0.004, dtype=None, chunk_lines=1024, out=None, bad_pixels=False):
     """Same recipe, only 1-based bands ``band_lo..band_hi``, generated on ``device`` with torch.
 
     Returns a float32 tensor ``(lines, D, samples)`` (the active slab of a BIL cube).
@@ -159,4 +159,35 @@ def make_slab_torch(lines, samples, band_lo, band_hi, device, seed=2, lib=None, 
         blk += noise * torch.randn(blk.shape, generator=gen, device=device)
         blk.clamp_(min=1.0e-4)
         out[l0:l1] = blk
+    if bad_pixels:
+        inject_bad_pixels_torch(out, seed)
     return out
+
+
+def inject_bad_pixels_torch(slab, seed):
+    """C3 bad pixels on an active slab ``(L, D, S)`` in place, same rates as :func:`make_cube`: 0.5 % whole
+    pixels = NODATA, 0.1 % single-band NaN, 0.1 % single-band negative, 0.05 % saturated (6.5 in every band),
+    0.02 % single-band +inf.  Returns the (L, S) bool image of pixels the filter must drop."""
+    import torch
+
+    L, D, S = slab.shape
+    rng = np.random.default_rng(1000 + int(seed))
+    npx = L * S
+    dev = slab.device
+
+    def pick(frac):
+        idx = rng.choice(npx, size=max(1, int(frac * npx)), replace=False)
+        return (torch.as_tensor(idx // S, device=dev), torch.as_tensor(idx % S, device=dev),
+                torch.as_tensor(rng.integers(0, D, size=idx.size), device=dev))
+
+    bad = torch.zeros((L, S), dtype=torch.bool, device=dev)
+    l, s, _ = pick(0.005)
+    slab[l, :, s] = NODATA
+    bad[l, s] = True
+    for frac, val in ((0.001, float("nan")), (0.001, -0.01), (0.0002, float("inf"))):
+        l, s, b = pick(frac)
+        slab[l, b, s] = val
+        bad[l, s] = True
+    l, s, _ = pick(0.0005)
+    slab[l, :, s] = torch.where(slab[l, :, s] == NODATA, slab[l, :, s], torch.full_like(slab[l, :, s], 6.5))
+    return bad

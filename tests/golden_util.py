@@ -27,6 +27,7 @@ def load_case(name):
     flags = case["flags"]
     case["model"] = flags[flags.index("-M") + 1] if "-M" in flags else "looshrinkage"
     case["reflectance"] = "-R" in flags
+    case["regfull"] = "-f" in flags
     case["kmodes"] = int(flags[flags.index("-k") + 1]) if "-k" in flags else 1
     case["reject_min"] = int((case["active"][1] - case["active"][0]) * 1.2) if "-r" in flags else 0   # :200
     if case["kmodes"] > 1:

@@ -50,7 +50,7 @@ def test_golden_reference_run(name):
     case = load_case(name)
     cube, active = case["cube"], case["active"]
     got = cmf_cube(cube, _abscf(active), active, model=case["model"], reflectance=case["reflectance"],
-                   labels=case.get("labels"), reject_min=case["reject_min"])
+                   labels=case.get("labels"), reject_min=case["reject_min"], regfull=case["regfull"])
     ref_mf = case["product"][..., -1]
     if case["kmodes"] > 1:
         # background modes: the partition of the seeded reference run is the input; rejected clusters keep

@@ -23,7 +23,7 @@ def test_restatement_matches_reference_run(name):
     assert orc.active_window(case["libname"], case["reflectance"]) == active
     res = orc.cmf_cube(cube, _abscf(active), active, model=case["model"],
                        reflectance=case["reflectance"], labels=case.get("labels"),
-                       reject_min=case["reject_min"] or None)
+                       reject_min=case["reject_min"] or None, regfull=case["regfull"])
     ref_mf = case["product"][..., -1]
     # masks: pixels left at nodata must be identical (invalid pixels, plus the rejected clusters with -r)
     if case["kmodes"] > 1:
