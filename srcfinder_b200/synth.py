@@ -189,5 +189,7 @@ def inject_bad_pixels_torch(slab, seed):
         slab[l, b, s] = val
         bad[l, s] = True
     l, s, _ = pick(0.0005)
-    slab[l, :, s] = torch.where(slab[l, :, s] == NODATA, slab[l, :, s], torch.full_like(slab[l, :, s], 6.5))
+    cur = slab[l, :, s]
+    # saturate only healthy values: a defect planted above must survive (the pixel stays dropped)
+    slab[l, :, s] = torch.where(torch.isfinite(cur) & ~(cur < 0), torch.full_like(cur, 6.5), cur)
     return bad

@@ -16,7 +16,8 @@ lib = _lib.load()
 names = {0: "dmma_tflops_32w", 8: "dmma_tflops_8w_ilp24", 1: "dfma_tflops", 6: "cvt_f32_f64_gops",
          7: "logdiv_gops", 9: "mma_sync_tf32_tflops", 10: "mma_sync_bf16_tflops", 11: "ffma_tflops", 2: "hbm_read_8B_gbs", 3: "hbm_read_16B_gbs", 4: "hbm_copy_gbs", 5: "hbm_bulk_read_gbs"}
 if os.environ.get("PROBE_TC5", "1") == "1":
-    for kind, name in {20: "tc5_selftest_n80", 21: "tc5_selftest_n80_swapped", 22: "tc5_selftest_n96_rowoff112",
+    # kind 21 (LBO/SBO swapped on purpose) faults and poisons the context: development use only
+    for kind, name in {20: "tc5_selftest_n80", 22: "tc5_selftest_n96_rowoff112",
                        23: "tc5_selftest_n112", 24: "tc5_selftest_n72", 25: "tc5_selftest_n256_k8"}.items():
         out[name] = lib.cmf_microbench(0, kind, 1)
         print(name, out[name], flush=True)
