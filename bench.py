@@ -58,32 +58,104 @@ def measured_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled through NVML every 10 ms while the timed region runs (an in-process
+    thread: nvidia-smi takes longer to start than a 10-step region lasts); `nvidia-smi -lms` is the fallback."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20),
+            ("hw_thermal_slowdown", 0x40))
 
-    def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index=0, uuid=None):
+        self.index, self.uuid = index, uuid
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.proc = self.thread = self.handle = self.nvml = None
+        self.stop = threading.Event()
+        self.source = None
+
+    def _open_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        if self.uuid:
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(self.uuid))
+            except Exception:
+                h = None
+        if h is None:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.index
+            toks = [t for t in vis.split(",") if t.strip()]
+            if toks and self.index < len(toks) and toks[self.index].strip().isdigit():
+                idx = int(toks[self.index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.nvml, self.handle = pynvml, h
+        self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+        self.mx.append(self.max_sm)
+        try:
+            bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        for name, bit in self.BITS:
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _loop_nvml(self):
+        while not self.stop.is_set():
+            try:
+                self._sample_nvml()
+            except Exception:
+                break
+            self.stop.wait(0.01)
+
+    def _pump_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            r = [t.strip() for t in line.split(",")]
+            try:
+                self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, flag in zip(names, r[2:6]):
+                if flag.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def __enter__(self):
         try:
+            self._open_nvml()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._loop_nvml, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.handle = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._pump_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
         return self
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
-
     def __exit__(self, *exc):
+        if self.handle is not None:
+            try:
+                self._sample_nvml()          # at least one sample taken before the region closes
+            except Exception:
+                pass
+            self.stop.set()
+            if self.thread is not None:
+                self.thread.join(timeout=1)
         if self.proc is not None:
             time.sleep(0.25)
             self.proc.terminate()
@@ -93,20 +165,10 @@ class ClockSampler(object):
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, flag in zip(names, r[2:6]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)),
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def abscf_window():
@@ -256,7 +318,11 @@ def run_gpu(args):
         step(False)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    try:
+        gpu_uuid = torch.cuda.get_device_properties(dev).uuid
+    except Exception:
+        gpu_uuid = None
+    with ClockSampler(local, gpu_uuid) as clocks:
         barrier()
         ev0.record(stream)
         for _ in range(args.steps):

@@ -98,6 +98,19 @@ __device__ __forceinline__ bool pixel_value_ok(float x) {
     return !(x < 0.0f) && (fabsf(x) <= 3.402823466e38f);
 }
 
+// log(det G) as the reference sees it (cmf/robust_mf.py:111-117): G_det is a double, so it is 0 when the
+// determinant is below half the smallest subnormal (2^-1075: the alpha is skipped), +inf above DBL_MAX
+// (nll = inf), and carries only a few bits in the subnormal range (log of the rounded value is what enters nll).
+// Returns -inf / +inf for the two excluded cases.
+__device__ __forceinline__ double det_roundtrip(double logdet) {
+    if (logdet > 709.782712893384) return __longlong_as_double(0x7ff0000000000000LL);
+    if (logdet < -708.3964185322641) {               // below 2^-1022: the subnormal grid has spacing 2^-1074
+        const double units = rint(exp(logdet + 744.4400719213812));   // det in units of 2^-1074, ties to even
+        return units >= 1.0 ? log(units) - 744.4400719213812 : -__longlong_as_double(0x7ff0000000000000LL);
+    }
+    return logdet;
+}
+
 __device__ __forceinline__ float2 ldg_nc_f2(const float* p) {
     float2 v;
     asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));

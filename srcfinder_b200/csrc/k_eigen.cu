@@ -709,9 +709,8 @@ __global__ void __launch_bounds__(256)
             if (!screened || ((tmask >> ((i >> 3) & 63)) & 1ull)) {
                 double fs = 0.0;
                 for (int c = 0; c < nchunk; ++c) fs += fpart[((long long)s * nchunk + c) * AP + i];
-                const double ld = logdet_g[(long long)s * AP + i];
-                if (ld < -744.4400719213812) v = inf;             // det underflows to 0 -> alpha skipped (:112-113)
-                else if (ld > 709.782712893384) v = inf;          // det overflows -> log(inf)
+                const double ld = det_roundtrip(logdet_g[(long long)s * AP + i]);
+                if (!(fabs(ld) < inf)) v = inf;   // det underflows to 0 -> alpha skipped; overflows -> log(inf) (:112-113)
                 else v = 0.5 * (const_term + ld) + fs / (2.0 * nl);
                 nll_g[(long long)s * A + i] = v;
             } else {

@@ -341,9 +341,9 @@ __global__ void __launch_bounds__(128)
         for (int c = 0; c < nchunk; ++c) fs += fscreen[((long long)s * nchunk + c) * AP16 + i];
         // the tcgen05 pass sums h + u; sum_k u_k = beta sum_k r_k is the closed form (k_screen5.cu)
         if (betaf_fold) fs -= (double)betaf_fold[(long long)s * AP16 + i] * rsum_g[(long long)s * AP + i];
-        const double ld = logdet_g[(long long)s * AP + i];
+        const double ld = det_roundtrip(logdet_g[(long long)s * AP + i]);
         double v;
-        if (ld < -744.4400719213812 || ld > 709.782712893384) v = inf;   // det under/overflow (:112-113)
+        if (!(fabs(ld) < inf)) v = inf;                    // det under/overflow (:112-113)
         else {
             v = 0.5 * (const_term + ld) + (rsum_g[(long long)s * AP + i] + fs) / (2.0 * nl);
             if (!(fabs(v) < inf)) bad = true;  // NaN or +-inf out of the data

@@ -179,6 +179,189 @@ __global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ s
     if (tid < CG && s0 + tid < S) colcnt_part[split * S + s0 + tid] = cnt;
 }
 
+// ---------------------------------------------------------------------------------------- K0 (pipelined)
+// The same pass as a two-stage software pipeline.  One CTA = CG columns x a line range, tiles of LT lines.
+// Every radiance is moved global -> shared by a 4-byte LDGSTS (cp.async) straight into the TRANSPOSED tile
+// [column][line][band], so the loads of tile i+1 are in flight while tile i is checked and written, and no
+// register is held across the memory latency.  The write side is then pure 16-byte traffic: thread <->
+// (column, 4 bands) reads LT float4 from shared memory, flags bad pixels, and stores LT float4 to the column's
+// contiguous [LT][DP] block of xt; its four FP64 band sums live in registers for the whole line range.
+// Shared layout: column stride CS = LT*DP + 4 floats (== 4 mod 32 banks) and the low two bits of the element
+// index XORed with a per-column key, so that the 32 lanes of one LDGSTS (CG columns x 32/CG bands) hit 32
+// different banks while the float4 reads stay aligned; the key is undone in registers.
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int CG>
+__device__ __forceinline__ int repack_key(int c) {
+    return CG == 16 ? ((c >> 3) & 1) << 1 : (c >> 3) & 3;
+}
+
+// resident CTAs per SM the register allocation is held to: what shared memory (227 KB) and threads (2048) allow
+constexpr int repack_pipe_minb(int nt, int cg, int lt) {
+    const int by_smem = (227 * 1024) / (2 * cg * (lt * 8 * nt + 4) * 4 + 1024 + 256);
+    const int by_thr = 2048 / (cg * 2 * nt);
+    const int m = by_smem < by_thr ? by_smem : by_thr;
+    return m < 1 ? 1 : (m > 4 ? 4 : m);
+}
+
+// validity of four radiances at once: as unsigned integers every finite value >= +0 is below 0x7f800000, so one
+// 3-input max + compare decides the common case; -0.0 (valid: not < 0) is the only value the fast test rejects
+// wrongly, and it is re-examined exactly (the reference's rule, cmf/robust_mf.py:282)
+__device__ __forceinline__ bool quad_ok(const float4& x) {
+    const uint32_t a = __float_as_uint(x.x), b = __float_as_uint(x.y), c = __float_as_uint(x.z),
+                   d = __float_as_uint(x.w);
+    const uint32_t m = max(max(a, b), max(c, d));
+    if (m < 0x7f800000u) return true;
+    return pixel_value_ok(x.x) && pixel_value_ok(x.y) && pixel_value_ok(x.z) && pixel_value_ok(x.w);
+}
+
+template <int KEY>
+__device__ __forceinline__ float4 repack_unkey(const float4& x) {
+    if (KEY == 0) return x;
+    if (KEY == 1) return make_float4(x.y, x.x, x.w, x.z);
+    if (KEY == 2) return make_float4(x.z, x.w, x.x, x.y);
+    return make_float4(x.w, x.z, x.y, x.x);
+}
+
+// pass A of one tile for a thread whose column has key KEY: shared -> registers, flag bad pixels
+template <int KEY, int LT, int DP, int CG>
+__device__ __forceinline__ void repack_pass_a(const float* src, int nl, int c, uint8_t* bd, float4 (&v)[LT]) {
+#pragma unroll
+    for (int l = 0; l < LT; ++l) {
+        if (l < nl) {
+            const float4 x = repack_unkey<KEY>(*reinterpret_cast<const float4*>(src + l * DP));
+            v[l] = x;
+            if (!quad_ok(x)) bd[l * CG + c] = 1;
+        }
+    }
+}
+
+template <int NT, int CG, int LT>
+__global__ void __launch_bounds__(CG * 2 * NT, repack_pipe_minb(NT, CG, LT)) repack_pipe_kernel(
+    const float* __restrict__ slab, long long line_pitch, int band_pitch, int L, int S, int D,
+    float* __restrict__ xt, uint8_t* __restrict__ mask, double* __restrict__ colsum_part,
+    int* __restrict__ colcnt_part, int lines_per_split, int line_base, int line_limit, int split_base,
+    const uint8_t* __restrict__ sel, int write_mask) {
+    constexpr int DP = 8 * NT, Q = 2 * NT, NTH = CG * Q, CS = LT * DP + 4;
+    extern __shared__ __align__(16) float tile[];   // [2][CG][CS]
+    __shared__ uint8_t bad[2][LT * CG];
+
+    const int tid = threadIdx.x;
+    const int s0 = blockIdx.x * CG;
+    const int split = split_base + blockIdx.y;
+    const int l_begin = line_base + blockIdx.y * lines_per_split;
+    const int l_end = min(line_limit, l_begin + lines_per_split);
+    // load side: lane <-> column (coalesced runs of CG floats per (line, band) row); a thread owns bands
+    // r_ld + k*Q, k = 0..3, of every line of the tile
+    const int c_ld = tid % CG, r_ld = tid / CG;
+    const bool ld_ok = s0 + c_ld < S;
+    const int key_ld = repack_key<CG>(c_ld);
+    uint32_t sdst[4];
+    long long goff[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int b = r_ld + k * Q;
+        sdst[k] = smem_u32(tile + (size_t)c_ld * CS + (b ^ key_ld));
+        goff[k] = (ld_ok && b < D) ? (long long)b * band_pitch : -1;
+    }
+    // store side: thread <-> (column, 4 consecutive bands)
+    const int c = tid / Q, q = tid % Q;
+    const bool col_ok = s0 + c < S;
+    const int key = repack_key<CG>(c);
+
+    for (int i = tid; i < 2 * CG * CS; i += NTH) tile[i] = 0.0f;      // padded bands stay zero for good
+    for (int i = tid; i < 2 * LT * CG; i += NTH) (&bad[0][0])[i] = 0;
+    __syncthreads();
+
+    auto issue = [&](int buf, int l0, int nl) {
+        const float* src = slab + (long long)l0 * line_pitch + s0 + c_ld;
+        const uint32_t boff = (uint32_t)(buf * CG * CS * sizeof(float));
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            if (l < nl) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (goff[k] >= 0)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst[k] + boff +
+                                                                                      (uint32_t)(l * DP * 4)),
+                                     "l"(src + goff[k])
+                                     : "memory");
+            }
+            src += line_pitch;
+        }
+        cp_async_commit();
+    };
+
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    int cnt = 0;
+    const int ntiles = (l_end - l_begin + LT - 1) / LT;
+    if (ntiles > 0) issue(0, l_begin, min(LT, l_end - l_begin));
+    for (int it = 0; it < ntiles; ++it) {
+        const int l0 = l_begin + it * LT;
+        const int nl = min(LT, l_end - l0);
+        const int buf = it & 1;
+        if (it + 1 < ntiles) {
+            issue(buf ^ 1, l0 + LT, min(LT, l_end - l0 - LT));
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();                                   // tile `it` has landed for every thread
+        uint8_t* bd = bad[buf];
+        float4 v[LT];
+        if (col_ok) {
+            const float* src = tile + (size_t)(buf * CG + c) * CS + 4 * q;
+            // the key changes every 8 columns, so this branch is uniform for all but a few warps
+            switch (key) {
+                case 0: repack_pass_a<0, LT, DP, CG>(src, nl, c, bd, v); break;
+                case 1: repack_pass_a<1, LT, DP, CG>(src, nl, c, bd, v); break;
+                case 2: repack_pass_a<2, LT, DP, CG>(src, nl, c, bd, v); break;
+                default: repack_pass_a<3, LT, DP, CG>(src, nl, c, bd, v); break;
+            }
+        }
+        __syncthreads();                                   // flags complete; this tile buffer may be refilled
+        // validity is a property of the pixel (cmf/robust_mf.py:282); a background-mode pass (sel != NULL)
+        // additionally drops the valid pixels that are not members of the mode being fitted (:341)
+        for (int i = tid; i < LT * CG; i += NTH) {
+            const int l = i / CG, cc = i % CG;
+            if (l < nl && s0 + cc < S) {
+                const long long o = (long long)(l0 + l) * S + s0 + cc;
+                if (write_mask) mask[o] = bd[i] ? 0 : 1;
+                if (sel != nullptr && sel[o] == 0) bd[i] = 1;
+            }
+            bad[buf ^ 1][i] = 0;                            // flags of the next tile (last read one tile ago)
+        }
+        if (sel != nullptr) __syncthreads();
+        if (col_ok) {
+            float* dst = xt + ((long long)(s0 + c) * L + l0) * DP + 4 * q;
+            const float qnan = __int_as_float(0x7fc00000);
+#pragma unroll
+            for (int l = 0; l < LT; ++l) {
+                if (l < nl) {
+                    float4 x = v[l];
+                    if (bd[l * CG + c]) {
+                        x = make_float4(qnan, qnan, qnan, qnan);
+                    } else {
+                        acc0 += (double)x.x; acc1 += (double)x.y; acc2 += (double)x.z; acc3 += (double)x.w;
+                        ++cnt;
+                    }
+                    *reinterpret_cast<float4*>(dst + l * DP) = x;
+                }
+            }
+        }
+    }
+    if (col_ok) {
+        double* o = colsum_part + ((long long)split * S + s0 + c) * DP + 4 * q;
+        o[0] = acc0; o[1] = acc1; o[2] = acc2; o[3] = acc3;
+        if (q == 0) colcnt_part[split * S + s0 + c] = cnt;
+    }
+}
+
 // ---------------------------------------------------------------------------------------- K0b
 // Splits [0, nsplit) give the column mean; the same kernel over the first `nsplit` = pilot splits gives the
 // pilot centre of the Gram pass (n == NULL: the count is not stored).
@@ -434,27 +617,45 @@ __global__ void colstats_kernel(const double* __restrict__ stat_part, int nlanes
 }
 
 // ---------------------------------------------------------------------------------------- launchers
-int repack_nsplit(const Dims& d) {
-    const int groups = (d.S + kRepackCG - 1) / kRepackCG;
-    int want = (148 * 5 + groups - 1) / groups;                 // ~5 CTAs per SM
-    int maxsplit = (d.L + 4 * kRepackLT - 1) / (4 * kRepackLT); // at least 4 tiles per CTA
-    int ns = want < maxsplit ? want : maxsplit;
-    return ns < 1 ? 1 : ns;
+// Repack plan: tile shape (CG columns x LT lines) of the pipelined kernel.  CG == 0 selects the older
+// single-stage kernel (kept for A/B measurements through tools/).
+struct RepackVariant { int cg, lt; };
+
+static RepackVariant repack_variant() {
+    // tuning hook (tools/ only): CMF_REPACK_VARIANT=CG,LT picks another instantiation, "0,0" the old kernel
+    static RepackVariant v = [] {
+        RepackVariant r{32, 8};     // measured best on B200 (profiles/r01g_tune_repack.json)
+        if (const char* e = getenv("CMF_REPACK_VARIANT")) sscanf(e, "%d,%d", &r.cg, &r.lt);
+        const bool known = (r.cg == 0) || ((r.cg == 16 || r.cg == 32) && (r.lt == 4 || r.lt == 8));
+        if (!known) r = RepackVariant{32, 8};
+        return r;
+    }();
+    return v;
+}
+
+template <int NT, int CG, int LT>
+static size_t repack_pipe_smem() { return (size_t)2 * CG * (LT * 8 * NT + 4) * sizeof(float); }
+
+template <int NT, int CG, int LT>
+static int repack_pipe_resident() {
+    const size_t smem = repack_pipe_smem<NT, CG, LT>();
+    cudaFuncSetAttribute(repack_pipe_kernel<NT, CG, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, repack_pipe_kernel<NT, CG, LT>, CG * 2 * NT, smem) !=
+        cudaSuccess) {
+        cudaGetLastError();
+        nb = 0;
+    }
+    return nb;
 }
 
 template <int NT>
-static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,
-                            int* colcnt_part, int lps, int line_base, int line_limit, int split_base,
-                            const uint8_t* sel, int write_mask, cudaStream_t st) {
-    constexpr int DP = 8 * NT;
-    const size_t smem = (size_t)kRepackLT * DP * (kRepackCG + 1) * sizeof(float);
-    cudaFuncSetAttribute(repack_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int nblk = (line_limit - line_base + lps - 1) / lps;
-    if (nblk <= 0) return;
-    dim3 grid((d.S + kRepackCG - 1) / kRepackCG, nblk);
-    repack_kernel<NT><<<grid, 256, smem, st>>>(slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, d.vec2, xt,
-                                               mask, colsum_part, colcnt_part, lps, line_base, line_limit,
-                                               split_base, sel, write_mask);
+static int repack_resident_t(const RepackVariant& v) {
+    if (v.cg == 16 && v.lt == 8) return repack_pipe_resident<NT, 16, 8>();
+    if (v.cg == 16 && v.lt == 4) return repack_pipe_resident<NT, 16, 4>();
+    if (v.cg == 32 && v.lt == 4) return repack_pipe_resident<NT, 32, 4>();
+    if (v.cg == 32 && v.lt == 8) return repack_pipe_resident<NT, 32, 8>();
+    return 0;
 }
 
 #define CMF_NT_SWITCH(nt, CALL)                                                      \
@@ -473,6 +674,67 @@ static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t
         case 12: { constexpr int NTc = 12; CALL; } break;                            \
         default: break;                                                              \
     }
+
+// Line ranges per column group.  The pipelined kernel is launched as (at most) one resident wave: every CTA
+// streams its whole line range, so the ranges are sized to fill the SMs' resident slots once.
+int repack_nsplit(const Dims& d) {
+    const RepackVariant v = repack_variant();
+    if (v.cg > 0) {
+        int resident = 0, sms = 148, dev = 0;
+        CMF_NT_SWITCH(d.NT, (resident = repack_resident_t<NTc>(v)));
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (resident > 0) {
+            const int groups = (d.S + v.cg - 1) / v.cg;
+            int ns = (sms * resident) / groups;
+            const int maxsplit = (d.L + 4 * v.lt - 1) / (4 * v.lt);     // at least 4 tiles per CTA
+            if (ns > maxsplit) ns = maxsplit;
+            return ns < 1 ? 1 : ns;
+        }
+    }
+    const int groups = (d.S + kRepackCG - 1) / kRepackCG;
+    int want = (148 * 5 + groups - 1) / groups;                 // ~5 CTAs per SM
+    int maxsplit = (d.L + 4 * kRepackLT - 1) / (4 * kRepackLT); // at least 4 tiles per CTA
+    int ns = want < maxsplit ? want : maxsplit;
+    return ns < 1 ? 1 : ns;
+}
+
+template <int NT, int CG, int LT>
+static void launch_repack_pipe(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,
+                               int* colcnt_part, int lps, int line_base, int line_limit, int split_base,
+                               const uint8_t* sel, int write_mask, cudaStream_t st) {
+    const size_t smem = repack_pipe_smem<NT, CG, LT>();
+    cudaFuncSetAttribute(repack_pipe_kernel<NT, CG, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int nblk = (line_limit - line_base + lps - 1) / lps;
+    if (nblk <= 0) return;
+    dim3 grid((d.S + CG - 1) / CG, nblk);
+    repack_pipe_kernel<NT, CG, LT><<<grid, CG * 2 * NT, smem, st>>>(slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D,
+                                                                    xt, mask, colsum_part, colcnt_part, lps,
+                                                                    line_base, line_limit, split_base, sel,
+                                                                    write_mask);
+}
+
+template <int NT>
+static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,
+                            int* colcnt_part, int lps, int line_base, int line_limit, int split_base,
+                            const uint8_t* sel, int write_mask, cudaStream_t st) {
+    const RepackVariant v = repack_variant();
+#define CMF_RV(CGv, LTv)                                                                                     \
+    if (v.cg == CGv && v.lt == LTv)                                                                          \
+        return launch_repack_pipe<NT, CGv, LTv>(d, slab, xt, mask, colsum_part, colcnt_part, lps, line_base, \
+                                                line_limit, split_base, sel, write_mask, st);
+    CMF_RV(16, 8) CMF_RV(16, 4) CMF_RV(32, 4) CMF_RV(32, 8)
+#undef CMF_RV
+    constexpr int DP = 8 * NT;
+    const size_t smem = (size_t)kRepackLT * DP * (kRepackCG + 1) * sizeof(float);
+    cudaFuncSetAttribute(repack_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int nblk = (line_limit - line_base + lps - 1) / lps;
+    if (nblk <= 0) return;
+    dim3 grid((d.S + kRepackCG - 1) / kRepackCG, nblk);
+    repack_kernel<NT><<<grid, 256, smem, st>>>(slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, d.vec2, xt,
+                                               mask, colsum_part, colcnt_part, lps, line_base, line_limit,
+                                               split_base, sel, write_mask);
+}
 
 int repack_lines_per_split(const Dims& d, int nsplit) {
     int lps = (d.L + nsplit - 1) / nsplit;
