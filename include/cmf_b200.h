@@ -69,7 +69,8 @@ enum {
     CMF_OUT_MODE_LIST = 15,   /* int8   [S][32]  the column's mode list (bgulab, :313-332); 127 = past the end */
     CMF_OUT_LABELS = 16,      /* int32  [L][S]   cluster labels in use (given by cmf_set_labels or found by cmf_set_clustering) */
     CMF_OUT_PCA = 17,         /* double [S][L][pcadim] projections the on-device k-means partitioned (:311) */
-    CMF_OUT_KMEANS_ITERS = 18 /* int32  [S]      reassignment passes the k-means needed */
+    CMF_OUT_KMEANS_ITERS = 18,/* int32  [S]      reassignment passes the k-means needed */
+    CMF_OUT_FLAGS = 19        /* uint8  [lines][samples] of the last cmf_pixel_flags() call */
 };
 
 typedef struct cmf_problem {
@@ -146,6 +147,43 @@ int cmf_run_host(cmf_ctx* ctx, const float* host_cube, double* mf_out, double* c
 int cmf_download(cmf_ctx* ctx, int what, void* host_dst, size_t bytes);   /* synchronous */
 void* cmf_device_ptr(cmf_ctx* ctx, int what);                            /* NULL if not available */
 size_t cmf_output_bytes(const cmf_ctx* ctx, int what);
+
+/* ---- the steps either side of the filter ---- */
+
+/* Per-pixel spectrometer flags of a radiance cube: the per-pixel tests of spectrometer_masks/masks_sds.py
+ * (get_saturation_mask :133-150, get_spec_mask :152-163, get_dark_mask :165-180, get_cloud_mask :182-230).
+ * Region growing, buffers and dilation (:232-330) are image morphology and are not part of this call.
+ * Band numbers are 0-based indices into the cube's band axis, as the reference indexes them; < 0 disables a test. */
+enum { CMF_FLAG_SATURATED = 1, CMF_FLAG_SPECULAR = 2, CMF_FLAG_DARK = 4, CMF_FLAG_CLOUD = 8 };
+typedef struct cmf_flag_spec {
+    int32_t sat_lo, sat_hi;      /* saturation window (bands whose wavelength is in 1945..2485 nm, :148) */
+    int32_t spec_band;           /* 25 (:159) */
+    int32_t dark_band;           /* 352, 2139 nm (:175) */
+    int32_t cloud_a, cloud_b;    /* 15 and 60 (450 nm, 670 nm; :194) */
+    float sat_thresh;            /* 6.0 (SAT_THRESH_DEFAULT, :50) */
+    float spec_thresh;           /* 9.0 (--visible-mask-growing-threshold, :102) */
+    float dark_thresh;           /* 0.104 (:78) */
+    float cloud_thresh;          /* 15.0 (SAT_THRESH_CLD, :52) */
+    float cloud_dwl;             /* wavelength[cloud_b] - wavelength[cloud_a]; the slope test is
+                                    (r_b - r_a) / cloud_dwl < 0 (:213-222) */
+} cmf_flag_spec;
+/* cube: (lines, bands, samples) float32 BIL, on the host (only the bands the tests read are transferred) or,
+ * with on_device != 0, already on the device.  flags_host: uint8 [lines][samples] of CMF_FLAG_* bits (may be
+ * NULL; CMF_OUT_FLAGS keeps the device copy).  Independent of cmf_set_problem.  Synchronous. */
+int cmf_pixel_flags(cmf_ctx* ctx, const float* cube, int on_device, int32_t lines, int32_t bands, int32_t samples,
+                    const cmf_flag_spec* spec, uint8_t* flags_host);
+
+/* Column profile of the scores of the last run (triage/cmf_profile.py:110-140): per cross-track column, over
+ * the pixels that are not no-data / NaN and are > 0, evaluated in float32 exactly as numpy does there.
+ *   robust == 0: npix, avg, std (ddof 0), min, max               (:127-130)
+ *   robust != 0: npix, med, mad, p-low, p-high                   (:123-125; nearest-rank percentiles at
+ *                q = (1 - p) * 100 and p * 100, the reference uses p = 0.95)
+ * out_host: double [5][samples]; columns without such a pixel give npix = 0 and NaN.  Synchronous. */
+int cmf_column_profile(cmf_ctx* ctx, int robust, double p, double* out_host);
+/* The same for a score image on the host (the last band of a product on disk, :112): double [lines][samples],
+ * `nodata` the product's 'data ignore value'.  Independent of cmf_set_problem.  Synchronous. */
+int cmf_column_profile_image(cmf_ctx* ctx, const double* mf_host, int32_t lines, int32_t samples, double nodata,
+                             int robust, double p, double* out_host);
 
 /* ---- instrumentation ---- */
 int cmf_kernel_count(void);

@@ -14,16 +14,17 @@ SYMBOLS = [
     "cmf_upload_bil", "cmf_bind_device_slab", "cmf_set_labels", "cmf_set_clustering", "cmf_set_regfull", "cmf_run", "cmf_sync", "cmf_run_host", "cmf_download",
     "cmf_device_ptr", "cmf_output_bytes", "cmf_kernel_count", "cmf_kernel_name", "cmf_kernel_times",
     "cmf_launch_count", "cmf_screen_kernel", "cmf_host_alloc", "cmf_host_free", "cmf_host_register", "cmf_host_unregister",
-    "cmf_microbench",
+    "cmf_microbench", "cmf_pixel_flags", "cmf_column_profile", "cmf_column_profile_image",
 ]
 
 OUT_MF, OUT_MASK, OUT_COLSTATS, OUT_ALPHA_INDEX, OUT_NLL, OUT_MU, OUT_WEIGHTS, OUT_STATUS, OUT_NVALID, \
     OUT_EIGVALS, OUT_SWEEPS, OUT_NCAND, OUT_SCREEN_TOL, OUT_CLUSTER_ID, OUT_ALPHA_IMAGE, OUT_MODE_LIST, OUT_LABELS, OUT_PCA, \
-    OUT_KMEANS_ITERS = range(19)
+    OUT_KMEANS_ITERS, OUT_FLAGS = range(20)
 RUN_TIMING = 1
 RUN_EXACT = 2
 RUN_ASYNC = 4
 MODEL_LOOSHRINKAGE, MODEL_EMPIRICAL = 0, 1
+FLAG_SATURATED, FLAG_SPECULAR, FLAG_DARK, FLAG_CLOUD = 1, 2, 4, 8
 COL_EMPTY, COL_DEGENERATE, COL_SINGULAR, COL_NOCONVERGE, COL_ALLINF = 1, 2, 4, 8, 16
 
 
@@ -33,6 +34,14 @@ class Problem(C.Structure):
         ("band_lo", C.c_int32), ("band_hi", C.c_int32), ("reflectance", C.c_int32), ("model", C.c_int32),
         ("num_alphas", C.c_int32), ("reserved", C.c_int32), ("nodata", C.c_double),
         ("alphas", C.POINTER(C.c_double)), ("abscf", C.POINTER(C.c_double)),
+    ]
+
+
+class FlagSpec(C.Structure):
+    _fields_ = [
+        ("sat_lo", C.c_int32), ("sat_hi", C.c_int32), ("spec_band", C.c_int32), ("dark_band", C.c_int32),
+        ("cloud_a", C.c_int32), ("cloud_b", C.c_int32), ("sat_thresh", C.c_float), ("spec_thresh", C.c_float),
+        ("dark_thresh", C.c_float), ("cloud_thresh", C.c_float), ("cloud_dwl", C.c_float),
     ]
 
 
@@ -77,6 +86,9 @@ def load():
         "cmf_host_register": (C.c_int, [vp, sz]),
         "cmf_host_unregister": (C.c_int, [vp]),
         "cmf_microbench": (C.c_double, [C.c_int, C.c_int, C.c_int]),
+        "cmf_pixel_flags": (C.c_int, [vp, vp, C.c_int, i32, i32, i32, C.POINTER(FlagSpec), vp]),
+        "cmf_column_profile": (C.c_int, [vp, C.c_int, C.c_double, vp]),
+        "cmf_column_profile_image": (C.c_int, [vp, vp, i32, i32, C.c_double, C.c_int, C.c_double, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -230,6 +230,31 @@ class ColumnwiseMF(object):
         """Per-column nll margin used by the screen (selection is exact while its error is below half of it)."""
         return self._get(_lib.OUT_SCREEN_TOL, np.float64, (self.S,))
 
+    def column_profile(self, robust=False, p=0.95):
+        """Column profile of the scores of the last run (triage/cmf_profile.py:110-140): dict of (S,) arrays
+        ``npix, avg, std, min, max`` or, with ``robust``, ``npix, med, mad, p05, p95`` (float32 arithmetic as
+        in the reference, returned as float64)."""
+        out = np.empty((5, self.S), dtype=np.float64)
+        self._check(self._lib.cmf_column_profile(self._ctx, int(bool(robust)), float(p), C.c_void_p(out.ctypes.data)))
+        names = ("npix", "med", "mad", "p05", "p95") if robust else ("npix", "avg", "std", "min", "max")
+        return dict(zip(names, out))
+
+    def pixel_flags(self, cube, spec, on_device=False, shape=None):
+        """Per-pixel spectrometer flags (spectrometer_masks/masks_sds.py:133-230) of a float32 BIL cube: a host
+        array (L, B, S) or, with ``on_device``, a device address plus ``shape``.  ``spec`` is a _lib.FlagSpec."""
+        if on_device:
+            L, B, S = shape
+            ptr = int(cube)
+        else:
+            if cube.dtype != np.float32 or not cube.flags.c_contiguous or cube.ndim != 3:
+                raise CmfError("cube must be a C-contiguous float32 (lines, bands, samples) array")
+            L, B, S = cube.shape
+            ptr = cube.ctypes.data
+        out = np.empty((L, S), dtype=np.uint8)
+        self._check(self._lib.cmf_pixel_flags(self._ctx, C.c_void_p(ptr), int(bool(on_device)), L, B, S,
+                                              C.byref(spec), C.c_void_p(out.ctypes.data)))
+        return out
+
     def results(self):
         cs = self.colstats()
         return dict(mf=self.mf(), mask=self.mask(), colnum=cs[0], colavg=cs[1], colstd=cs[2],

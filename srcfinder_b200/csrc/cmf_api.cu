@@ -87,6 +87,9 @@ struct cmf_ctx {
     bool timed = false;
     bool screened = false;                          // the last run used the screening path
     int launches = 0;
+    // products either side of the filter (k_products.cu); independent of the problem buffers
+    uint8_t* flags_d = nullptr;
+    size_t flags_bytes = 0;
 };
 
 namespace {
@@ -345,6 +348,7 @@ OutDesc out_desc(const cmf_ctx* c, int what) {
         case CMF_OUT_LABELS: return {c->labels_d, c->labels_d ? LS * sizeof(int32_t) : 0};
         case CMF_OUT_PCA: return {c->ypca, c->auto_cluster ? LS * c->pcadim * sizeof(double) : 0};
         case CMF_OUT_KMEANS_ITERS: return {c->km_iters, c->auto_cluster ? (size_t)d.S * sizeof(int) : 0};
+        case CMF_OUT_FLAGS: return {c->flags_d, c->flags_bytes};
         default: return {nullptr, 0};
     }
 }
@@ -383,6 +387,7 @@ void cmf_destroy(cmf_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->flags_d) { cudaFree(ctx->flags_d); ctx->flags_d = nullptr; }
     free_buffers(ctx);
     for (int i = 0; i <= K_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (auto& set : ctx->ev_sets) for (cudaEvent_t e : set) cudaEventDestroy(e);
@@ -690,18 +695,21 @@ const char* cmf_screen_kernel(const cmf_ctx* ctx) {
 }
 
 size_t cmf_output_bytes(const cmf_ctx* ctx, int what) {
+    if (ctx && what == CMF_OUT_FLAGS) return ctx->flags_bytes;
     if (!ctx || !ctx->have_problem) return 0;
     return out_desc(ctx, what).bytes;
 }
 
 void* cmf_device_ptr(cmf_ctx* ctx, int what) {
+    if (ctx && what == CMF_OUT_FLAGS) return ctx->flags_d;
     if (!ctx || !ctx->have_problem) return nullptr;
     return out_desc(ctx, what).ptr;
 }
 
 int cmf_download(cmf_ctx* ctx, int what, void* host_dst, size_t bytes) {
     if (!ctx || !host_dst) return CMF_E_ARG;
-    if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_download before cmf_set_problem");
+    if (!ctx->have_problem && what != CMF_OUT_FLAGS)
+        return fail(ctx, CMF_E_STATE, "cmf_download before cmf_set_problem");
     CK(cudaSetDevice(ctx->device));
     const OutDesc o = out_desc(ctx, what);
     if (!o.ptr) return fail(ctx, CMF_E_ARG, "unknown output id");
@@ -709,6 +717,117 @@ int cmf_download(cmf_ctx* ctx, int what, void* host_dst, size_t bytes) {
     CK(cudaMemcpyAsync(host_dst, o.ptr, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return CMF_OK;
+}
+
+// ---- products either side of the filter ----
+int cmf_pixel_flags(cmf_ctx* ctx, const float* cube, int on_device, int32_t lines, int32_t bands, int32_t samples,
+                    const cmf_flag_spec* spec, uint8_t* flags_host) {
+    if (!ctx || !cube || !spec) return CMF_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (lines <= 0 || bands <= 0 || samples <= 0) return fail(ctx, CMF_E_ARG, "bad cube shape");
+    const int singles[4] = {spec->spec_band, spec->dark_band, spec->cloud_a, spec->cloud_b};
+    if (spec->sat_lo < 0 || spec->sat_hi >= bands || spec->sat_hi < spec->sat_lo)
+        return fail(ctx, CMF_E_ARG, "saturation window outside the cube");
+    for (int b : singles)
+        if (b >= bands) return fail(ctx, CMF_E_ARG, "flag band outside the cube");
+    if ((spec->cloud_a < 0) != (spec->cloud_b < 0)) return fail(ctx, CMF_E_ARG, "cloud test needs both bands");
+    const size_t LS = (size_t)lines * samples;
+    if (ctx->flags_bytes != LS) {
+        if (ctx->flags_d) { cudaFree(ctx->flags_d); ctx->flags_d = nullptr; ctx->flags_bytes = 0; }
+        void* q = nullptr;
+        if (cudaMalloc(&q, LS) != cudaSuccess) { cudaGetLastError(); return fail(ctx, CMF_E_NOMEM, "flags allocation failed"); }
+        ctx->flags_d = reinterpret_cast<uint8_t*>(q);
+        ctx->flags_bytes = LS;
+    }
+    FlagSpec f{spec->sat_lo, spec->sat_hi, spec->spec_band, spec->dark_band, spec->cloud_a, spec->cloud_b,
+               spec->sat_thresh, spec->spec_thresh, spec->dark_thresh, spec->cloud_thresh, spec->cloud_dwl};
+    float* packed = nullptr;
+    if (on_device) {
+        launch_pixel_flags(cube, (long long)bands * samples, samples, lines, samples, f, ctx->flags_d, ctx->stream);
+    } else {
+        // only the bands the tests read cross PCIe: the window as one strided copy, the single bands one each
+        const int nsat = spec->sat_hi - spec->sat_lo + 1;
+        const int nb = nsat + 4;
+        void* q = nullptr;
+        if (cudaMalloc(&q, LS * nb * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, CMF_E_NOMEM, "flag band buffer allocation failed");
+        }
+        packed = reinterpret_cast<float*>(q);
+        const size_t row = (size_t)samples * sizeof(float);
+        cudaError_t e = cudaMemcpy2DAsync(packed, row * nb, cube + (size_t)spec->sat_lo * samples, row * bands,
+                                          row * nsat, lines, cudaMemcpyHostToDevice, ctx->stream);
+        int idx[4];
+        for (int k = 0; k < 4 && e == cudaSuccess; ++k) {
+            idx[k] = singles[k] < 0 ? -1 : nsat + k;
+            if (singles[k] >= 0)
+                e = cudaMemcpy2DAsync(packed + (size_t)(nsat + k) * samples, row * nb,
+                                      cube + (size_t)singles[k] * samples, row * bands, row, lines,
+                                      cudaMemcpyHostToDevice, ctx->stream);
+        }
+        if (e != cudaSuccess) { cudaFree(packed); return fail(ctx, CMF_E_CUDA, std::string("flag band upload: ") + cudaGetErrorString(e)); }
+        f.sat_lo = 0; f.sat_hi = nsat - 1;
+        f.spec_band = idx[0]; f.dark_band = idx[1]; f.cloud_a = idx[2]; f.cloud_b = idx[3];
+        launch_pixel_flags(packed, (long long)nb * samples, samples, lines, samples, f, ctx->flags_d, ctx->stream);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && flags_host)
+        e = cudaMemcpyAsync(flags_host, ctx->flags_d, LS, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (packed) cudaFree(packed);
+    if (e != cudaSuccess) return fail(ctx, CMF_E_CUDA, std::string("cmf_pixel_flags: ") + cudaGetErrorString(e));
+    return CMF_OK;
+}
+
+namespace {
+int column_profile_impl(cmf_ctx* ctx, const double* mf_dev, int L, int S, double nodata, int robust, double p,
+                        double* out_host) {
+    void *colv = nullptr, *out = nullptr;
+    if (cudaMalloc(&colv, (size_t)L * S * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&out, (size_t)5 * S * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        if (colv) cudaFree(colv);
+        return fail(ctx, CMF_E_NOMEM, "profile scratch allocation failed");
+    }
+    // the percentiles the reference asks numpy for: q = (1 - p) * 100 and p * 100, then q / 100 inside numpy
+    const double qlo = ((1.0 - p) * 100.0) / 100.0, qhi = (p * 100.0) / 100.0;
+    launch_column_profile(mf_dev, L, S, nodata, robust, qlo, qhi, reinterpret_cast<float*>(colv),
+                          reinterpret_cast<double*>(out), ctx->stream);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(out_host, out, (size_t)5 * S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(colv);
+    cudaFree(out);
+    if (e != cudaSuccess) return fail(ctx, CMF_E_CUDA, std::string("cmf_column_profile: ") + cudaGetErrorString(e));
+    return CMF_OK;
+}
+}  // namespace
+
+int cmf_column_profile(cmf_ctx* ctx, int robust, double p, double* out_host) {
+    if (!ctx || !out_host) return CMF_E_ARG;
+    if (!ctx->have_problem || !ctx->mf) return fail(ctx, CMF_E_STATE, "cmf_column_profile before a run");
+    if (robust && !(p > 0.0 && p < 1.0)) return fail(ctx, CMF_E_ARG, "percentile fraction must be inside (0, 1)");
+    CK(cudaSetDevice(ctx->device));
+    return column_profile_impl(ctx, ctx->mf, ctx->d.L, ctx->d.S, ctx->nodata, robust, p, out_host);
+}
+
+int cmf_column_profile_image(cmf_ctx* ctx, const double* mf_host, int32_t lines, int32_t samples, double nodata,
+                             int robust, double p, double* out_host) {
+    if (!ctx || !mf_host || !out_host) return CMF_E_ARG;
+    if (lines <= 0 || samples <= 0) return fail(ctx, CMF_E_ARG, "bad image shape");
+    if (robust && !(p > 0.0 && p < 1.0)) return fail(ctx, CMF_E_ARG, "percentile fraction must be inside (0, 1)");
+    CK(cudaSetDevice(ctx->device));
+    void* img = nullptr;
+    const size_t bytes = (size_t)lines * samples * sizeof(double);
+    if (cudaMalloc(&img, bytes) != cudaSuccess) { cudaGetLastError(); return fail(ctx, CMF_E_NOMEM, "image allocation failed"); }
+    cudaError_t e = cudaMemcpyAsync(img, mf_host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = CMF_OK;
+    if (e != cudaSuccess) rc = fail(ctx, CMF_E_CUDA, std::string("image upload: ") + cudaGetErrorString(e));
+    else rc = column_profile_impl(ctx, reinterpret_cast<const double*>(img), lines, samples, nodata, robust, p, out_host);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(img);
+    return rc;
 }
 
 int cmf_kernel_count(void) { return K_COUNT; }

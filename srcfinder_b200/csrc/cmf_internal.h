@@ -35,6 +35,19 @@ struct Dims {
     int vec2;                // 8-byte loads allowed (S, pitches even and base aligned)
 };
 
+// per-pixel spectrometer flags (spectrometer_masks/masks_sds.py:133-233); band indices are 0-based positions
+// in the buffer handed to the kernel, < 0 disables a test
+enum : uint8_t { kFlagSaturated = 1, kFlagSpecular = 2, kFlagDark = 4, kFlagCloud = 8 };
+struct FlagSpec {
+    int sat_lo, sat_hi, spec_band, dark_band, cloud_a, cloud_b;
+    float sat_thresh, spec_thresh, dark_thresh, cloud_thresh, cloud_dwl;
+};
+void launch_pixel_flags(const float* cube, long long line_pitch, int band_pitch, int L, int S, const FlagSpec& f,
+                        uint8_t* flags, cudaStream_t st);
+// column profiles of a score image (triage/cmf_profile.py:110-140); colv is [S][L] float scratch, out [5][S]
+void launch_column_profile(const double* mf, int L, int S, double nodata, int robust, double qlo, double qhi,
+                           float* colv, double* out, cudaStream_t st);
+
 inline int ntri(int nt) { return nt * (nt + 1) / 2; }
 
 void launch_repack(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,

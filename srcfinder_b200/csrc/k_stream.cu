@@ -202,8 +202,8 @@ __device__ __forceinline__ int repack_key(int c) {
 }
 
 // resident CTAs per SM the register allocation is held to: what shared memory (227 KB) and threads (2048) allow
-constexpr int repack_pipe_minb(int nt, int cg, int lt) {
-    const int by_smem = (227 * 1024) / (2 * cg * (lt * 8 * nt + 4) * 4 + 1024 + 256);
+constexpr int repack_pipe_minb(int nt, int cg, int lt, int ns) {
+    const int by_smem = (227 * 1024) / (ns * cg * (lt * 8 * nt + 4) * 4 + 1024 + 256);
     const int by_thr = 2048 / (cg * 2 * nt);
     const int m = by_smem < by_thr ? by_smem : by_thr;
     return m < 1 ? 1 : (m > 4 ? 4 : m);
@@ -241,14 +241,14 @@ __device__ __forceinline__ void repack_pass_a(const float* src, int nl, int c, u
     }
 }
 
-template <int NT, int CG, int LT>
-__global__ void __launch_bounds__(CG * 2 * NT, repack_pipe_minb(NT, CG, LT)) repack_pipe_kernel(
+template <int NT, int CG, int LT, int NS>
+__global__ void __launch_bounds__(CG * 2 * NT, repack_pipe_minb(NT, CG, LT, NS)) repack_pipe_kernel(
     const float* __restrict__ slab, long long line_pitch, int band_pitch, int L, int S, int D,
     float* __restrict__ xt, uint8_t* __restrict__ mask, double* __restrict__ colsum_part,
     int* __restrict__ colcnt_part, int lines_per_split, int line_base, int line_limit, int split_base,
     const uint8_t* __restrict__ sel, int write_mask) {
     constexpr int DP = 8 * NT, Q = 2 * NT, NTH = CG * Q, CS = LT * DP + 4;
-    extern __shared__ __align__(16) float tile[];   // [2][CG][CS]
+    extern __shared__ __align__(16) float tile[];   // [NS][CG][CS]: ring of NS tiles
     __shared__ uint8_t bad[2][LT * CG];
 
     const int tid = threadIdx.x;
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(CG * 2 * NT, repack_pipe_minb(NT, CG, LT)) rep
     const bool col_ok = s0 + c < S;
     const int key = repack_key<CG>(c);
 
-    for (int i = tid; i < 2 * CG * CS; i += NTH) tile[i] = 0.0f;      // padded bands stay zero for good
+    for (int i = tid; i < NS * CG * CS; i += NTH) tile[i] = 0.0f;      // padded bands stay zero for good
     for (int i = tid; i < 2 * LT * CG; i += NTH) (&bad[0][0])[i] = 0;
     __syncthreads();
 
@@ -300,19 +300,22 @@ __global__ void __launch_bounds__(CG * 2 * NT, repack_pipe_minb(NT, CG, LT)) rep
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     int cnt = 0;
     const int ntiles = (l_end - l_begin + LT - 1) / LT;
-    if (ntiles > 0) issue(0, l_begin, min(LT, l_end - l_begin));
+    // ring of NS tiles: tiles it .. it+NS-1 are in flight while tile `it` is consumed.  One commit group per
+    // tile slot (empty past the end), so "all but the NS-1 newest groups complete" always means tile `it`.
+#pragma unroll
+    for (int p = 0; p < NS - 1; ++p) {
+        if (p < ntiles) issue(p, l_begin + p * LT, min(LT, l_end - (l_begin + p * LT)));
+        else cp_async_commit();
+    }
+    int buf = 0, nbuf = NS - 1;
     for (int it = 0; it < ntiles; ++it) {
         const int l0 = l_begin + it * LT;
         const int nl = min(LT, l_end - l0);
-        const int buf = it & 1;
-        if (it + 1 < ntiles) {
-            issue(buf ^ 1, l0 + LT, min(LT, l_end - l0 - LT));
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+        if (it + NS - 1 < ntiles) issue(nbuf, l0 + (NS - 1) * LT, min(LT, l_end - l0 - (NS - 1) * LT));
+        else cp_async_commit();
+        cp_async_wait<NS - 1>();
         __syncthreads();                                   // tile `it` has landed for every thread
-        uint8_t* bd = bad[buf];
+        uint8_t* bd = bad[it & 1];
         float4 v[LT];
         if (col_ok) {
             const float* src = tile + (size_t)(buf * CG + c) * CS + 4 * q;
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(CG * 2 * NT, repack_pipe_minb(NT, CG, LT)) rep
                 if (write_mask) mask[o] = bd[i] ? 0 : 1;
                 if (sel != nullptr && sel[o] == 0) bd[i] = 1;
             }
-            bad[buf ^ 1][i] = 0;                            // flags of the next tile (last read one tile ago)
+            bad[(it & 1) ^ 1][i] = 0;                       // flags of the next tile (last read one tile ago)
         }
         if (sel != nullptr) __syncthreads();
         if (col_ok) {
@@ -354,6 +357,8 @@ __global__ void __launch_bounds__(CG * 2 * NT, repack_pipe_minb(NT, CG, LT)) rep
                 }
             }
         }
+        nbuf = buf;
+        buf = buf + 1 == NS ? 0 : buf + 1;
     }
     if (col_ok) {
         double* o = colsum_part + ((long long)split * S + s0 + c) * DP + 4 * q;
@@ -617,31 +622,45 @@ __global__ void colstats_kernel(const double* __restrict__ stat_part, int nlanes
 }
 
 // ---------------------------------------------------------------------------------------- launchers
-// Repack plan: tile shape (CG columns x LT lines) of the pipelined kernel.  CG == 0 selects the older
-// single-stage kernel (kept for A/B measurements through tools/).
-struct RepackVariant { int cg, lt; };
+// Repack plan: tile shape (CG columns x LT lines) and ring depth NS of the pipelined kernel.  CG == 0 selects
+// the older single-stage kernel (kept for A/B measurements through tools/).
+struct RepackVariant { int cg, lt, ns; };
 
-static RepackVariant repack_variant() {
-    // tuning hook (tools/ only): CMF_REPACK_VARIANT=CG,LT picks another instantiation, "0,0" the old kernel
+#define CMF_REPACK_VARIANTS(X) X(32, 8, 2) X(32, 8, 3) X(32, 4, 3) X(32, 4, 4) X(16, 8, 3) X(16, 4, 2) X(16, 4, 3) X(16, 4, 4)
+
+static RepackVariant repack_variant_requested() {
+    // tuning hook (tools/ only): CMF_REPACK_VARIANT=CG,LT,NS picks another instantiation, "0,0,0" the old kernel
     static RepackVariant v = [] {
-        RepackVariant r{32, 8};     // measured best on B200 (profiles/r01g_tune_repack.json)
-        if (const char* e = getenv("CMF_REPACK_VARIANT")) sscanf(e, "%d,%d", &r.cg, &r.lt);
-        const bool known = (r.cg == 0) || ((r.cg == 16 || r.cg == 32) && (r.lt == 4 || r.lt == 8));
-        if (!known) r = RepackVariant{32, 8};
-        return r;
+        const RepackVariant dflt{32, 4, 4};     // measured best on B200 (profiles/r01g_tune_repack.json)
+        RepackVariant r = dflt;
+        if (const char* e = getenv("CMF_REPACK_VARIANT")) sscanf(e, "%d,%d,%d", &r.cg, &r.lt, &r.ns);
+        bool known = r.cg == 0;
+#define CMF_RV(CGv, LTv, NSv) known = known || (r.cg == CGv && r.lt == LTv && r.ns == NSv);
+        CMF_REPACK_VARIANTS(CMF_RV)
+#undef CMF_RV
+        return known ? r : dflt;
     }();
     return v;
 }
 
-template <int NT, int CG, int LT>
-static size_t repack_pipe_smem() { return (size_t)2 * CG * (LT * 8 * NT + 4) * sizeof(float); }
+// the variant that is launched for NT band tiles: a ring that does not fit shared memory at this band count
+// falls back to the two-stage (16, 4) tile
+static RepackVariant repack_variant(int nt) {
+    const RepackVariant v = repack_variant_requested();
+    if (v.cg > 0 && (size_t)v.ns * v.cg * (v.lt * 8 * nt + 4) * sizeof(float) > 227 * 1024) return RepackVariant{16, 4, 2};
+    return v;
+}
 
-template <int NT, int CG, int LT>
+template <int NT, int CG, int LT, int NS>
+static size_t repack_pipe_smem() { return (size_t)NS * CG * (LT * 8 * NT + 4) * sizeof(float); }
+
+template <int NT, int CG, int LT, int NS>
 static int repack_pipe_resident() {
-    const size_t smem = repack_pipe_smem<NT, CG, LT>();
-    cudaFuncSetAttribute(repack_pipe_kernel<NT, CG, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = repack_pipe_smem<NT, CG, LT, NS>();
+    if (smem > 227 * 1024) return 0;
+    cudaFuncSetAttribute(repack_pipe_kernel<NT, CG, LT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, repack_pipe_kernel<NT, CG, LT>, CG * 2 * NT, smem) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, repack_pipe_kernel<NT, CG, LT, NS>, CG * 2 * NT, smem) !=
         cudaSuccess) {
         cudaGetLastError();
         nb = 0;
@@ -651,10 +670,10 @@ static int repack_pipe_resident() {
 
 template <int NT>
 static int repack_resident_t(const RepackVariant& v) {
-    if (v.cg == 16 && v.lt == 8) return repack_pipe_resident<NT, 16, 8>();
-    if (v.cg == 16 && v.lt == 4) return repack_pipe_resident<NT, 16, 4>();
-    if (v.cg == 32 && v.lt == 4) return repack_pipe_resident<NT, 32, 4>();
-    if (v.cg == 32 && v.lt == 8) return repack_pipe_resident<NT, 32, 8>();
+#define CMF_RV(CGv, LTv, NSv) \
+    if (v.cg == CGv && v.lt == LTv && v.ns == NSv) return repack_pipe_resident<NT, CGv, LTv, NSv>();
+    CMF_REPACK_VARIANTS(CMF_RV)
+#undef CMF_RV
     return 0;
 }
 
@@ -678,7 +697,7 @@ static int repack_resident_t(const RepackVariant& v) {
 // Line ranges per column group.  The pipelined kernel is launched as (at most) one resident wave: every CTA
 // streams its whole line range, so the ranges are sized to fill the SMs' resident slots once.
 int repack_nsplit(const Dims& d) {
-    const RepackVariant v = repack_variant();
+    const RepackVariant v = repack_variant(d.NT);
     if (v.cg > 0) {
         int resident = 0, sms = 148, dev = 0;
         CMF_NT_SWITCH(d.NT, (resident = repack_resident_t<NTc>(v)));
@@ -687,6 +706,7 @@ int repack_nsplit(const Dims& d) {
         if (resident > 0) {
             const int groups = (d.S + v.cg - 1) / v.cg;
             int ns = (sms * resident) / groups;
+            if (const char* e = getenv("CMF_REPACK_NSPLIT")) ns = atoi(e);      // tuning hook (tools/ only)
             const int maxsplit = (d.L + 4 * v.lt - 1) / (4 * v.lt);     // at least 4 tiles per CTA
             if (ns > maxsplit) ns = maxsplit;
             return ns < 1 ? 1 : ns;
@@ -699,31 +719,31 @@ int repack_nsplit(const Dims& d) {
     return ns < 1 ? 1 : ns;
 }
 
-template <int NT, int CG, int LT>
+template <int NT, int CG, int LT, int NS>
 static void launch_repack_pipe(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,
                                int* colcnt_part, int lps, int line_base, int line_limit, int split_base,
                                const uint8_t* sel, int write_mask, cudaStream_t st) {
-    const size_t smem = repack_pipe_smem<NT, CG, LT>();
-    cudaFuncSetAttribute(repack_pipe_kernel<NT, CG, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = repack_pipe_smem<NT, CG, LT, NS>();
+    cudaFuncSetAttribute(repack_pipe_kernel<NT, CG, LT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int nblk = (line_limit - line_base + lps - 1) / lps;
     if (nblk <= 0) return;
     dim3 grid((d.S + CG - 1) / CG, nblk);
-    repack_pipe_kernel<NT, CG, LT><<<grid, CG * 2 * NT, smem, st>>>(slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D,
-                                                                    xt, mask, colsum_part, colcnt_part, lps,
-                                                                    line_base, line_limit, split_base, sel,
-                                                                    write_mask);
+    repack_pipe_kernel<NT, CG, LT, NS><<<grid, CG * 2 * NT, smem, st>>>(slab, d.line_pitch, d.band_pitch, d.L, d.S,
+                                                                        d.D, xt, mask, colsum_part, colcnt_part, lps,
+                                                                        line_base, line_limit, split_base, sel,
+                                                                        write_mask);
 }
 
 template <int NT>
 static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,
                             int* colcnt_part, int lps, int line_base, int line_limit, int split_base,
                             const uint8_t* sel, int write_mask, cudaStream_t st) {
-    const RepackVariant v = repack_variant();
-#define CMF_RV(CGv, LTv)                                                                                     \
-    if (v.cg == CGv && v.lt == LTv)                                                                          \
-        return launch_repack_pipe<NT, CGv, LTv>(d, slab, xt, mask, colsum_part, colcnt_part, lps, line_base, \
-                                                line_limit, split_base, sel, write_mask, st);
-    CMF_RV(16, 8) CMF_RV(16, 4) CMF_RV(32, 4) CMF_RV(32, 8)
+    const RepackVariant v = repack_variant(NT);
+#define CMF_RV(CGv, LTv, NSv)                                                                                \
+    if (v.cg == CGv && v.lt == LTv && v.ns == NSv)                                                   \
+        return launch_repack_pipe<NT, CGv, LTv, NSv>(d, slab, xt, mask, colsum_part, colcnt_part, lps,       \
+                                                     line_base, line_limit, split_base, sel, write_mask, st);
+    CMF_REPACK_VARIANTS(CMF_RV)
 #undef CMF_RV
     constexpr int DP = 8 * NT;
     const size_t smem = (size_t)kRepackLT * DP * (kRepackCG + 1) * sizeof(float);

@@ -1,0 +1,121 @@
+"""The steps either side of the filter through the C ABI against their CPU oracles:
+per-pixel spectrometer flags (bit-exact) and column profiles (bit-exact in float32: numpy's own evaluation order
+is replayed on the device)."""
+import numpy as np
+import pytest
+
+from oracle import products_oracle as po
+from srcfinder_b200 import ColumnwiseMF, cmf_profile, envi, masks, synth
+
+pytestmark = pytest.mark.gpu
+
+ACTIVE = [351, 422]
+
+
+def _wavelengths(nb=425):
+    return 376.86 + 5.0087 * np.arange(nb)          # AVIRIS-NG band centres (nm), ~5 nm sampling
+
+
+def _flag_cube(L, S, seed):
+    rng = np.random.default_rng(seed)
+    cube = synth.make_cube(L, S, seed=seed, bad_pixels=True)
+    pick = lambda frac: rng.random((L, S)) < frac
+    sat = pick(0.02)
+    cube[:, 400, :][sat] = 7.5                       # saturated in the SWIR window
+    cube[:, 25, :][sat & pick(0.5)] = 9.5            # ... and bright in the visible: specular
+    cube[:, 25, :][pick(0.01)] = 11.0                # bright at band 25 alone is not specular
+    cube[:, 352, :][pick(0.03)] = 0.05               # dark at 2139 nm
+    cube[:, 352, :][pick(0.01)] = -9999.0            # no-data is not dark
+    cube[:, 352, :][pick(0.005)] = np.float32(0.104)  # exactly the threshold (float32): not dark
+    cld = pick(0.03)
+    cube[:, 15, :][cld] = 18.0
+    cube[:, 60, :][cld] = np.where(rng.random(cld.sum()) < 0.5, 12.0, 25.0)   # negative / positive slope
+    cube[:, 313, :][pick(0.002)] = 6.5               # first band of the window
+    cube[:, 312, :][pick(0.002)] = 50.0              # just outside the window
+    cube[:, 420, :][pick(0.002)] = np.nan            # NaN never compares greater
+    cube[:, 421, :][pick(0.002)] = np.float32(6.0)   # equal to the threshold: not saturated
+    return cube
+
+
+def test_pixel_flags_against_oracle():
+    L, S = 300, 50
+    cube = _flag_cube(L, S, seed=21)
+    wave = _wavelengths()
+    ref = po.pixel_flags(cube, wave)
+    got = masks.pixel_flags(cube, wave)
+    assert got.dtype == np.uint8 and got.shape == (L, S)
+    assert np.array_equal(got, ref)
+    for bit in (masks.SATURATED, masks.SPECULAR, masks.DARK, masks.CLOUD):
+        assert (ref & bit).any(), "fixture must exercise bit %d" % bit
+    assert not ((ref & masks.SPECULAR).astype(bool) & ~(ref & masks.SATURATED).astype(bool)).any()
+
+
+def test_pixel_flags_device_cube_and_options():
+    import torch
+    L, S = 128, 37                                   # odd sample count: unaligned rows
+    cube = _flag_cube(L, S, seed=22)
+    wave = _wavelengths()
+    kw = dict(threshold=5.0, waverange=(2000, 2400), dark_threshold=0.2, cldthreshold=[10.0],
+              visible_mask_growing_threshold=8.0)
+    ref = po.pixel_flags(cube, wave, threshold=5.0, waverange=(2000, 2400), dark_threshold=0.2, cldthreshold=(10.0,),
+                         visible_mask_growing_threshold=8.0)
+    assert np.array_equal(masks.pixel_flags(cube, wave, **kw), ref)
+    dev = torch.from_numpy(cube).cuda()
+    with ColumnwiseMF(L, 425, S, ACTIVE, synth.load_ch4_library()[ACTIVE[0] - 1:ACTIVE[1], 2]) as eng:
+        got = eng.pixel_flags(dev.data_ptr(), masks.flag_spec(wave, **kw), on_device=True, shape=(L, 425, S))
+    assert np.array_equal(got, ref)
+
+
+def _score_image(L, S, seed):
+    rng = np.random.default_rng(seed)
+    mf = rng.normal(0.0, 420.0, (L, S)) * rng.uniform(0.5, 2.0, S)[None, :]
+    mf[rng.random((L, S)) < 0.03] = -9999.0
+    mf[rng.random((L, S)) < 0.002] = np.nan
+    mf[:, 3] = -9999.0                               # a skipped column
+    mf[:, 5] = -np.abs(mf[:, 5])                     # no positive pixel
+    mf[: L - 1, 7] = -9999.0
+    mf[L - 1, 7] = 12.5                              # a single valid pixel
+    mf[2:, 8] = -9999.0
+    mf[:2, 8] = (3.0, 8.0)                           # two valid pixels: the even-count median
+    return mf
+
+
+@pytest.mark.parametrize("robust", [False, True])
+def test_column_profile_image_bit_exact(robust):
+    L, S = 3001, 23
+    mf = _score_image(L, S, seed=31)
+    ref = po.column_profile(mf, -9999, use_robust_stats=robust)
+    got = cmf_profile.column_profile_image(mf, -9999.0, robust=robust)
+    assert list(got) == list(ref)
+    for k in ref:
+        r = np.asarray(ref[k], dtype=np.float64)
+        assert np.array_equal(got[k], r, equal_nan=True), (k, np.flatnonzero(got[k] != r)[:5])
+    assert got["npix"][3] == 0 and np.isnan(got[list(got)[1]][3])
+
+
+def test_column_profile_of_a_run_and_cli(tmp_path):
+    """Profile of the scores left on the device by a run == profile of the product on disk == oracle."""
+    L, S = 1500, 12
+    cube = synth.make_cube(L, S, seed=33, bad_pixels=True)
+    ab = synth.load_ch4_library()[ACTIVE[0] - 1:ACTIVE[1], 2]
+    with ColumnwiseMF(L, 425, S, ACTIVE, ab) as eng:
+        eng.upload(cube)
+        eng.run()
+        mf = eng.mf()
+        plain, robust = eng.column_profile(), eng.column_profile(robust=True)
+    for got, ref in ((plain, po.column_profile(mf)), (robust, po.column_profile(mf, use_robust_stats=True))):
+        for k in ref:
+            assert np.array_equal(got[k], np.asarray(ref[k], dtype=np.float64), equal_nan=True), k
+    # the CLI on a 4-band BIP product (triage/cmf_profile.py:92-135)
+    out = str(tmp_path / "ang_cmf")
+    mm = envi.create_image(out, {"samples": S, "lines": L, "bands": 4, "data type": 5, "interleave": "bip",
+                                 "byte order": 0, "data ignore value": -9999})
+    mm[..., 3] = mf
+    mm.flush()
+    assert cmf_profile.main(["--robust", "--outdir", str(tmp_path), out]) == 0
+    rows = open(str(tmp_path / "ang_cmf_column_stats.csv")).read().splitlines()
+    assert rows[0] == "npix,med,mad,p05,p95" and len(rows) == S + 1
+    vals = np.array([[float(t) if t else np.nan for t in r.split(",")] for r in rows[1:]])
+    for j, k in enumerate(("npix", "med", "mad", "p05", "p95")):
+        assert np.array_equal(vals[:, j], robust[k], equal_nan=True)
+    assert cmf_profile.summarize(out, str(tmp_path), True) is False      # exists -> skipped (:104-106)

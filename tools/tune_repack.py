@@ -1,5 +1,5 @@
-"""Tuning sweep of the repack pass (GPU box): one subprocess per CMF_REPACK_VARIANT ("0,0" = the single-stage
-kernel).  Every variant must give the same masks / alpha indices, and scores equal to ~1e-9 sigma."""
+"""Tuning sweep of the repack pass (GPU box): one subprocess per CMF_REPACK_VARIANT ("0,0,0" = the single-stage
+kernel; "CG,LT,NS:nsplit" also forces the number of line ranges).  Every variant must give the same masks / alpha indices, and scores equal to ~1e-9 sigma."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = r'''
@@ -25,8 +25,11 @@ with ColumnwiseMF(L, 425, S, active, ab) as eng:
                       "colstd_sum": float(cs[2].sum()), "colavg_absmax": float(np.abs(cs[1]).max())}))
 ''' % ROOT
 out = {}
-for v in ["0,0", "16,8", "16,4", "32,4", "32,8"]:
-    env = dict(os.environ, CMF_REPACK_VARIANT=v)
+VARIANTS = ["0,0,0", "32,8,2", "32,8,3", "32,4,3", "32,4,4", "16,8,3", "16,4,2", "16,4,3", "16,4,4"]
+for v in sys.argv[1:] or VARIANTS:
+    env = dict(os.environ, CMF_REPACK_VARIANT=v.split(":")[0])
+    if ":" in v:
+        env["CMF_REPACK_NSPLIT"] = v.split(":")[1]
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
     line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-600:]
     print(v, line, flush=True)
