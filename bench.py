@@ -247,12 +247,12 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": float(np.mean(secs) * 1e3) if secs else None, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -280,6 +280,11 @@ def run_gpu(args):
                          "(use --impl reference for the host baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    try:
+        gpu_uuid = torch.cuda.get_device_properties(dev).uuid
+    except Exception:
+        gpu_uuid = None
+    cpus_bound = bind_to_gpu_numa_node(gpu_uuid, local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -318,10 +323,6 @@ def run_gpu(args):
         step(False)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    try:
-        gpu_uuid = torch.cuda.get_device_properties(dev).uuid
-    except Exception:
-        gpu_uuid = None
     with ClockSampler(local, gpu_uuid) as clocks:
         barrier()
         ev0.record(stream)
@@ -397,7 +398,7 @@ def run_gpu(args):
     if rank == 0:
         if not args.no_cpu and world == 1:
             out["cpu_baseline"] = cpu_baseline_leg(L, budget_s=args.cpu_seconds)
-        print(json.dumps(out))
+        emit(out)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -487,6 +488,46 @@ def load_traffic():
     return {}
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner under NCCL_DEBUG, worker
+    processes) also write to fd 1, so everything else is pointed at stderr and the result line goes to a
+    private duplicate of the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
+def bind_to_gpu_numa_node(uuid, index):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity) before the pinned host cube is
+    allocated, so the flightline a rank streams over PCIe sits in the memory of the socket the GPU hangs off."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(uuid)) if uuid else None
+        except Exception:
+            h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -500,6 +541,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

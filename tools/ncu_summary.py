@@ -44,7 +44,8 @@ def main():
     lines = ["| kernel | " + " | ".join(k for k, _ in METRICS) + " |", "|---|" + "---|" * len(METRICS)]
     traffic = {}
     for r in data:
-        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("cmf::", "")
+        name = r[idx["Kernel Name"]].replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("unnamed>::", "")
+        name = name.split("(")[0].replace("void ", "").replace("cmf::", "")
         cells = []
         vals = {}
         for key, m in METRICS:
