@@ -126,6 +126,14 @@ int cmf_set_clustering(cmf_ctx* ctx, int kmodes, int pcadim, int reject_min, int
  * Cholesky whitening ahead of the same eigen-solve.  No effect on unimodal runs (the reference tests bgmodes > 1). */
 int cmf_set_regfull(cmf_ctx* ctx, int enable);
 
+/* Opt-in, default off (= the reference's behaviour): keep pixels out of the BACKGROUND STATISTICS.  A pixel with
+ * exclude[l*S + s] != 0 -- e.g. the saturated / specular / dark / cloud pixels cmf_pixel_flags() reports
+ *  -- does not enter the column mean (:347), the covariance (:52-70) or the alpha search
+ * (:105-127, n = the pixels that do).  Every valid pixel (:282) is still scored with the resulting filter and
+ * CMF_OUT_COLSTATS covers every scored pixel; CMF_OUT_NVALID then holds the background count.  Unimodal runs
+ * only (ignored while labels / clustering are set).  exclude == NULL returns to the default.  Host pointer. */
+int cmf_set_exclusion(cmf_ctx* ctx, const uint8_t* exclude);
+
 /* ---- compute: the whole column loop (:297-392) for every column, no host round trip ---- */
 enum {
     CMF_RUN_TIMING = 1,           /* bracket every kernel with CUDA events (see cmf_kernel_times) */

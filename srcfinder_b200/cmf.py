@@ -125,6 +125,17 @@ class ColumnwiseMF(object):
         """``-f``: regularise every mode fit with the covariance of the whole column (cmf/robust_mf.py:358)."""
         self._check(self._lib.cmf_set_regfull(self._ctx, 1 if enable else 0))
 
+    def set_exclusion(self, exclude):
+        """Opt-in (default off = reference behaviour): pixels where ``exclude`` (L, S) is true stay out of the
+        background statistics (mean, covariance, alpha search) but are still scored; ``None`` clears."""
+        if exclude is None:
+            self._check(self._lib.cmf_set_exclusion(self._ctx, C.c_void_p(None)))
+            return
+        ex = np.ascontiguousarray(np.asarray(exclude) != 0, dtype=np.uint8)
+        if ex.shape != (self.L, self.S):
+            raise CmfError("exclusion mask must be (lines, samples) = %r, got %r" % ((self.L, self.S), ex.shape))
+        self._check(self._lib.cmf_set_exclusion(self._ctx, C.c_void_p(ex.ctypes.data)))
+
     def labels(self):
         return self._get(_lib.OUT_LABELS, np.int32, (self.L, self.S))
 

@@ -90,6 +90,9 @@ struct cmf_ctx {
     // products either side of the filter (k_products.cu); independent of the problem buffers
     uint8_t* flags_d = nullptr;
     size_t flags_bytes = 0;
+    // opt-in exclusion of pixels from the background statistics (cmf_set_exclusion): 1 = pixel takes part
+    bool have_excl = false;
+    uint8_t* excl_sel = nullptr;
 };
 
 namespace {
@@ -218,6 +221,7 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
     mark(0);
     // ---- pass over every valid pixel: validity mask, column-major copy, column sums
     const bool chased = blocks_ready != nullptr && !modes;
+    const uint8_t* excl = (!modes && ctx->have_excl) ? ctx->excl_sel : nullptr;
     if (blocks_ready) {
         // one block = one Gram chunk: its repack and (unimodal) its Gram partial run as soon as its copy lands
         int line = 0;
@@ -225,7 +229,7 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
             const int lim = std::min(d.L, line + lines_per_block);
             cudaStreamWaitEvent(st, (*blocks_ready)[b], 0);
             launch_repack(d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, line,
-                          lim, nullptr, 1, st);
+                          lim, excl, 1, st);
             ++ctx->launches;
             if (chased) {
                 if (b == 0) {
@@ -240,14 +244,21 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
         }
     } else {
         launch_repack(d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, 0, d.L,
-                      nullptr, 1, st);
+                      excl, 1, st);
         ++ctx->launches;
     }
     mark(1);
     if (!modes) {
         fit_and_score(ctx, exact, nullptr, nullptr, mark, chased);
-        launch_colstats(d, ctx->stat_part, ctx->nlanes, ctx->n, ctx->nodata, ctx->colstats, st);
-        ++ctx->launches;
+        if (excl) {
+            // every valid pixel was scored, the statistics count them all (n holds the background pixels only)
+            launch_count_mask(d, ctx->mask, ctx->nuse, st);
+            launch_colstats_modes(d, ctx->mf, ctx->mask, ctx->nuse, ctx->nodata, ctx->colstats, st);
+            ctx->launches += 2;
+        } else {
+            launch_colstats(d, ctx->stat_part, ctx->nlanes, ctx->n, ctx->nodata, ctx->colstats, st);
+            ++ctx->launches;
+        }
         mark(11);
     } else {
         // ---- background modes (cmf/robust_mf.py:306-344): one fit-and-score pass per mode-list entry
@@ -432,6 +443,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     ctx->labels_d = nullptr; ctx->sel = nullptr; ctx->inlier = nullptr; ctx->cluster_img = nullptr;
     ctx->alpha_img = nullptr;
     ctx->auto_cluster = false; ctx->regfull = false; ctx->y_pd = 0;
+    ctx->have_excl = false; ctx->excl_sel = nullptr;
     ctx->gram_full = nullptr; ctx->vtop = nullptr; ctx->ypca = nullptr; ctx->pick = nullptr;
     ctx->km_iters = nullptr; ctx->lab8 = nullptr;
     Dims& d = ctx->d;
@@ -627,6 +639,23 @@ int cmf_set_regfull(cmf_ctx* ctx, int enable) {
         if (rc) return rc;
     }
     ctx->regfull = enable != 0;
+    return CMF_OK;
+}
+
+int cmf_set_exclusion(cmf_ctx* ctx, const uint8_t* exclude) {
+    if (!ctx) return CMF_E_ARG;
+    if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_set_exclusion before cmf_set_problem");
+    CK(cudaSetDevice(ctx->device));
+    if (!exclude) { ctx->have_excl = false; return CMF_OK; }
+    const size_t LS = (size_t)ctx->d.L * ctx->d.S;
+    if (!ctx->excl_sel) {
+        cudaError_t e = dalloc(ctx, &ctx->excl_sel, LS);
+        if (e != cudaSuccess) return fail(ctx, CMF_E_NOMEM, std::string("exclusion buffer: ") + cudaGetErrorString(e));
+    }
+    CK(cudaMemcpyAsync(ctx->excl_sel, exclude, LS, cudaMemcpyHostToDevice, ctx->stream));
+    launch_invert_u8(ctx->excl_sel, (long long)LS, ctx->stream);      // exclude != 0  ->  sel = 0
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_excl = true;
     return CMF_OK;
 }
 

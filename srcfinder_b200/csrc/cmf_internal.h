@@ -42,6 +42,9 @@ struct FlagSpec {
     int sat_lo, sat_hi, spec_band, dark_band, cloud_a, cloud_b;
     float sat_thresh, spec_thresh, dark_thresh, cloud_thresh, cloud_dwl;
 };
+// exclusion support: sel = (exclude == 0), per-column count of the valid-pixel mask
+void launch_invert_u8(uint8_t* p, long long n, cudaStream_t st);
+void launch_count_mask(const Dims& d, const uint8_t* mask, int* count, cudaStream_t st);
 void launch_pixel_flags(const float* cube, long long line_pitch, int band_pitch, int L, int S, const FlagSpec& f,
                         uint8_t* flags, cudaStream_t st);
 // column profiles of a score image (triage/cmf_profile.py:110-140); colv is [S][L] float scratch, out [5][S]

@@ -55,6 +55,37 @@ void launch_pixel_flags(const float* cube, long long line_pitch, int band_pitch,
     pixel_flags_kernel<<<grid, 256, 0, st>>>(cube, line_pitch, band_pitch, L, S, f, flags);
 }
 
+// ---------------------------------------------------------------------------------------- exclusion helpers
+__global__ void invert_u8_kernel(uint8_t* p, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = p[i] ? 0 : 1;
+}
+
+void launch_invert_u8(uint8_t* p, long long n, cudaStream_t st) {
+    invert_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n);
+}
+
+// valid pixels per column (nuse, cmf/robust_mf.py:302) from the mask image; one CTA per column, fixed order
+__global__ void __launch_bounds__(256) count_mask_kernel(const uint8_t* __restrict__ mask, int L, int S,
+                                                         int* __restrict__ count) {
+    __shared__ int red[8];
+    const int s = blockIdx.x;
+    int c = 0;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) c += mask[(long long)l * S + s] ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        count[s] = t;
+    }
+}
+
+void launch_count_mask(const Dims& d, const uint8_t* mask, int* count, cudaStream_t st) {
+    count_mask_kernel<<<d.S, 256, 0, st>>>(mask, d.L, d.S, count);
+}
+
 // ---------------------------------------------------------------------------------------- profiles
 // K-P0: score image f64 [L][S] -> float32 [S][L] (the reference converts to float32 first, cmf_profile.py:112),
 // NaN where the pixel is no-data, NaN or not positive (:113-114, :122).  32x32 transposing tiles.

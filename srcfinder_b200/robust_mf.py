@@ -52,6 +52,10 @@ def build_parser():
                    help="model name (looshrinkage (default)|empirical)")
     p.add_argument("--active", type=str, default=None,
                    help="extension: explicit 1-based active window lo,hi (other sensors, e.g. EMIT)")
+    p.add_argument("--exclude", type=str, default=None,
+                   help="extension, default off: comma-separated spectrometer flags (saturated,specular,dark,cloud; "
+                        "spectrometer_masks/masks_sds.py tests) whose pixels stay out of the background statistics "
+                        "(they are still scored); needs a 'wavelength' list in the input header")
     p.add_argument("--device", type=int, default=0, help="extension: CUDA device index")
     p.add_argument("input", type=str, metavar="INPUT", help="path to input image")
     p.add_argument("library", type=str, metavar="LIBRARY", help="path to target library file")
@@ -136,6 +140,23 @@ def run(args, log=print):
     with ColumnwiseMF(L, B, S, active, abscf, model=args.model, reflectance=args.reflectance,
                       alphas=alpha_grid(), nodata=nodata, device=args.device) as eng:
         eng.upload(cube)
+        if args.exclude:
+            if args.kmeans > 1:
+                raise CmfError("--exclude applies to unimodal runs only")
+            from . import masks
+            names = {"saturated": masks.SATURATED, "specular": masks.SPECULAR, "dark": masks.DARK,
+                     "cloud": masks.CLOUD}
+            bits = 0
+            for tok in args.exclude.split(","):
+                if tok.strip() not in names:
+                    raise CmfError("unknown flag %r in --exclude" % tok)
+                bits |= names[tok.strip()]
+            if "wavelength" not in meta:
+                raise CmfError("--exclude needs the band wavelengths in the input header")
+            wave = np.array([float(w) for w in meta["wavelength"]])
+            flags = eng.pixel_flags(cube, masks.flag_spec(wave))
+            eng.set_exclusion((flags & bits) != 0)
+            log("excluding %d flagged pixels from the background statistics" % int(((flags & bits) != 0).sum()))
         if args.kmeans > 1:
             # PCA + k-means partition on the device (:306-313; deterministic, the reference's is unseeded),
             # rejection of small clusters (-r, :316-324) and the full-column regulariser (-f, :358)

@@ -211,6 +211,22 @@ def test_empirical_and_co2_window():
         _check_against(got, ref["mf"], ref["mask"], aidx, ref["colstd"])
 
 
+def test_reflectance_target():
+    """-R (cmf/robust_mf.py:379, :383-384): target = abscf - mu and no ppm scaling.  The reference pairs -R with the
+    416-band window [5, 420] (:187), wider than this build's 96-band limit, so the formula is
+    checked on the CH4 and CO2 windows; the wide window itself must fail loudly, never fall back."""
+    cube = synth.make_cube(500, 5, seed=43, bad_pixels=True)
+    for active, model in (([351, 422], "looshrinkage"), ([309, 391], "empirical")):
+        ab = _abscf(active)
+        ref = orc.cmf_cube(cube, ab, active, model=model, reflectance=True)
+        got = cmf_cube(cube, ab, active, model=model, reflectance=True)
+        aidx = ref["alpha_index"] if model == "looshrinkage" else None
+        _check_against(got, ref["mf"], ref["mask"], aidx, ref["colstd"])
+    from srcfinder_b200 import CmfError
+    with pytest.raises(CmfError, match="wider than 96 bands"):
+        ColumnwiseMF(16, 425, 4, [5, 420], np.zeros(416), reflectance=True)
+
+
 def test_device_resident_full_cube_and_run_host():
     """Binding a full BIL cube that already sits in HBM (line pitch B*S) and the one-call host API give the
     same bits as upload + run."""

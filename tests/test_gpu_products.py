@@ -119,3 +119,49 @@ def test_column_profile_of_a_run_and_cli(tmp_path):
     for j, k in enumerate(("npix", "med", "mad", "p05", "p95")):
         assert np.array_equal(vals[:, j], robust[k], equal_nan=True)
     assert cmf_profile.summarize(out, str(tmp_path), True) is False      # exists -> skipped (:104-106)
+
+
+def test_exclusion_from_background_statistics():
+    """Opt-in exclusion: flagged pixels stay out of the mean / covariance / alpha search but are
+    scored with the resulting filter.  Expected values come from the oracle's own column fit on the kept pixels."""
+    from oracle import cmf_oracle as orc
+    L, S = 700, 6
+    cube = synth.make_cube(L, S, seed=35, bad_pixels=True)
+    rng = np.random.default_rng(35)
+    ok = cube[:, 400, :] > 0
+    hot = (rng.random((L, S)) < 0.03) & ok
+    cube[:, 330:423, :] = np.where(hot[:, None, :], cube[:, 330:423, :] * 4.0 + 5.0, cube[:, 330:423, :])   # flares
+    wave = _wavelengths()
+    ab = synth.load_ch4_library()[ACTIVE[0] - 1:ACTIVE[1], 2]
+    with ColumnwiseMF(L, 425, S, ACTIVE, ab) as eng:
+        eng.upload(cube)
+        flags = eng.pixel_flags(cube, masks.flag_spec(wave))
+        excl = (flags & masks.SATURATED) != 0
+        assert excl.sum() > 20 and np.array_equal(flags, po.pixel_flags(cube, wave))
+        eng.run()
+        plain = eng.results()
+        eng.set_exclusion(excl)
+        eng.run()
+        got = eng.results()
+        nbg = eng.nvalid()
+        eng.set_exclusion(None)
+        eng.run()
+        back = eng.results()
+    assert np.array_equal(back["mf"], plain["mf"], equal_nan=True)          # clearing restores the default
+    assert np.array_equal(got["mask"], plain["mask"])                         # validity is untouched (:282)
+    assert not np.array_equal(got["mf"], plain["mf"])
+    alphas, nll = orc.alpha_grid(), np.zeros(201)
+    for c in range(S):
+        full = cube[:, ACTIVE[0] - 1:ACTIVE[1], c]
+        use = orc.valid_rows(full)
+        keep = use[~excl[use, c]]
+        assert nbg[c] == len(keep)
+        fit = orc.column_filter(np.float64(full[keep]), ab, alphas, nll, len(keep))
+        want = (np.float64(full[use]) - fit["mu"]).dot(fit["weights"])
+        assert got["alpha_index"][c] == fit["alpha_index"]
+        sd = np.std(want)
+        assert np.max(np.abs(got["mf"][use, c] - want)) / sd < 1e-6
+        assert np.all(got["mf"][~plain["mask"][:, c], c] == -9999.0)
+        assert got["colnum"][c] == len(use)
+        assert got["colavg"][c] == pytest.approx(np.mean(want), abs=1e-6 * sd)
+        assert got["colstd"][c] == pytest.approx(sd, rel=1e-8)
