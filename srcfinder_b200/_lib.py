@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcmf_b200.so")
+# CMF_B200_LIB: development hook for instrumented builds of the same library (tools/ only)
+LIB_PATH = os.environ.get("CMF_B200_LIB") or os.path.join(_HERE, "libcmf_b200.so")
 
 # every symbol include/cmf_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [

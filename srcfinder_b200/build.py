@@ -37,7 +37,7 @@ def _compile(src):
     path = os.path.join(CSRC, src)
     if not _stale(obj, [path] + hdrs):
         return obj, ""
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-c", path, "-o", obj]
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("CMF_NVCC_EXTRA", "").split() + ["-c", path, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, res.stdout, res.stderr))

@@ -224,7 +224,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 enum { kEigDiag = 0, kEigNone = 1, kEigFull = 2 };
 
 template <int NT, int MODE>
-__global__ void __launch_bounds__(kQlThreads)
+__global__ void __launch_bounds__(kQlThreads, 5)
     eigen_ql_kernel(const double* __restrict__ gram_part, int nchunk, const int* __restrict__ n_g, int D,
         const double* __restrict__ mu_g, const double* __restrict__ ctr_g,
                     double* __restrict__ P_g, double* __restrict__ lam_g, double* __restrict__ slogT_g,
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kQlThreads)
     double* cs = e + DP;             // [2*DP]    rotation (c, s) pairs of one QL iteration
     double* red = cs + 2 * DP;       // [8]       reduction scratch / broadcast
     double* tl = red + 8;            // [DP][LD]  kEigFull only: T -> its Cholesky factor L (lower)
-    __shared__ int sh_m, sh_cnt, sh_flag, sh_bad;
+    __shared__ int sh_m2[2], sh_cnt2[2], sh_flag, sh_bad;
 
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kQlThreads / 32;
@@ -370,6 +370,9 @@ __global__ void __launch_bounds__(kQlThreads)
         __syncthreads();
     }
 
+#ifdef CMF_EIGEN_PROF
+    long long pt0 = clock64(), pt1 = 0, pt2 = 0, pser = 0;
+#endif
     // ---- tred2: reduce to tridiagonal form, lower triangle, rows n-1 .. 1
     for (int i = D - 1; i >= 1; --i) {
         const int l = i - 1;
@@ -398,10 +401,25 @@ __global__ void __launch_bounds__(kQlThreads)
                 part = 0.0;
                 for (int j = tid; j <= l; j += blockDim.x) {
                     a[j * LD + i] = a[i * LD + j] / h;
-                    double gj = 0.0;
-                    for (int k = 0; k <= j; ++k) gj += a[j * LD + k] * a[i * LD + k];
-                    for (int k = j + 1; k <= l; ++k) gj += a[k * LD + j] * a[i * LD + k];
-                    gj /= h;
+                    // four independent partial sums: a dependent FP64 add costs far more than its issue slot
+                    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+                    int k = 0;
+                    for (; k + 3 <= j; k += 4) {
+                        g0 += a[j * LD + k] * a[i * LD + k];
+                        g1 += a[j * LD + k + 1] * a[i * LD + k + 1];
+                        g2 += a[j * LD + k + 2] * a[i * LD + k + 2];
+                        g3 += a[j * LD + k + 3] * a[i * LD + k + 3];
+                    }
+                    for (; k <= j; ++k) g0 += a[j * LD + k] * a[i * LD + k];
+                    k = j + 1;
+                    for (; k + 3 <= l; k += 4) {
+                        g0 += a[k * LD + j] * a[i * LD + k];
+                        g1 += a[(k + 1) * LD + j] * a[i * LD + k + 1];
+                        g2 += a[(k + 2) * LD + j] * a[i * LD + k + 2];
+                        g3 += a[(k + 3) * LD + j] * a[i * LD + k + 3];
+                    }
+                    for (; k <= l; ++k) g0 += a[k * LD + j] * a[i * LD + k];
+                    double gj = ((g0 + g1) + (g2 + g3)) / h;
                     e[j] = gj;
                     part += gj * a[i * LD + j];
                 }
@@ -423,15 +441,25 @@ __global__ void __launch_bounds__(kQlThreads)
     }
     if (tid == 0) { d[0] = 0.0; e[0] = 0.0; }
     __syncthreads();
+#ifdef CMF_EIGEN_PROF
+    pt1 = clock64();
+#endif
     // ---- accumulate the transformations: a becomes the orthogonal matrix Q
     for (int i = 0; i < D; ++i) {
         const int l = i - 1;
         if (d[i] != 0.0) {
             // g_j = sum_k a[i][k] a[k][j]; kept in cs[] (free until the QL phase)
             for (int j = tid; j <= l; j += blockDim.x) {
-                double g = 0.0;
-                for (int k = 0; k <= l; ++k) g += a[i * LD + k] * a[k * LD + j];
-                cs[j] = g;
+                double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+                int k = 0;
+                for (; k + 3 <= l; k += 4) {
+                    g0 += a[i * LD + k] * a[k * LD + j];
+                    g1 += a[i * LD + k + 1] * a[(k + 1) * LD + j];
+                    g2 += a[i * LD + k + 2] * a[(k + 2) * LD + j];
+                    g3 += a[i * LD + k + 3] * a[(k + 3) * LD + j];
+                }
+                for (; k <= l; ++k) g0 += a[i * LD + k] * a[k * LD + j];
+                cs[j] = (g0 + g1) + (g2 + g3);
             }
             __syncthreads();
             for (int k = warp; k <= l; k += NW) {
@@ -445,8 +473,17 @@ __global__ void __launch_bounds__(kQlThreads)
         __syncthreads();
     }
 
-    // ---- tql2: implicit-shift QL on (d, e); thread 0 runs the rotation recurrence of one iteration and
-    // leaves the (c, s) sequence in shared memory, then every thread applies it to its row of Q.
+#ifdef CMF_EIGEN_PROF
+    pt2 = clock64();
+#endif
+    // ---- tql2: implicit-shift QL on (d, e).  The rotation recurrence of an iteration is a serial FP64 chain
+    // (it was 60 % of this kernel), and it only needs (d, e) -- not the eigenvectors.  So warp 0 (lane 0) runs
+    // the recurrences of ALL iterations back to back and hands each iteration's (c, s) sequence to warps 1-3,
+    // which apply it to their rows of Q while the next recurrence is already running: two message buffers,
+    // named barriers 1/2 = "buffer full", 3/4 = "buffer free".  The chain itself is kept short: one rsqrt instead
+    // of sqrt + divide, and the next (d, e) entries are loaded before they are needed.
+    // Buffer 0 is cs[]; buffer 1 lives in dinv[] (saved in a register meanwhile) and the unused pad column of a.
+    const double dinv_keep = (tid < DP) ? dinv[tid] : 0.0;
     if (tid == 0) {
         for (int i = 1; i < D; ++i) e[i - 1] = e[i];
         e[D - 1] = 0.0;
@@ -454,70 +491,164 @@ __global__ void __launch_bounds__(kQlThreads)
     }
     __syncthreads();
     int total_iter = 0;
-    for (int l = 0; l < D; ++l) {
-        for (int iter = 0;; ++iter) {
-            if (tid == 0) {
-                int m = l;
-                for (; m < D - 1; ++m) {
-                    const double dd = fabs(d[m]) + fabs(d[m + 1]);
-                    if (fabs(e[m]) <= 1.1102230246251565e-16 * dd) break;
-                }
-                int cnt = 0;
-                if (m != l && iter < kQlMaxIter) {
-                    double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
-                    double r = sqrt(g * g + 1.0);
-                    g = d[m] - d[l] + e[l] / (g + copysign(r, g));
-                    double sn = 1.0, c = 1.0, p = 0.0;
-                    int i = m - 1;
-                    bool under = false;
-                    for (; i >= l; --i) {
-                        double f = sn * e[i];
-                        const double b = c * e[i];
-                        r = sqrt(f * f + g * g);
-                        e[i + 1] = r;
-                        if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; under = true; break; }
-                        const double rinv = 1.0 / r;
-                        sn = f * rinv;
-                        c = g * rinv;
-                        g = d[i + 1] - p;
-                        r = (d[i] - g) * sn + 2.0 * c * b;
-                        p = sn * r;
-                        d[i + 1] = g + p;
-                        g = c * r - b;
-                        cs[2 * cnt] = c; cs[2 * cnt + 1] = sn;      // rotation of columns (i, i+1)
-                        ++cnt;
+    // barrier ids are immediates (a register id makes ptxas reserve all 16 barriers, which costs a resident CTA)
+    auto bar_sync = [](int id) {
+        switch (id) {
+            case 1: asm volatile("bar.sync 1, %0;" ::"n"(kQlThreads) : "memory"); break;
+            case 2: asm volatile("bar.sync 2, %0;" ::"n"(kQlThreads) : "memory"); break;
+            case 3: asm volatile("bar.sync 3, %0;" ::"n"(kQlThreads) : "memory"); break;
+            default: asm volatile("bar.sync 4, %0;" ::"n"(kQlThreads) : "memory"); break;
+        }
+    };
+    auto bar_arrive = [](int id) {
+        switch (id) {
+            case 1: asm volatile("bar.arrive 1, %0;" ::"n"(kQlThreads) : "memory"); break;
+            case 2: asm volatile("bar.arrive 2, %0;" ::"n"(kQlThreads) : "memory"); break;
+            case 3: asm volatile("bar.arrive 3, %0;" ::"n"(kQlThreads) : "memory"); break;
+            default: asm volatile("bar.arrive 4, %0;" ::"n"(kQlThreads) : "memory"); break;
+        }
+    };
+    // element t of buffer `buf`: c at cptr[t * cstride], s at sptr[t * sstride]
+    auto cbase = [&](int buf) { return buf ? dinv : cs; };
+    auto sbase = [&](int buf) { return buf ? a + DP : cs + 1; };
+    auto cstr = [](int buf) { return buf ? 1 : 2; };
+    auto sstr = [](int buf) { return buf ? LD : 2; };
+    if (warp == 0) {
+        int k = 0;                                     // message counter
+        for (int l = 0; l < D; ++l) {
+            for (int iter = 0;; ++iter) {
+                const int buf = k & 1;
+                if (k >= 2) bar_sync(3 + buf);          // the consumers are done with message k-2
+                int m = l, cnt = 0;
+#ifdef CMF_EIGEN_PROF
+                const long long ps0 = clock64();
+#endif
+                // first m >= l with a negligible e[m] (m = D-1 if none): the 32 lanes test 32 entries at a time
+                {
+                    m = D - 1;
+                    for (int base = l; base < D - 1; base += 32) {
+                        const int mm = base + lane;
+                        bool small = false;
+                        if (mm < D - 1) {
+                            const double dd = fabs(d[mm]) + fabs(d[mm + 1]);
+                            small = fabs(e[mm]) <= 1.1102230246251565e-16 * dd;
+                        }
+                        const unsigned hit = __ballot_sync(0xffffffffu, small);
+                        if (hit) { m = base + __ffs(hit) - 1; break; }
                     }
-                    if (!under) { d[l] -= p; e[l] = g; e[m] = 0.0; }
-                } else if (m != l) {
-                    sh_flag = 1;       // iteration cap: give up on this eigenvalue (status NoConverge)
-                    m = l;
                 }
-                sh_m = m; sh_cnt = cnt;
+                if (lane == 0) {
+                    if (m != l && iter < kQlMaxIter) {
+                        double* cw = cbase(buf);
+                        double* sw = sbase(buf);
+                        const int cst = cstr(buf), sst = sstr(buf);
+                        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                        double r = sqrt(g * g + 1.0);
+                        g = d[m] - d[l] + e[l] / (g + copysign(r, g));
+                        double sn = 1.0, c = 1.0, p = 0.0;
+                        int i = m - 1;
+                        bool under = false;
+                        double e_i = e[i], d_i = d[i], d_i1 = d[i + 1];
+                        for (; i >= l && !under; --i) {
+                            double e_n = 0.0, d_n = 0.0;
+                            if (i > l) { e_n = e[i - 1]; d_n = d[i - 1]; }      // next step's operands, early
+                            const double f = sn * e_i;
+                            const double b = c * e_i;
+                            const double h = f * f + g * g;
+                            // 1/sqrt(h) without a branch on the chain: hardware seed (2^-22) and one third-order
+                            // correction, exact to rounding for the normal, positive h that occur here
+                            under = !(h > 0.0);
+                            double x0;
+                            asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(h));
+                            const double err = fma(-h * x0, x0, 1.0);
+                            const double rinv = under ? 0.0 : fma(fma(err, 0.375, 0.5), x0 * err, x0);
+                            // r2 = (d_i - g2) sn' + 2 c' b with sn' = f rinv, c' = g rinv: everything that does not
+                            // need rinv is formed beside the rsqrt, so only two levels follow it on the chain
+                            const double g2 = d_i1 - p;
+                            const double w = fma(d_i - g2, f, 2.0 * g * b);
+                            e[i + 1] = h * rinv;
+                            sn = f * rinv;
+                            c = g * rinv;
+                            const double r2 = w * rinv;
+                            if (!under) {
+                                p = sn * r2;
+                                d[i + 1] = g2 + p;
+                                g = c * r2 - b;
+                                cw[cnt * cst] = c; sw[cnt * sst] = sn;          // rotation of columns (i, i+1)
+                                ++cnt;
+                            } else {
+                                d[i + 1] = g2;                                  // r == 0: d[i+1] -= p, e[m] = 0
+                                e[m] = 0.0;
+                            }
+                            e_i = e_n; d_i1 = d_i; d_i = d_n;
+                        }
+                        if (!under) { d[l] -= p; e[l] = g; e[m] = 0.0; }
+                    } else if (m != l) {
+                        sh_flag = 1;       // iteration cap: give up on this eigenvalue (status NoConverge)
+                        m = l;
+                    }
+                    sh_m2[buf] = m; sh_cnt2[buf] = cnt;
+                }
+#ifdef CMF_EIGEN_PROF
+                if (lane == 0) pser += clock64() - ps0;
+#endif
+                m = __shfl_sync(0xffffffffu, m, 0);
+                __threadfence_block();
+                __syncwarp();
+                bar_arrive(1 + buf);                    // message k is ready
+                ++k;
+                if (m == l) break;
+                ++total_iter;
             }
-            __syncthreads();
-            const int m = sh_m, cnt = sh_cnt;
-            if (m == l) break;
-            ++total_iter;
-            // apply: rotation t acts on columns (i, i+1), i = m-1-t
-            for (int k = tid; k < D; k += blockDim.x) {
-                double* row = a + k * LD;
+        }
+        // end-of-stream message
+        const int buf = k & 1;
+        if (k >= 2) bar_sync(3 + buf);
+        if (lane == 0) { sh_m2[buf] = 0; sh_cnt2[buf] = -1; }
+        __threadfence_block();
+        __syncwarp();
+        bar_arrive(1 + buf);
+    } else {
+        const int row_id = tid - 32;                    // kQlThreads - 32 = 96 >= D rows of Q
+        for (int k = 0;; ++k) {
+            const int buf = k & 1;
+            bar_sync(1 + buf);
+            const int m = sh_m2[buf], cnt = sh_cnt2[buf];
+            if (cnt < 0) break;
+            if (cnt > 0 && row_id < D) {
+                // rotation t acts on columns (i, i+1), i = m-1-t
+                const double* cr = cbase(buf);
+                const double* sr = sbase(buf);
+                const int cst = cstr(buf), sst = sstr(buf);
+                double* row = a + row_id * LD;
                 double f = row[m];
                 for (int t = 0; t < cnt; ++t) {
                     const int i = m - 1 - t;
-                    const double c = cs[2 * t], sn = cs[2 * t + 1];
+                    const double c = cr[t * cst], sn = sr[t * sst];
                     const double zi = row[i];
                     row[i + 1] = sn * zi + c * f;
                     f = c * zi - sn * f;
                 }
                 row[m - cnt] = f;
             }
-            __syncthreads();
+            bar_arrive(3 + buf);                        // buffer free again
         }
     }
+    __syncthreads();
+    if (tid < DP) dinv[tid] = dinv_keep;
+    __syncthreads();
     if (tid < DP) lam_g[(long long)s * DP + tid] = (tid < D) ? d[tid] : 0.0;
     if (tid == 0) {
         status_g[s] = sh_flag ? kStatusNoConverge : kStatusOk;
+#ifdef CMF_EIGEN_PROF
+        {   // profiling build: phase cycles packed into the sweeps word (tred2/8k, accumulate/8k, tql2/32k, serial/32k)
+            const long long pt3 = clock64();
+            auto q = [](long long v, int sh) { long long t = v >> sh; return (int)(t > 255 ? 255 : t); };
+            sweeps_g[s] = q(pt1 - pt0, 13) | (q(pt2 - pt1, 13) << 8) | (q(pt3 - pt2, 15) << 16) | (q(pser, 15) << 24);
+        }
+#else
         sweeps_g[s] = total_iter;
+#endif
     }
     if (MODE == kEigFull) {
         // P = L^-T V: back substitution, one eigenvector (column of a) per thread

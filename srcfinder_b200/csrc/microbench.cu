@@ -177,6 +177,27 @@ float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime
 
 }  // namespace
 
+// dependent-issue latency in cycles of one FP64 op, one thread of one warp (kinds 12-15): the serial rotation
+// recurrence of the QL eigen-solver is a chain of such ops, so its length is what bounds K2
+template <int OP>
+__global__ void fp64_latency_kernel(double* out, long long* cycles, int n, double seed) {
+    double x = seed, y = 1.0 + seed * 1e-3;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (OP == 0) x = fma(x, y, 1e-9);            // DFMA
+            else if (OP == 1) x = rsqrt(x) + 1.5;        // rsqrt + DADD
+            else if (OP == 2) x = sqrt(x) + 2.0;         // sqrt + DADD
+            else x = 1.0 / x + 0.5;                      // divide + DADD
+        }
+    }
+    const long long t1 = clock64();
+    out[0] = x;
+    cycles[0] = t1 - t0;
+}
+
 extern "C" double cmf_microbench(int device, int kind, int iters) {
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;
     cudaDeviceProp prop;
@@ -251,6 +272,21 @@ extern "C" double cmf_microbench(int device, int kind, int iters) {
         const double sec = time_ms(e0, e1) * 1e-3 / iters;
         result = (kind == 4 ? 2.0 : 1.0) * (double)bytes / sec * 1e-9;   // GB/s
         cudaFree(in); cudaFree(flag); if (outp) cudaFree(outp);
+    }
+    else if (kind >= 12 && kind <= 15) {
+        double* o; long long* c;
+        cudaMalloc(&o, 8); cudaMalloc(&c, 8);
+        const int n = 4096;
+        for (int rep = 0; rep < 2; ++rep) {
+            if (kind == 12) fp64_latency_kernel<0><<<1, 1>>>(o, c, n, 1.0000001);
+            else if (kind == 13) fp64_latency_kernel<1><<<1, 1>>>(o, c, n, 1.7);
+            else if (kind == 14) fp64_latency_kernel<2><<<1, 1>>>(o, c, n, 1.7);
+            else fp64_latency_kernel<3><<<1, 1>>>(o, c, n, 1.7);
+        }
+        long long cyc = 0;
+        cudaMemcpy(&cyc, c, 8, cudaMemcpyDeviceToHost);
+        result = (double)cyc / (8.0 * n);                  // cycles per op (kinds 13-15 include one DADD)
+        cudaFree(o); cudaFree(c);
     }
     else if (kind >= 20 && kind <= 25) {
         // tcgen05 TS-form self test: max |D - A.B^T| (exact inputs, so 0 when the layouts are right)
