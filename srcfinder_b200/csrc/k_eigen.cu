@@ -239,8 +239,11 @@ __global__ void __launch_bounds__(kQlThreads, 5)
     double* cs = e + DP;             // [2*DP]    rotation (c, s) pairs of one QL iteration
     double* red = cs + 2 * DP;       // [8]       reduction scratch / broadcast
     double* tl = red + 8;            // [DP][LD]  kEigFull only: T -> its Cholesky factor L (lower)
-    __shared__ int sh_m2[2], sh_cnt2[2], sh_flag, sh_bad;
+    __shared__ int sh_m2[2], sh_cnt2[2], sh_flag, sh_bad, sh_iter;
 
+#ifdef CMF_EIGEN_PROF
+    const long long pstart = clock64();
+#endif
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kQlThreads / 32;
     const int n = n_g[s];
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(kQlThreads, 5)
     }
 
 #ifdef CMF_EIGEN_PROF
-    long long pt0 = clock64(), pt1 = 0, pt2 = 0, pser = 0;
+    long long pt0 = clock64(), pt1 = 0, pt2 = 0, pt3 = 0, pser = 0;
 #endif
     // ---- tred2: reduce to tridiagonal form, lower triangle, rows n-1 .. 1
     for (int i = D - 1; i >= 1; --i) {
@@ -496,8 +499,11 @@ __global__ void __launch_bounds__(kQlThreads, 5)
         for (int i = 1; i < D; ++i) e[i - 1] = e[i];
         e[D - 1] = 0.0;
         sh_flag = 0;
+        sh_iter = 0;
     }
     __syncthreads();
+    // (giving the CTAs of one SM different producer warps through per-SM tickets was measured: 7 % slower)
+    constexpr int pw = 0;                               // the producer warp
     int total_iter = 0;
     // barrier ids are immediates (a register id makes ptxas reserve all 16 barriers, which costs a resident CTA)
     auto bar_sync = [](int id) {
@@ -521,7 +527,7 @@ __global__ void __launch_bounds__(kQlThreads, 5)
     auto sbase = [&](int buf) { return buf ? a + DP : cs + 1; };
     auto cstr = [](int buf) { return buf ? 1 : 2; };
     auto sstr = [](int buf) { return buf ? LD : 2; };
-    if (warp == 0) {
+    if (warp == pw) {
         int k = 0;                                     // message counter
         for (int l = 0; l < D; ++l) {
             for (int iter = 0;; ++iter) {
@@ -612,12 +618,12 @@ __global__ void __launch_bounds__(kQlThreads, 5)
         // end-of-stream message
         const int buf = k & 1;
         if (k >= 2) bar_sync(3 + buf);
-        if (lane == 0) { sh_m2[buf] = 0; sh_cnt2[buf] = -1; }
+        if (lane == 0) { sh_m2[buf] = 0; sh_cnt2[buf] = -1; sh_iter = total_iter; }
         __threadfence_block();
         __syncwarp();
         bar_arrive(1 + buf);
     } else {
-        const int row_id = tid - 32;                    // kQlThreads - 32 = 96 >= D rows of Q
+        const int row_id = ((warp - pw - 1) & (NW - 1)) * 32 + lane;   // 3 consumer warps = 96 >= D rows of Q
         for (int k = 0;; ++k) {
             const int buf = k & 1;
             bar_sync(1 + buf);
@@ -649,13 +655,9 @@ __global__ void __launch_bounds__(kQlThreads, 5)
     if (tid == 0) {
         status_g[s] = sh_flag ? kStatusNoConverge : kStatusOk;
 #ifdef CMF_EIGEN_PROF
-        {   // profiling build: phase cycles packed into the sweeps word (tred2/8k, accumulate/8k, tql2/32k, serial/32k)
-            const long long pt3 = clock64();
-            auto q = [](long long v, int sh) { long long t = v >> sh; return (int)(t > 255 ? 255 : t); };
-            sweeps_g[s] = q(pt1 - pt0, 13) | (q(pt2 - pt1, 13) << 8) | (q(pt3 - pt2, 15) << 16) | (q(pser, 15) << 24);
-        }
+        pt3 = clock64();
 #else
-        sweeps_g[s] = total_iter;
+        sweeps_g[s] = sh_iter;
 #endif
     }
     if (MODE == kEigFull) {
@@ -674,6 +676,15 @@ __global__ void __launch_bounds__(kQlThreads, 5)
         const int b = idx / DP, j = idx % DP;
         Pout[idx] = (b < D && j < D) ? dinv[b] * a[b * LD + j] : 0.0;
     }
+#ifdef CMF_EIGEN_PROF
+    __syncthreads();
+    if (tid == 0) {   // profiling build: phase cycles packed into the sweeps word instead of the iteration count
+        const long long pend = clock64();
+        auto q = [](long long v, int sh) { long long t = v >> sh; return (int)(t > 255 ? 255 : t); };
+        (void)pt1; (void)pser;
+        sweeps_g[s] = q(pt0 - pstart, 13) | (q(pt2 - pt0, 14) << 8) | (q(pt3 - pt2, 15) << 16) | (q(pend - pt3, 13) << 24);
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------- K2b

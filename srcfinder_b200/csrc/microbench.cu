@@ -198,6 +198,52 @@ __global__ void fp64_latency_kernel(double* out, long long* cycles, int n, doubl
     cycles[0] = t1 - t0;
 }
 
+// the rotation recurrence of the QL eigen-solver (k_eigen.cu, tql2 producer) in isolation: cycles per step of one
+// lane, with `blockDim.x / 32` warps per CTA all running their own copy (kind 16: one warp on one SM; kind 17: 20 warps
+// per SM like 5 resident eigen CTAs, every warp a chain; kind 18: 5 chains per SM, one per CTA)
+__global__ void ql_chain_kernel(double* out, long long* cycles, int n, int steps) {
+    __shared__ double dsh[8][80], esh[8][80], csh[8][160];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* d = dsh[w]; double* e = esh[w]; double* cs = csh[w];
+    if (lane == 0) for (int i = 0; i < 80; ++i) { d[i] = 1.0 + 0.01 * i; e[i] = 0.3 + 0.001 * i; }
+    __syncwarp();
+    long long t0 = 0, t1 = 0;
+    if (lane == 0) {
+        t0 = clock64();
+        double g = 0.37, sn = 1.0, c = 1.0, p = 0.0;
+        for (int rep = 0; rep < n; ++rep) {
+            int i = steps - 1, cnt = 0;
+            double e_i = e[i], d_i = d[i], d_i1 = d[i + 1];
+            bool under = false;
+            for (; i >= 0 && !under; --i) {
+                double e_n = 0.0, d_n = 0.0;
+                if (i > 0) { e_n = e[i - 1]; d_n = d[i - 1]; }
+                const double f = sn * e_i, b = c * e_i;
+                const double h = f * f + g * g;
+                under = !(h > 0.0);
+                double x0;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(h));
+                const double err = fma(-h * x0, x0, 1.0);
+                const double rinv = under ? 0.0 : fma(fma(err, 0.375, 0.5), x0 * err, x0);
+                const double g2 = d_i1 - p;
+                const double wv = fma(d_i - g2, f, 2.0 * g * b);
+                e[i + 1] = h * rinv;
+                sn = f * rinv; c = g * rinv;
+                const double r2 = wv * rinv;
+                p = sn * r2;
+                d[i + 1] = g2 + p;
+                g = c * r2 - b;
+                cs[2 * cnt] = c; cs[2 * cnt + 1] = sn; ++cnt;
+                e_i = e_n; d_i1 = d_i; d_i = d_n;
+            }
+            g = 0.37 + 1e-3 * g; sn = 1.0; c = 1.0; p = 0.0;
+        }
+        t1 = clock64();
+        out[blockIdx.x * 8 + w] = g + d[3];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
 extern "C" double cmf_microbench(int device, int kind, int iters) {
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;
     cudaDeviceProp prop;
@@ -286,6 +332,20 @@ extern "C" double cmf_microbench(int device, int kind, int iters) {
         long long cyc = 0;
         cudaMemcpy(&cyc, c, 8, cudaMemcpyDeviceToHost);
         result = (double)cyc / (8.0 * n);                  // cycles per op (kinds 13-15 include one DADD)
+        cudaFree(o); cudaFree(c);
+    }
+    else if (kind >= 16 && kind <= 18) {
+        double* o; long long* c;
+        cudaMalloc(&o, 8 * 8 * 148 * 8); cudaMalloc(&c, 8);
+        const int n = 64, steps = 70;
+        for (int rep = 0; rep < 2; ++rep) {
+            if (kind == 16) ql_chain_kernel<<<1, 32>>>(o, c, n, steps);
+            else if (kind == 17) ql_chain_kernel<<<sms * 5, 128>>>(o, c, n, steps);
+            else ql_chain_kernel<<<sms * 5, 32>>>(o, c, n, steps);
+        }
+        long long cyc = 0;
+        cudaMemcpy(&cyc, c, 8, cudaMemcpyDeviceToHost);
+        result = (double)cyc / ((double)n * steps);        // cycles per rotation step
         cudaFree(o); cudaFree(c);
     }
     else if (kind >= 20 && kind <= 25) {

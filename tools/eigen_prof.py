@@ -12,8 +12,8 @@ with ColumnwiseMF(L, 425, S, active, ab) as eng:
     eng.run(); eng.run(timing=True)
     w = eng.sweeps().astype(np.int64)
     kt = eng.kernel_times()
-t1, t2, t3, ser = (w & 255) * 8192, ((w >> 8) & 255) * 8192, ((w >> 16) & 255) * 32768, ((w >> 24) & 255) * 32768
-for name, v in (("tred2", t1), ("accumulate", t2), ("tql2", t3), ("tql2 serial part", ser)):
-    print("%-18s median %8.0f kcycles   max %8.0f" % (name, np.median(v) / 1e3, v.max() / 1e3))
+pro, red, tql, epi = (w & 255) * 8192, ((w >> 8) & 255) * 16384, ((w >> 16) & 255) * 32768, ((w >> 24) & 255) * 8192
+for name, v in (("prologue (Gram sum, scaling)", pro), ("tred2 + accumulate", red), ("tql2", tql), ("epilogue (P, lam)", epi)):
+    print("%-30s median %8.0f kcycles   max %8.0f" % (name, np.median(v) / 1e3, v.max() / 1e3))
 print("note: the instrumented build reports phase cycles instead of the iteration count")
 print("eigen kernel %.3f ms = %.0f kcycles at 1.965 GHz" % (kt["eigen"], kt["eigen"] * 1.965e3))
