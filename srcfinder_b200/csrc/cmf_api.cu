@@ -120,8 +120,16 @@ void free_buffers(cmf_ctx* c) {
 template <typename T>
 cudaError_t dalloc(cmf_ctx* c, T** p, size_t count) {
     void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
-    if (e == cudaSuccess) { c->allocs.push_back(q); *p = reinterpret_cast<T*>(q); }
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e == cudaSuccess) {
+        c->allocs.push_back(q);
+        *p = reinterpret_cast<T*>(q);
+        // testing hook: CMF_POISON=1 fills every work buffer with 0xFF (NaN / -1) so that any read of memory the
+        // pipeline has not written shows up (fresh cudaMalloc pages are usually zero, recycled ones are not)
+        static const bool poison = getenv("CMF_POISON") != nullptr;
+        if (poison) e = cudaMemset(q, 0xFF, bytes);
+    }
     return e;
 }
 

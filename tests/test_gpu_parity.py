@@ -285,6 +285,31 @@ def test_async_host_calls_on_two_contexts():
         assert np.array_equal(gai.numpy(), ai)
 
 
+def test_no_read_of_unwritten_work_memory():
+    """CMF_POISON=1 fills every work buffer with 0xFF at allocation (NaN / -1): results must not change, i.e. no
+    kernel relies on cudaMalloc handing out zeroed pages (recycled pages are not)."""
+    import subprocess, sys, os
+    code = ("import numpy as np, sys; sys.path.insert(0, %r)\n"
+            "from srcfinder_b200 import cmf_cube, synth\n"
+            "cube = synth.make_cube(640, 9, seed=77, bad_pixels=True)\n"
+            "ab = synth.load_ch4_library()[350:422, 2]\n"
+            "r = cmf_cube(cube, ab, [351, 422]); k = cmf_cube(cube, ab, [351, 422], kmodes=3, reject_min=85, regfull=True)\n"
+            "np.savez(sys.argv[1], mf=r['mf'], ai=r['alpha_index'], cs=r['colstd'], kmf=k['mf'], kai=k['alpha_index'])\n"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import tempfile
+    outs = []
+    for poison in (False, True):
+        env = dict(os.environ)
+        env.pop("CMF_POISON", None)
+        if poison:
+            env["CMF_POISON"] = "1"
+        path = os.path.join(tempfile.mkdtemp(), "r.npz")
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env)
+        outs.append(np.load(path))
+    for key in ("mf", "ai", "cs", "kmf", "kai"):
+        assert np.array_equal(outs[0][key], outs[1][key], equal_nan=True), key
+
+
 def test_error_paths():
     from srcfinder_b200 import CmfError
     ab = _abscf([351, 422])
