@@ -71,6 +71,7 @@ struct cmf_ctx {
     bool auto_cluster = false, regfull = false;
     int pcadim = 6, km_max_iter = 100, y_pd = 0;
     double *gram_full = nullptr, *vtop = nullptr, *ypca = nullptr;
+    int32_t* qpca = nullptr;      // quantised projections [S][pcadim][L] of the k-means
     int *pick = nullptr, *km_iters = nullptr;
     uint8_t* lab8 = nullptr;
     bool can_screen = false;
@@ -281,7 +282,7 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
             launch_eigen(d, ctx->gram_full, ctx->nchunk_gram, ctx->nuse, ctx->mu, nullptr, ctx->P, ctx->lam, ctx->slogT,
                          ctx->status, ctx->sweeps, 0, st, 1);
             launch_pca_kmeans(d, ctx->xt, ctx->mask, ctx->mu, ctx->nuse, ctx->P, ctx->lam, ctx->pcadim, ctx->kmodes,
-                              ctx->km_max_iter, ctx->pick, ctx->vtop, ctx->ypca, ctx->lab8, ctx->labels_d,
+                              ctx->km_max_iter, ctx->pick, ctx->vtop, ctx->ypca, ctx->qpca, ctx->lab8, ctx->labels_d,
                               ctx->km_iters, st);
             ctx->launches += 4;
         }
@@ -452,7 +453,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     ctx->alpha_img = nullptr;
     ctx->auto_cluster = false; ctx->regfull = false; ctx->y_pd = 0;
     ctx->have_excl = false; ctx->excl_sel = nullptr;
-    ctx->gram_full = nullptr; ctx->vtop = nullptr; ctx->ypca = nullptr; ctx->pick = nullptr;
+    ctx->gram_full = nullptr; ctx->vtop = nullptr; ctx->ypca = nullptr; ctx->qpca = nullptr; ctx->pick = nullptr;
     ctx->km_iters = nullptr; ctx->lab8 = nullptr;
     Dims& d = ctx->d;
     d.L = p->lines; d.S = p->samples; d.D = D; d.NT = NT; d.DP = 8 * NT;
@@ -620,6 +621,7 @@ int cmf_set_clustering(cmf_ctx* ctx, int kmodes, int pcadim, int reject_min, int
         cudaError_t e = cudaSuccess;
         auto A_ = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
         A_(dalloc(ctx, &ctx->ypca, LS * pcadim));
+        A_(dalloc(ctx, &ctx->qpca, LS * pcadim));
         if (!ctx->lab8) {
             A_(dalloc(ctx, &ctx->lab8, LS));
             A_(dalloc(ctx, &ctx->pick, (size_t)d.S * kMaxPcaDim));

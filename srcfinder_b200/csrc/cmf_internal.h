@@ -103,7 +103,8 @@ void launch_fill_f64(double* p, long long n, double v, cudaStream_t st);
 // PCA projection (P, lam = eigenvectors / eigenvalues of the column covariance, launch_eigen target 1) + k-means
 void launch_pca_kmeans(const Dims& d, const float* xt, const uint8_t* mask, const double* mu, const int* n,
                        const double* P, const double* lam, int pcadim, int k, int max_iter, int* pick,
-                       double* vtop, double* y, uint8_t* lab8, int32_t* labels, int* iters, cudaStream_t st);
+                       double* vtop, double* y, int32_t* q, uint8_t* lab8, int32_t* labels, int* iters,
+                       cudaStream_t st);
 void launch_colstats_modes(const Dims& d, const double* mf, const uint8_t* inlier, const int* nuse,
                            double nodata, double* colstats, cudaStream_t st);
 int score_plan(const Dims& d, int sm_count, int* lines_per_cta);

@@ -122,9 +122,17 @@ __device__ __forceinline__ long long block_minmax_i64(long long v, bool want_max
     return t;
 }
 
+// The Lloyd iterations work on the quantised projections only: they are written once as int32 [pd][L] per column
+// (component-major, so every load is a coalesced run of lines; INT_MIN in component 0 marks an invalid pixel, so
+// the strided mask image is not read again) and every iteration is ONE pass: a pixel is reassigned and added to the
+// integer sums of its new cluster in the same sweep.  The per-warp sums are built from warp-wide integer
+// reductions (REDUX: |q| <= 2^24, 32 lanes fit int32) instead of shared-memory atomics that all lanes of a
+// spatially coherent batch would aim at the same address.  Arithmetic and tie rules are unchanged (exact integer
+// sums, double distances summed over the components in order), so labels are bit-identical to the numpy
+// restatement in oracle/cluster_oracle.py.
 __global__ void __launch_bounds__(kKmThreads)
     kmeans_kernel(const double* __restrict__ y_g, const uint8_t* __restrict__ mask, const int* __restrict__ n_g,
-                  int L, int S, int pd, int k, int max_iter, uint8_t* __restrict__ lab8_g,
+                  int L, int S, int pd, int k, int max_iter, int32_t* __restrict__ q_g, uint8_t* __restrict__ lab8_g,
                   int32_t* __restrict__ labels, int* __restrict__ iters_g) {
     extern __shared__ unsigned long long smu[];
     // per-warp integer accumulators [warp][k][pd + 1] (sums, then the count), centroids [k][pd]
@@ -135,9 +143,11 @@ __global__ void __launch_bounds__(kKmThreads)
     __shared__ long long redi[kKmWarps];
     __shared__ int changed;
     __shared__ int hist[kKmInitBins], part[kKmThreads];
+    constexpr int32_t kInvalid = INT32_MIN;
 
-    const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5;
+    const int s = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double* y = y_g + (long long)s * L * pd;
+    int32_t* q = q_g + (long long)s * L * pd;              // [pd][L]
     uint8_t* lab8 = lab8_g + (long long)s * L;
     const int n = n_g[s];
     if (n == 0) {
@@ -154,14 +164,18 @@ __global__ void __launch_bounds__(kKmThreads)
     int e = 0;
     if (mx > 0.0) frexp(mx, &e);
     const double scale = ldexp(1.0, 24 - e);
-    // extremes of component 1
+    // quantise once; extremes of component 1
     long long lo = (1LL << 62), hi = -(1LL << 62);
-    for (int l = tid; l < L; l += blockDim.x)
+    for (int l = tid; l < L; l += blockDim.x) {
         if (mask[(long long)l * S + s]) {
-            const long long q = llrint(y[(long long)l * pd] * scale);
-            lo = q < lo ? q : lo;
-            hi = q > hi ? q : hi;
+            for (int p = 0; p < pd; ++p) q[(long long)p * L + l] = (int32_t)llrint(y[(long long)l * pd + p] * scale);
+            const long long q0 = q[l];
+            lo = q0 < lo ? q0 : lo;
+            hi = q0 > hi ? q0 : hi;
+        } else {
+            q[l] = kInvalid;
         }
+    }
     lo = block_minmax_i64(lo, false, redi);
     hi = block_minmax_i64(hi, true, redi);
     const long long span = hi - lo + 1;
@@ -170,11 +184,10 @@ __global__ void __launch_bounds__(kKmThreads)
     // saturated outliers.)
     for (int i = tid; i < kKmInitBins; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int l = tid; l < L; l += blockDim.x)
-        if (mask[(long long)l * S + s]) {
-            const long long q = llrint(y[(long long)l * pd] * scale);
-            atomicAdd(&hist[(int)(((q - lo) * kKmInitBins) / span)], 1);
-        }
+    for (int l = tid; l < L; l += blockDim.x) {
+        const int32_t q0 = q[l];
+        if (q0 != kInvalid) atomicAdd(&hist[(int)((((long long)q0 - lo) * kKmInitBins) / span)], 1);
+    }
     __syncthreads();
     {
         constexpr int per = kKmInitBins / kKmThreads;
@@ -195,34 +208,76 @@ __global__ void __launch_bounds__(kKmThreads)
             below += cnt;
         }
     }
-    __syncthreads();
-    for (int l = tid; l < L; l += blockDim.x) {
-        int lab = 0;
-        if (mask[(long long)l * S + s]) {
-            const long long q = llrint(y[(long long)l * pd] * scale);
-            lab = hist[(int)(((q - lo) * kKmInitBins) / span)];
-        }
-        lab8[l] = (uint8_t)lab;
-    }
     for (int i = tid; i < k * pd; i += blockDim.x) cen[i] = 0.0;
+    for (int i = tid; i < kKmWarps * k * stride; i += blockDim.x) acc[i] = 0;
+    if (tid == 0) changed = 0;
+    __syncthreads();
+
+    long long* mine = acc + warp * k * stride;
+    const int Lpad = (L + 31) & ~31;                       // whole warps walk the column together
+    // one sweep: (assign) the label of every valid pixel, then its quantised components into the sums of that label
+    auto sweep = [&](bool assign) {
+        int any = 0;
+        for (int l = tid; l < Lpad; l += blockDim.x) {
+            int32_t qi[kMaxPcaDim];
+            bool valid = false;
+            if (l < L) {
+                qi[0] = q[l];
+                valid = qi[0] != kInvalid;
+            }
+            int lab = -1;
+            if (valid) {
+#pragma unroll
+                for (int p = 1; p < kMaxPcaDim; ++p)
+                    if (p < pd) qi[p] = q[(long long)p * L + l];
+                if (assign) {
+                    // nearest centroid, squared distance summed over components in order, first minimum
+                    int best = 0;
+                    double bd = 0.0;
+                    for (int c = 0; c < k; ++c) {
+                        double dsq = 0.0;
+#pragma unroll
+                        for (int p = 0; p < kMaxPcaDim; ++p)
+                            if (p < pd) {
+                                const double df = __dsub_rn((double)qi[p], cen[c * pd + p]);
+                                dsq = __dadd_rn(dsq, __dmul_rn(df, df));
+                            }
+                        if (c == 0 || dsq < bd) { bd = dsq; best = c; }
+                    }
+                    if (best != lab8[l]) { lab8[l] = (uint8_t)best; any = 1; }
+                    lab = best;
+                } else {
+                    lab = hist[(int)((((long long)qi[0] - lo) * kKmInitBins) / span)];
+                    lab8[l] = (uint8_t)lab;
+                }
+            } else if (!assign && l < L) {
+                lab8[l] = 0;
+            }
+            // integer sums of the batch, one cluster at a time (a batch of 32 neighbouring lines rarely holds
+            // more than two)
+            unsigned todo = __ballot_sync(0xffffffffu, lab >= 0);
+            while (todo) {
+                const int c = __shfl_sync(0xffffffffu, lab, __ffs(todo) - 1);
+                const bool in = lab == c;
+                const unsigned members = __ballot_sync(0xffffffffu, in);
+#pragma unroll
+                for (int p = 0; p < kMaxPcaDim; ++p)
+                    if (p < pd) {
+                        const int v = __reduce_add_sync(0xffffffffu, in ? qi[p] : 0);
+                        if (lane == 0) mine[c * stride + p] += v;
+                    }
+                if (lane == 0) mine[c * stride + pd] += __popc(members);
+                todo &= ~members;
+            }
+        }
+        return any;
+    };
+    sweep(false);
     __syncthreads();
 
     int iter = 0;
     for (;; ++iter) {
         // ---- centroids of the current partition (integer sums: order-free, exact)
-        for (int i = tid; i < kKmWarps * k * stride; i += blockDim.x) acc[i] = 0;
-        if (tid == 0) changed = 0;
-        __syncthreads();
-        long long* mine = acc + warp * k * stride;
-        for (int l = tid; l < L; l += blockDim.x) {
-            if (!mask[(long long)l * S + s]) continue;
-            const int lab = lab8[l];
-            unsigned long long* dst = reinterpret_cast<unsigned long long*>(mine + lab * stride);
-            for (int p = 0; p < pd; ++p)
-                atomicAdd(dst + p, (unsigned long long)llrint(y[(long long)l * pd + p] * scale));
-            atomicAdd(dst + pd, 1ull);
-        }
-        __syncthreads();
         for (int i = tid; i < k * pd; i += blockDim.x) {
             const int c = i / pd, p = i % pd;
             long long sum = 0, cnt = 0;
@@ -234,44 +289,32 @@ __global__ void __launch_bounds__(kKmThreads)
         }
         __syncthreads();
         if (iter >= max_iter) break;
-        // ---- reassign: nearest centroid, squared distance summed over components in order, first minimum
-        int any = 0;
-        for (int l = tid; l < L; l += blockDim.x) {
-            if (!mask[(long long)l * S + s]) continue;
-            double q[kMaxPcaDim];
-            for (int p = 0; p < pd; ++p) q[p] = (double)llrint(y[(long long)l * pd + p] * scale);
-            int best = 0;
-            double bd = 0.0;
-            for (int c = 0; c < k; ++c) {
-                double dsq = 0.0;
-                for (int p = 0; p < pd; ++p) {
-                    const double df = __dsub_rn(q[p], cen[c * pd + p]);
-                    dsq = __dadd_rn(dsq, __dmul_rn(df, df));
-                }
-                if (c == 0 || dsq < bd) { bd = dsq; best = c; }
-            }
-            if (best != lab8[l]) { lab8[l] = (uint8_t)best; any = 1; }
-        }
-        if (any) changed = 1;
+        for (int i = tid; i < kKmWarps * k * stride; i += blockDim.x) acc[i] = 0;
         __syncthreads();
-        if (!changed) break;
+        // ---- reassign and rebuild the sums in the same pass
+        if (sweep(true)) changed = 1;
         __syncthreads();
+        const int ch = changed;
+        __syncthreads();
+        if (tid == 0) changed = 0;
+        if (!ch) break;
     }
     for (int l = tid; l < L; l += blockDim.x)
-        labels[(long long)l * S + s] = mask[(long long)l * S + s] ? (int32_t)lab8[l] : 0;
+        labels[(long long)l * S + s] = (q[l] != kInvalid) ? (int32_t)lab8[l] : 0;
     if (tid == 0) iters_g[s] = iter;
 }
 
 void launch_pca_kmeans(const Dims& d, const float* xt, const uint8_t* mask, const double* mu, const int* n,
                        const double* P, const double* lam, int pcadim, int k, int max_iter, int* pick,
-                       double* vtop, double* y, uint8_t* lab8, int32_t* labels, int* iters, cudaStream_t st) {
+                       double* vtop, double* y, int32_t* q, uint8_t* lab8, int32_t* labels, int* iters,
+                       cudaStream_t st) {
     pca_pick_kernel<<<d.S, 128, 0, st>>>(lam, P, mu, n, d.D, d.DP, pcadim, pick, vtop);
     const dim3 grid((d.L + 255) / 256, d.S);
     const size_t smem = (size_t)(d.D * pcadim + d.D) * sizeof(double);
     pca_project_kernel<<<grid, 256, smem, st>>>(xt, mask, mu, vtop, d.L, d.S, d.D, d.DP, pcadim, y);
     const size_t smem2 = (size_t)(kKmWarps * k * (pcadim + 1)) * sizeof(long long) + (size_t)k * pcadim * sizeof(double);
     cudaFuncSetAttribute(kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    kmeans_kernel<<<d.S, kKmThreads, smem2, st>>>(y, mask, n, d.L, d.S, pcadim, k, max_iter, lab8, labels, iters);
+    kmeans_kernel<<<d.S, kKmThreads, smem2, st>>>(y, mask, n, d.L, d.S, pcadim, k, max_iter, q, lab8, labels, iters);
 }
 
 }  // namespace cmf
