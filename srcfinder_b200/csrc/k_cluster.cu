@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256)
 constexpr int kKmThreads = 256;
 constexpr int kKmWarps = kKmThreads / 32;
 constexpr int kKmInitBins = 4096;
+constexpr int kSmallK = 4;          // up to this many clusters the sums are kept per thread
 
 __device__ __forceinline__ double block_max(double v, double* red) {
 #pragma unroll
@@ -130,7 +131,8 @@ __device__ __forceinline__ long long block_minmax_i64(long long v, bool want_max
 // spatially coherent batch would aim at the same address.  Arithmetic and tie rules are unchanged (exact integer
 // sums, double distances summed over the components in order), so labels are bit-identical to the numpy
 // restatement in oracle/cluster_oracle.py.
-__global__ void __launch_bounds__(kKmThreads)
+template <int PDM>
+__global__ void __launch_bounds__(kKmThreads, PDM <= 8 ? 3 : 2)
     kmeans_kernel(const double* __restrict__ y_g, const uint8_t* __restrict__ mask, const int* __restrict__ n_g,
                   int L, int S, int pd, int k, int max_iter, int32_t* __restrict__ q_g, uint8_t* __restrict__ lab8_g,
                   int32_t* __restrict__ labels, int* __restrict__ iters_g) {
@@ -139,6 +141,8 @@ __global__ void __launch_bounds__(kKmThreads)
     const int stride = pd + 1;
     long long* acc = reinterpret_cast<long long*>(smu);
     double* cen = reinterpret_cast<double*>(acc + kKmWarps * k * stride);
+    int* priv = reinterpret_cast<int*>(cen + k * pd);   // [k][pd + 1][threads], only when k <= kSmallK
+    const bool small = k <= kSmallK;
     __shared__ double redd[kKmWarps];
     __shared__ long long redi[kKmWarps];
     __shared__ int changed;
@@ -210,6 +214,7 @@ __global__ void __launch_bounds__(kKmThreads)
     }
     for (int i = tid; i < k * pd; i += blockDim.x) cen[i] = 0.0;
     for (int i = tid; i < kKmWarps * k * stride; i += blockDim.x) acc[i] = 0;
+    if (small) for (int i = tid; i < k * stride * kKmThreads; i += blockDim.x) priv[i] = 0;
     if (tid == 0) changed = 0;
     __syncthreads();
 
@@ -218,18 +223,24 @@ __global__ void __launch_bounds__(kKmThreads)
     // one sweep: (assign) the label of every valid pixel, then its quantised components into the sums of that label
     auto sweep = [&](bool assign) {
         int any = 0;
-        for (int l = tid; l < Lpad; l += blockDim.x) {
-            int32_t qi[kMaxPcaDim];
-            bool valid = false;
-            if (l < L) {
-                qi[0] = q[l];
-                valid = qi[0] != kInvalid;
+        int since = 0;
+        // thread-private 32-bit sums in shared memory, element (c, p) of thread t at priv[(c * stride + p) * T + t]
+        auto flush = [&]() {
+            for (int i = 0; i < k * stride; ++i) {
+                const int v = priv[i * kKmThreads + tid];
+                if (v != 0) {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(mine + i), (unsigned long long)(long long)v);
+                    priv[i * kKmThreads + tid] = 0;
+                }
             }
+        };
+        for (int l = tid; l < Lpad; l += blockDim.x) {
+            int32_t qi[PDM];
+#pragma unroll
+            for (int p = 0; p < PDM; ++p) qi[p] = (p < pd && l < L) ? q[(long long)p * L + l] : kInvalid;
+            const bool valid = l < L && qi[0] != kInvalid;
             int lab = -1;
             if (valid) {
-#pragma unroll
-                for (int p = 1; p < kMaxPcaDim; ++p)
-                    if (p < pd) qi[p] = q[(long long)p * L + l];
                 if (assign) {
                     // nearest centroid, squared distance summed over components in order, first minimum
                     int best = 0;
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(kKmThreads)
                     for (int c = 0; c < k; ++c) {
                         double dsq = 0.0;
 #pragma unroll
-                        for (int p = 0; p < kMaxPcaDim; ++p)
+                        for (int p = 0; p < PDM; ++p)
                             if (p < pd) {
                                 const double df = __dsub_rn((double)qi[p], cen[c * pd + p]);
                                 dsq = __dadd_rn(dsq, __dmul_rn(df, df));
@@ -253,6 +264,19 @@ __global__ void __launch_bounds__(kKmThreads)
             } else if (!assign && l < L) {
                 lab8[l] = 0;
             }
+            if (small) {
+                // few clusters: private 32-bit sums per thread (|q| <= 2^24, flushed before 64 additions could
+                // overflow) -- plain read-modify-write, no atomics, no warp reductions
+                if (lab >= 0) {
+                    int* dst = priv + (lab * stride) * kKmThreads + tid;
+#pragma unroll
+                    for (int p = 0; p < PDM; ++p)
+                        if (p < pd) dst[p * kKmThreads] += qi[p];
+                    dst[pd * kKmThreads] += 1;
+                }
+                if (++since == 64) { flush(); since = 0; }
+                continue;
+            }
             // integer sums of the batch, one cluster at a time (a batch of 32 neighbouring lines rarely holds
             // more than two)
             unsigned todo = __ballot_sync(0xffffffffu, lab >= 0);
@@ -261,7 +285,7 @@ __global__ void __launch_bounds__(kKmThreads)
                 const bool in = lab == c;
                 const unsigned members = __ballot_sync(0xffffffffu, in);
 #pragma unroll
-                for (int p = 0; p < kMaxPcaDim; ++p)
+                for (int p = 0; p < PDM; ++p)
                     if (p < pd) {
                         const int v = __reduce_add_sync(0xffffffffu, in ? qi[p] : 0);
                         if (lane == 0) mine[c * stride + p] += v;
@@ -270,6 +294,7 @@ __global__ void __launch_bounds__(kKmThreads)
                 todo &= ~members;
             }
         }
+        if (small) flush();
         return any;
     };
     sweep(false);
@@ -312,9 +337,16 @@ void launch_pca_kmeans(const Dims& d, const float* xt, const uint8_t* mask, cons
     const dim3 grid((d.L + 255) / 256, d.S);
     const size_t smem = (size_t)(d.D * pcadim + d.D) * sizeof(double);
     pca_project_kernel<<<grid, 256, smem, st>>>(xt, mask, mu, vtop, d.L, d.S, d.D, d.DP, pcadim, y);
-    const size_t smem2 = (size_t)(kKmWarps * k * (pcadim + 1)) * sizeof(long long) + (size_t)k * pcadim * sizeof(double);
-    cudaFuncSetAttribute(kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    kmeans_kernel<<<d.S, kKmThreads, smem2, st>>>(y, mask, n, d.L, d.S, pcadim, k, max_iter, q, lab8, labels, iters);
+    const size_t smem2 = (size_t)(kKmWarps * k * (pcadim + 1)) * sizeof(long long) + (size_t)k * pcadim * sizeof(double) +
+                         (k <= kSmallK ? (size_t)k * (pcadim + 1) * kKmThreads * sizeof(int) : 0);
+    if (pcadim <= 8) {
+        cudaFuncSetAttribute(kmeans_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        kmeans_kernel<8><<<d.S, kKmThreads, smem2, st>>>(y, mask, n, d.L, d.S, pcadim, k, max_iter, q, lab8, labels, iters);
+    } else {
+        cudaFuncSetAttribute(kmeans_kernel<kMaxPcaDim>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        kmeans_kernel<kMaxPcaDim><<<d.S, kKmThreads, smem2, st>>>(y, mask, n, d.L, d.S, pcadim, k, max_iter, q, lab8, labels,
+                                                              iters);
+    }
 }
 
 }  // namespace cmf
