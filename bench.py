@@ -441,14 +441,28 @@ def measure_e2e(torch, eng, slab, L, S, D, args, world, rank, dev, barrier):
     import torch.distributed as dist
     from srcfinder_b200 import ColumnwiseMF
     nbytes = L * BANDS * S * 4
+    host_note = "pinned float32 BIL cube (L,425,S); only the active window is copied"
+    own = []
     try:
         host = torch.zeros((L, BANDS, S), dtype=torch.float32, pin_memory=True)
-    except Exception as exc:                                    # not enough lockable memory on this box
-        return {"value": None, "unit": UNIT, "error": "pinned %d-byte host cube failed: %s" % (nbytes, exc)}
-    host[:, ACTIVE[0] - 1:ACTIVE[1], :].copy_(slab)             # only the bands the path reads carry data
-    torch.cuda.synchronize()
-    eng2 = ColumnwiseMF(L, BANDS, S, ACTIVE, abscf_window(), device=dev.index)
-    engines = [eng, eng2]
+        host[:, ACTIVE[0] - 1:ACTIVE[1], :].copy_(slab)         # only the bands the path reads carry data
+        torch.cuda.synchronize()
+        eng2 = ColumnwiseMF(L, BANDS, S, ACTIVE, abscf_window(), device=dev.index)
+        engines = [eng, eng2]
+        own = [eng2]
+    except Exception as exc:
+        # not enough lockable memory for the full 425-band cube on this box: the same bytes cross PCIe from a
+        # pinned cube that holds the active window only (declared as a D-band cube)
+        try:
+            host = torch.zeros((L, D, S), dtype=torch.float32, pin_memory=True)
+            host.copy_(slab)
+            torch.cuda.synchronize()
+            engines = [ColumnwiseMF(L, D, S, [1, D], abscf_window(), device=dev.index) for _ in range(2)]
+            own = list(engines)
+            host_note = ("pinned float32 BIL cube of the active window only (L,%d,S): the full %d-byte cube could "
+                         "not be pinned (%s); identical bytes cross PCIe" % (D, nbytes, str(exc)[:80]))
+        except Exception as exc2:
+            return {"value": None, "unit": UNIT, "error": "pinned host cube failed: %s" % (exc2,)}
     mf = [torch.empty((L, S), dtype=torch.float64, pin_memory=True) for _ in range(2)]
     cs = [torch.empty((3, S), dtype=torch.float64, pin_memory=True) for _ in range(2)]
     ai = [torch.empty((S,), dtype=torch.int32, pin_memory=True) for _ in range(2)]
@@ -481,14 +495,15 @@ def measure_e2e(torch, eng, slab, L, S, D, args, world, rank, dev, barrier):
         dt, dt_sync = float(t[0].item()), float(t[1].item())
     checksum = float(cs[0][2].sum())                            # the result really came back
     same = bool(torch.equal(mf[0], mf[1])) if steps > 1 else None
-    eng2.close()
+    for e_ in own:
+        e_.close()
     return {"value": world * L * S * steps / dt / 1e6, "unit": UNIT, "ms_per_step": dt / steps * 1e3,
             "h2d_bytes_per_step": L * D * S * 4, "d2h_bytes_per_step": L * S * 8 + 3 * S * 8 + S * 4,
             "steps": steps, "mode": "two contexts used alternately, cmf_run_host(CMF_RUN_ASYNC): the next "
                                     "flightline uploads while the previous one is scored",
             "sync_call": {"value": world * L * S * steps / dt_sync / 1e6, "unit": UNIT,
                           "ms_per_step": dt_sync / steps * 1e3},
-            "host_buffer": "pinned float32 BIL cube (L,425,S); only the active window is copied",
+            "host_buffer": host_note, "h2d_gbs": L * D * S * 4 / (dt / steps) / 1e9,
             "colstd_checksum": checksum, "both_contexts_identical": same}
 
 
