@@ -217,7 +217,9 @@ int cmf_host_unregister(void* p);
  *       5 bulk-async-copy read GB/s, 6 f32->f64 conversions G/s, 7 FP64 log+divide pairs G/s,
  *       9 legacy mma.sync tf32 TFLOP/s, 10 legacy mma.sync bf16 TFLOP/s, 11 FP32 FFMA TFLOP/s,
  *       12-15 dependent-issue latency in cycles of DFMA / rsqrt+DADD / sqrt+DADD / divide+DADD (one thread),
- *       16-18 cycles per step of the QL rotation recurrence: alone / 20 chains per SM / 5 chains per SM */
+ *       16-18 cycles per step of the QL rotation recurrence: alone / 20 chains per SM / 5 chains per SM,
+ *       30-33 GB/s of the two halves of the repack pass alone: slab read through 4-byte LDGSTS / 8-byte LDGSTS /
+ *             8-byte loads, and the 16-byte xt write side */
 double cmf_microbench(int device, int kind, int iters);
 
 #ifdef __cplusplus

@@ -367,6 +367,165 @@ __global__ void __launch_bounds__(CG * 2 * NT, repack_pipe_minb(NT, CG, LT, NS))
     }
 }
 
+// ---------------------------------------------------------------------------------------- K0 (pair copies)
+// The same pipeline with 8-byte copies.  Measured in isolation on B200 (cmf_microbench kinds 30-33): the slab read
+// through 4-byte LDGSTS runs at 2.1 TB/s -- it alone took 1.6 of the pass's 1.9 ms -- through 8-byte LDGSTS at
+// 3.9 TB/s, and the 16-byte write side at 5.3 TB/s.  So whenever the rows are 8-byte aligned (even sample count
+// and pitches: d.vec2) a copy moves the radiances of TWO neighbouring columns, and the shared tile is
+// [column pair][line][band] in float2 units: pair stride 2 mod 16 units plus an XOR of the lowest unit index bit
+// for pairs 8..15 keeps the 16 lanes of a half-warp copy on 16 different 8-byte bank pairs, and a thread's four
+// bands x two columns are two aligned 16-byte reads.  thread <-> (column pair, 4 bands): 2 LDS.128 in, two
+// validity tests, 8 FP64 column-sum adds and 2 STG.128 out per line.  Always 32 columns per CTA.
+template <int NT, int LT, int NS>
+__global__ void __launch_bounds__(32 * NT, repack_pipe_minb(NT, 32, LT, NS)) repack_pair_kernel(
+    const float* __restrict__ slab, long long line_pitch, int band_pitch, int L, int S, int D,
+    float* __restrict__ xt, uint8_t* __restrict__ mask, double* __restrict__ colsum_part,
+    int* __restrict__ colcnt_part, int lines_per_split, int line_base, int line_limit, int split_base,
+    const uint8_t* __restrict__ sel, int write_mask) {
+    constexpr int DP = 8 * NT, Q = 2 * NT, NP = 16, CG = 32, NTH = NP * Q, CS2 = LT * DP + 2;   // float2 units
+    extern __shared__ __align__(16) float2 tile2[];   // [NS][NP][CS2]
+    __shared__ uint8_t bad[2][LT * CG];
+
+    const int tid = threadIdx.x;
+    const int s0 = blockIdx.x * CG;
+    const int split = split_base + blockIdx.y;
+    const int l_begin = line_base + blockIdx.y * lines_per_split;
+    const int l_end = min(line_limit, l_begin + lines_per_split);
+    // load side: half-warp <-> the 16 column pairs of one (line, band) row; a thread owns bands r_ld + k*Q
+    const int p_ld = tid % NP, r_ld = tid / NP;
+    const bool ld_ok = s0 + 2 * p_ld < S;
+    const int key_ld = (p_ld >> 3) & 1;
+    uint32_t sdst[4];
+    long long goff[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int b = r_ld + k * Q;
+        sdst[k] = smem_u32(tile2 + (size_t)p_ld * CS2 + (b ^ key_ld));
+        goff[k] = (ld_ok && b < D) ? (long long)b * band_pitch : -1;
+    }
+    // store side: thread <-> (column pair, 4 consecutive bands)
+    const int cp = tid / Q, q = tid % Q;
+    const bool col_ok = s0 + 2 * cp < S;
+    const int key = (cp >> 3) & 1;
+
+    for (int i = tid; i < NS * NP * CS2; i += NTH) tile2[i] = make_float2(0.f, 0.f);   // padded bands stay zero
+    for (int i = tid; i < 2 * LT * CG; i += NTH) (&bad[0][0])[i] = 0;
+    __syncthreads();
+
+    auto issue = [&](int buf, int l0, int nl) {
+        const float* src = slab + (long long)l0 * line_pitch + s0 + 2 * p_ld;
+        const uint32_t boff = (uint32_t)(buf * NP * CS2 * sizeof(float2));
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            if (l < nl) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (goff[k] >= 0)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sdst[k] + boff +
+                                                                                      (uint32_t)(l * DP * 8)),
+                                     "l"(src + goff[k])
+                                     : "memory");
+            }
+            src += line_pitch;
+        }
+        cp_async_commit();
+    };
+
+    double acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = 0.0;
+    int cnt0 = 0, cnt1 = 0;
+    const int ntiles = (l_end - l_begin + LT - 1) / LT;
+#pragma unroll
+    for (int p = 0; p < NS - 1; ++p) {
+        if (p < ntiles) issue(p, l_begin + p * LT, min(LT, l_end - (l_begin + p * LT)));
+        else cp_async_commit();
+    }
+    int buf = 0, nbuf = NS - 1;
+    for (int it = 0; it < ntiles; ++it) {
+        const int l0 = l_begin + it * LT;
+        const int nl = min(LT, l_end - l0);
+        if (it + NS - 1 < ntiles) issue(nbuf, l0 + (NS - 1) * LT, min(LT, l_end - l0 - (NS - 1) * LT));
+        else cp_async_commit();
+        cp_async_wait<NS - 1>();
+        __syncthreads();                                   // tile `it` has landed for every thread
+        uint8_t* bd = bad[it & 1];
+        float4 v0[LT], v1[LT];                             // the two columns of the pair
+        if (col_ok) {
+            const float4* src = reinterpret_cast<const float4*>(tile2 + (size_t)(buf * NP + cp) * CS2 + 4 * q);
+#pragma unroll
+            for (int l = 0; l < LT; ++l) {
+                if (l < nl) {
+                    float4 a = src[l * (DP / 2)], b = src[l * (DP / 2) + 1];   // units (4q, 4q+1), (4q+2, 4q+3)
+                    if (key) {   // pairs 8..15 hold neighbouring bands swapped (uniform for all but a few warps)
+                        a = make_float4(a.z, a.w, a.x, a.y);
+                        b = make_float4(b.z, b.w, b.x, b.y);
+                    }
+                    const float4 x0 = make_float4(a.x, a.z, b.x, b.z), x1 = make_float4(a.y, a.w, b.y, b.w);
+                    v0[l] = x0;
+                    v1[l] = x1;
+                    if (!quad_ok(x0)) bd[l * CG + 2 * cp] = 1;
+                    if (!quad_ok(x1)) bd[l * CG + 2 * cp + 1] = 1;
+                }
+            }
+        }
+        __syncthreads();                                   // flags complete; this tile buffer may be refilled
+        for (int i = tid; i < LT * CG; i += NTH) {
+            const int l = i / CG, cc = i % CG;
+            if (l < nl && s0 + cc < S) {
+                const long long o = (long long)(l0 + l) * S + s0 + cc;
+                if (write_mask) mask[o] = bd[i] ? 0 : 1;
+                if (sel != nullptr && sel[o] == 0) bd[i] = 1;
+            }
+            bad[(it & 1) ^ 1][i] = 0;                       // flags of the next tile (last read one tile ago)
+        }
+        if (sel != nullptr) __syncthreads();
+        if (col_ok) {
+            float* dst0 = xt + ((long long)(s0 + 2 * cp) * L + l0) * DP + 4 * q;
+            float* dst1 = dst0 + (long long)L * DP;
+            const float qnan = __int_as_float(0x7fc00000);
+            const float4 nan4 = make_float4(qnan, qnan, qnan, qnan);
+#pragma unroll
+            for (int l = 0; l < LT; ++l) {
+                if (l < nl) {
+                    float4 x0 = v0[l], x1 = v1[l];
+                    if (bd[l * CG + 2 * cp]) {
+                        x0 = nan4;
+                    } else {
+                        acc[0][0] += (double)x0.x; acc[0][1] += (double)x0.y; acc[0][2] += (double)x0.z;
+                        acc[0][3] += (double)x0.w;
+                        ++cnt0;
+                    }
+                    if (bd[l * CG + 2 * cp + 1]) {
+                        x1 = nan4;
+                    } else {
+                        acc[1][0] += (double)x1.x; acc[1][1] += (double)x1.y; acc[1][2] += (double)x1.z;
+                        acc[1][3] += (double)x1.w;
+                        ++cnt1;
+                    }
+                    *reinterpret_cast<float4*>(dst0 + l * DP) = x0;
+                    *reinterpret_cast<float4*>(dst1 + l * DP) = x1;
+                }
+            }
+        }
+        nbuf = buf;
+        buf = buf + 1 == NS ? 0 : buf + 1;
+    }
+    if (col_ok) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            double* o = colsum_part + ((long long)split * S + s0 + 2 * cp + j) * DP + 4 * q;
+            o[0] = acc[j][0]; o[1] = acc[j][1]; o[2] = acc[j][2]; o[3] = acc[j][3];
+        }
+        if (q == 0) {
+            colcnt_part[split * S + s0 + 2 * cp] = cnt0;
+            colcnt_part[split * S + s0 + 2 * cp + 1] = cnt1;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------- K0b
 // Splits [0, nsplit) give the column mean; the same kernel over the first `nsplit` = pilot splits gives the
 // pilot centre of the Gram pass (n == NULL: the count is not stored).
@@ -626,7 +785,7 @@ __global__ void colstats_kernel(const double* __restrict__ stat_part, int nlanes
 // the older single-stage kernel (kept for A/B measurements through tools/).
 struct RepackVariant { int cg, lt, ns; };
 
-#define CMF_REPACK_VARIANTS(X) X(32, 8, 2) X(32, 8, 3) X(32, 4, 3) X(32, 4, 4) X(16, 8, 3) X(16, 4, 2) X(16, 4, 3) X(16, 4, 4)
+#define CMF_REPACK_VARIANTS(X) X(32, 8, 2) X(32, 8, 3) X(32, 4, 3) X(32, 4, 4) X(32, 4, 5) X(32, 4, 6) X(32, 2, 8) X(16, 8, 3) X(16, 4, 2) X(16, 4, 3) X(16, 4, 4)
 
 static RepackVariant repack_variant_requested() {
     // tuning hook (tools/ only): CMF_REPACK_VARIANT=CG,LT,NS picks another instantiation, "0,0,0" the old kernel
@@ -668,6 +827,40 @@ static int repack_pipe_resident() {
     return nb;
 }
 
+// 8-byte copies (repack_pair_kernel) whenever the rows allow it; CMF_REPACK_PAIR=0 keeps the 4-byte kernel (tools/)
+static bool repack_use_pair(const Dims& d, const RepackVariant& v) {
+    static const bool enabled = [] { const char* e = getenv("CMF_REPACK_PAIR"); return !(e && e[0] == '0'); }();
+    return enabled && d.vec2 && v.cg == 32;
+}
+
+template <int NT, int LT, int NS>
+static size_t repack_pair_smem() { return (size_t)NS * 16 * (LT * 8 * NT + 2) * sizeof(float2); }
+
+template <int NT, int LT, int NS>
+static int repack_pair_resident() {
+    const size_t smem = repack_pair_smem<NT, LT, NS>();
+    if (smem > 227 * 1024) return 0;
+    cudaFuncSetAttribute(repack_pair_kernel<NT, LT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, repack_pair_kernel<NT, LT, NS>, 32 * NT, smem) != cudaSuccess) {
+        cudaGetLastError();
+        nb = 0;
+    }
+    return nb;
+}
+
+template <int NT>
+static int repack_pair_resident_t(const RepackVariant& v) {
+    if (v.lt == 4 && v.ns == 4) return repack_pair_resident<NT, 4, 4>();
+    if (v.lt == 4 && v.ns == 5) return repack_pair_resident<NT, 4, 5>();
+    if (v.lt == 4 && v.ns == 6) return repack_pair_resident<NT, 4, 6>();
+    if (v.lt == 2 && v.ns == 8) return repack_pair_resident<NT, 2, 8>();
+    if (v.lt == 4 && v.ns == 3) return repack_pair_resident<NT, 4, 3>();
+    if (v.lt == 8 && v.ns == 2) return repack_pair_resident<NT, 8, 2>();
+    if (v.lt == 8 && v.ns == 3) return repack_pair_resident<NT, 8, 3>();
+    return 0;
+}
+
 template <int NT>
 static int repack_resident_t(const RepackVariant& v) {
 #define CMF_RV(CGv, LTv, NSv) \
@@ -700,7 +893,8 @@ int repack_nsplit(const Dims& d) {
     const RepackVariant v = repack_variant(d.NT);
     if (v.cg > 0) {
         int resident = 0, sms = 148, dev = 0;
-        CMF_NT_SWITCH(d.NT, (resident = repack_resident_t<NTc>(v)));
+        if (repack_use_pair(d, v)) { CMF_NT_SWITCH(d.NT, (resident = repack_pair_resident_t<NTc>(v))); }
+        else { CMF_NT_SWITCH(d.NT, (resident = repack_resident_t<NTc>(v))); }
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (resident > 0) {
@@ -739,6 +933,23 @@ static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t
                             int* colcnt_part, int lps, int line_base, int line_limit, int split_base,
                             const uint8_t* sel, int write_mask, cudaStream_t st) {
     const RepackVariant v = repack_variant(NT);
+    if (repack_use_pair(d, v)) {
+        const int nblk = (line_limit - line_base + lps - 1) / lps;
+        if (nblk <= 0) return;
+        dim3 grid((d.S + 31) / 32, nblk);
+#define CMF_RP(LTv, NSv)                                                                                          \
+        if (v.lt == LTv && v.ns == NSv) {                                                                         \
+            const size_t smem = repack_pair_smem<NT, LTv, NSv>();                                                 \
+            cudaFuncSetAttribute(repack_pair_kernel<NT, LTv, NSv>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                 (int)smem);                                                                      \
+            repack_pair_kernel<NT, LTv, NSv><<<grid, 32 * NT, smem, st>>>(                                        \
+                slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, xt, mask, colsum_part, colcnt_part, lps,         \
+                line_base, line_limit, split_base, sel, write_mask);                                              \
+            return;                                                                                               \
+        }
+        CMF_RP(4, 4) CMF_RP(4, 3) CMF_RP(8, 2) CMF_RP(8, 3) CMF_RP(4, 5) CMF_RP(4, 6) CMF_RP(2, 8)
+#undef CMF_RP
+    }
 #define CMF_RV(CGv, LTv, NSv)                                                                                \
     if (v.cg == CGv && v.lt == LTv && v.ns == NSv)                                                   \
         return launch_repack_pipe<NT, CGv, LTv, NSv>(d, slab, xt, mask, colsum_part, colcnt_part, lps,       \

@@ -244,6 +244,68 @@ __global__ void ql_chain_kernel(double* out, long long* cycles, int n, int steps
     if (blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = t1 - t0;
 }
 
+// The two halves of the repack pass in isolation (kinds 30-33), same shapes as repack_pipe_kernel<9, 32, 4, 4>:
+//   READ : slab [L][72][598] -> shared, runs of 32 columns (128 B) per (line, band) row, 4-line tiles, ring of 4,
+//          through 4-byte LDGSTS (kind 30), 8-byte LDGSTS (31) or plain 8-byte loads to registers (32)
+//   WRITE: 16-byte stores of each column's contiguous [4][72] block of xt [598][L][72] (33)
+template <int MODE>
+__global__ void __launch_bounds__(576) repack_half_kernel(const float* __restrict__ slab, float* __restrict__ xt,
+                                                          int L, int S, int D, int lines_per_cta, float* sink) {
+    constexpr int CG = 32, LT = 4, NS = 4, DP = 72, CS = LT * DP + 4;
+    extern __shared__ __align__(16) float tile[];
+    const int tid = threadIdx.x, s0 = blockIdx.x * CG;
+    const int l_begin = blockIdx.y * lines_per_cta, l_end = min(L, l_begin + lines_per_cta);
+    const int ntiles = (l_end - l_begin + LT - 1) / LT;
+    float accf = 0.f;
+    if (MODE <= 2) {
+        const int w = (MODE == 0) ? 1 : 2;                       // columns per copy
+        const int c_ld = (tid % (CG / w)) * w, r_ld = tid / (CG / w);
+        const int rows_per_pass = 576 / (CG / w);
+        const bool ok = s0 + c_ld < S;
+        for (int it = 0; it < ntiles + NS - 1; ++it) {
+            if (it < ntiles && ok) {
+                const int l0 = l_begin + it * LT, buf = it % NS;
+                for (int r = r_ld; r < LT * D; r += rows_per_pass) {
+                    const int l = r / D, b = r - l * D;
+                    if (l0 + l >= l_end) break;
+                    const float* src = slab + ((long long)(l0 + l) * D + b) * S + s0 + c_ld;
+                    float* dst = tile + (size_t)buf * CG * CS + (size_t)(r * CG + c_ld);
+                    if (MODE == 0)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+                    else if (MODE == 1)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+                    else {
+                        const float2 v = *reinterpret_cast<const float2*>(src);
+                        accf += v.x + v.y;
+                    }
+                }
+            }
+            if (MODE != 2) {
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 3;" ::: "memory");
+                __syncthreads();
+            }
+        }
+        if (MODE != 2) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            accf = tile[tid];
+        }
+    } else {
+        const int c = tid / 18, q = tid % 18;
+        if (s0 + c < S) {
+            for (int it = 0; it < ntiles; ++it) {
+                const int l0 = l_begin + it * LT;
+                float* dst = xt + ((long long)(s0 + c) * L + l0) * DP + 4 * q;
+#pragma unroll
+                for (int l = 0; l < LT; ++l)
+                    if (l0 + l < l_end) *reinterpret_cast<float4*>(dst + l * DP) = make_float4(1.f, 2.f, 3.f, (float)it);
+            }
+        }
+    }
+    if (accf == 123.456f) sink[0] = accf;
+}
+
 extern "C" double cmf_microbench(int device, int kind, int iters) {
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;
     cudaDeviceProp prop;
@@ -347,6 +409,35 @@ extern "C" double cmf_microbench(int device, int kind, int iters) {
         cudaMemcpy(&cyc, c, 8, cudaMemcpyDeviceToHost);
         result = (double)cyc / ((double)n * steps);        // cycles per rotation step
         cudaFree(o); cudaFree(c);
+    }
+    else if (kind >= 30 && kind <= 33) {
+        const int L = 20000, S = 598, D = 72;
+        const size_t n = (size_t)L * S * D;
+        float *slab, *xt, *sink;
+        if (cudaMalloc(&slab, n * 4) != cudaSuccess) return -1.0;
+        if (cudaMalloc(&xt, n * 4) != cudaSuccess) { cudaFree(slab); return -1.0; }
+        cudaMalloc(&sink, 16);
+        cudaMemset(slab, 0, n * 4);
+        const size_t smem = (size_t)4 * 32 * (4 * 72 + 4) * 4;
+        const dim3 grid(19, 7);
+        const int lpc = (L + 6) / 7;
+        auto run = [&]() {
+            if (kind == 30) repack_half_kernel<0><<<grid, 576, smem>>>(slab, xt, L, S, D, lpc, sink);
+            else if (kind == 31) repack_half_kernel<1><<<grid, 576, smem>>>(slab, xt, L, S, D, lpc, sink);
+            else if (kind == 32) repack_half_kernel<2><<<grid, 576, smem>>>(slab, xt, L, S, D, lpc, sink);
+            else repack_half_kernel<3><<<grid, 576, smem>>>(slab, xt, L, S, D, lpc, sink);
+        };
+        cudaFuncSetAttribute(repack_half_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(repack_half_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(repack_half_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(repack_half_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        run(); cudaDeviceSynchronize();
+        cudaEventRecord(e0);
+        for (int i = 0; i < iters; ++i) run();
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        const double sec = time_ms(e0, e1) * 1e-3 / iters;
+        result = (double)n * 4 / sec * 1e-9;                  // GB/s of the 3.44 GB slab (read) or xt (write)
+        cudaFree(slab); cudaFree(xt); cudaFree(sink);
     }
     else if (kind >= 20 && kind <= 25) {
         // tcgen05 TS-form self test: max |D - A.B^T| (exact inputs, so 0 when the layouts are right)

@@ -13,6 +13,6 @@ cut -c1-900 gpurun_out/bench.json
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 cut -c1-400 gpurun_out/bench_ref.json
 PROBE_RUNS=2 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python tools/profile_target.py > gpurun_out/ncu_launch.log 2>&1
-PROBE_RUNS=2 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'loo_screen5_kernel|loo_kernel|score_tiled_kernel|gram_kernel|repack_pipe_kernel|eigen_ql_kernel' -s 6 -c 6 -o gpurun_out/prof_r01 -f python tools/profile_target.py > gpurun_out/ncu_full.log 2>&1
+PROBE_RUNS=2 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'loo_screen5_kernel|loo_kernel|score_tiled_kernel|gram_kernel|repack_pair_kernel|eigen_ql_kernel' -s 6 -c 6 -o gpurun_out/prof_r01 -f python tools/profile_target.py > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 ls -la gpurun_out
