@@ -7,8 +7,6 @@
 namespace cmf {
 
 constexpr int kMaxNT = 12;          // active bands padded to 8*NT, NT <= 12 (D <= 96) for the shared-memory kernels
-constexpr int kRepackCG = 16;       // columns per repack tile
-constexpr int kRepackLT = 8;        // lines per repack tile
 constexpr int kGramTL = 16;         // lines per Gram tile (4 k-steps of DMMA.8x8x4)
 constexpr int kLooMT = 2;           // 8-pixel m-tiles per LOO pass
 constexpr int kScoreLines = 8;      // lines per thread in the scoring pass (scalar kernel)

@@ -1,5 +1,6 @@
 // HBM-bound streaming kernels of the columnwise matched filter (sm_100a):
-//   K0  repack_kernel   BIL active slab [L][D][S] -> column-major [S][L][DP] + valid mask + column sums
+//   K0  repack_pair_kernel / repack_pipe_kernel   BIL active slab [L][D][S] -> column-major [S][L][DP] + valid mask
+//       + column sums (8-byte / 4-byte copy variants)
 //   K0b mean_kernel     per-column mean / valid count from the K0 partials (fixed order)
 //   K5  score_kernel    the scoring pass: one read of the slab, fused mask + mean removal + dot + scale
 //   K6  colstats_kernel per-column npix / mean / std of the written scores
@@ -14,173 +15,9 @@
 
 namespace cmf {
 
-// ---------------------------------------------------------------------------------------- K0
-// One CTA = 16 columns x a line range.  Per 8-line tile: coalesced loads of the 16-column runs of every
-// (line, band) row into a padded shared tile, per-pixel validity (all D bands finite and >= 0), FP64
-// column sums over valid pixels kept in registers, then a transposed, fully coalesced write of each
-// column's [8][DP] block.  Invalid pixels are written as NaN in every band so later passes need no mask.
-template <int NT>
-__global__ void __launch_bounds__(256) repack_kernel(const float* __restrict__ slab, long long line_pitch,
-                                                     int band_pitch, int L, int S, int D, int vec2,
-                                                     float* __restrict__ xt, uint8_t* __restrict__ mask,
-                                                     double* __restrict__ colsum_part,
-                                                     int* __restrict__ colcnt_part, int lines_per_split,
-                                                     int line_base, int line_limit, int split_base,
-                                                     const uint8_t* __restrict__ sel, int write_mask) {
-    constexpr int DP = 8 * NT, CG = kRepackCG, LT = kRepackLT, CGP = CG + 1;
-    constexpr int NACC = (DP * CG + 255) / 256;
-    extern __shared__ float tile[];  // [LT][DP][CGP]
-    __shared__ uint8_t bad[LT * CG];
-
-    const int tid = threadIdx.x;
-    const int s0 = blockIdx.x * CG;
-    const int split = split_base + blockIdx.y;            // global index of this line range
-    const int l_begin = line_base + blockIdx.y * lines_per_split;
-    const int l_end = min(line_limit, l_begin + lines_per_split);
-
-    double acc[NACC];
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    int cnt = 0;
-
-    for (int l0 = l_begin; l0 < l_end; l0 += LT) {
-        const int nl = min(LT, l_end - l0);
-        __syncthreads();  // previous tile fully consumed
-        if (tid < LT * CG) bad[tid] = 0;
-        if (DP != D) {    // zero the padded bands once per tile
-            const int npad = DP - D;
-            for (int i = tid; i < nl * npad * CG; i += 256) {
-                const int c = i % CG, r = i / CG;
-                const int l = r / npad, b = D + r % npad;
-                tile[(l * DP + b) * CGP + c] = 0.0f;
-            }
-        }
-        __syncthreads();
-        // ---- phase 1: load rows (l, b) of 16 columns; loads are issued in batches of U before any use
-        const int rows = nl * D;
-        if (vec2) {
-            const int c2 = (tid & 7) * 2;
-            const int col = s0 + c2;
-            constexpr int U = 9;
-            if (col < S) {
-                int r = tid >> 3;
-                int l = r / D, b = r - l * D;
-                const float* p = slab + (long long)(l0 + l) * line_pitch + (long long)b * band_pitch + col;
-                while (r < rows) {
-                    float2 v[U];
-                    int off[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        off[u] = -1;
-                        if (r < rows) {
-                            v[u] = ldg_nc_f2(p);
-                            off[u] = (l * DP + b) * CGP + c2 + ((l * CG + c2) << 16);
-                        }
-                        r += 32; b += 32;
-                        p += 32LL * band_pitch;
-                        while (b >= D) { b -= D; ++l; p += line_pitch - (long long)D * band_pitch; }
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (off[u] >= 0) {
-                            float* t = tile + (off[u] & 0xffff);
-                            t[0] = v[u].x;
-                            t[1] = v[u].y;
-                            const int bo = off[u] >> 16;
-                            if (!pixel_value_ok(v[u].x)) bad[bo] = 1;
-                            if (!pixel_value_ok(v[u].y)) bad[bo + 1] = 1;
-                        }
-                    }
-                }
-            }
-        } else {
-            const int c1 = tid & 15;
-            const int col = s0 + c1;
-            constexpr int U = 9;
-            if (col < S) {
-                int r = tid >> 4;
-                int l = r / D, b = r - l * D;
-                const float* p = slab + (long long)(l0 + l) * line_pitch + (long long)b * band_pitch + col;
-                while (r < rows) {
-                    float v[U];
-                    int off[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        off[u] = -1;
-                        if (r < rows) {
-                            v[u] = ldg_nc_f1(p);
-                            off[u] = (l * DP + b) * CGP + c1 + ((l * CG + c1) << 16);
-                        }
-                        r += 16; b += 16;
-                        p += 16LL * band_pitch;
-                        while (b >= D) { b -= D; ++l; p += line_pitch - (long long)D * band_pitch; }
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (off[u] >= 0) {
-                            tile[off[u] & 0xffff] = v[u];
-                            if (!pixel_value_ok(v[u])) bad[off[u] >> 16] = 1;
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // validity is a property of the pixel (cmf/robust_mf.py:282); a background-mode pass (sel != NULL)
-        // additionally drops the valid pixels that are not members of the mode being fitted (:341)
-        if (tid < LT * CG) {
-            const int l = tid / CG, c = tid % CG;
-            if (l < nl && s0 + c < S) {
-                const long long o = (long long)(l0 + l) * S + s0 + c;
-                if (write_mask) mask[o] = bad[tid] ? 0 : 1;
-                if (sel != nullptr && sel[o] == 0) bad[tid] = 1;
-            }
-        }
-        __syncthreads();
-        // ---- phase 2: FP64 column sums over the included pixels (thread <-> fixed (band, column))
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) {
-            const int idx = tid + k * 256;
-            if (idx < DP * CG) {
-                const int b = idx / CG, c = idx % CG;
-                double a = 0.0;
-                for (int l = 0; l < nl; ++l)
-                    if (!bad[l * CG + c]) a += (double)tile[(l * DP + b) * CGP + c];
-                acc[k] += a;
-            }
-        }
-        if (tid < CG) {
-            int k = 0;
-            for (int l = 0; l < nl; ++l) k += bad[l * CG + tid] ? 0 : 1;
-            cnt += k;
-        }
-        // ---- phase 3: transposed write, each column's [nl][DP] block is contiguous in xt
-        const int per_col = nl * DP;
-        const float qnan = __int_as_float(0x7fc00000);
-        for (int c = 0; c < CG; ++c) {
-            if (s0 + c >= S) break;
-            float* dst = xt + ((long long)(s0 + c) * L + l0) * DP;
-            for (int i = tid; i < per_col; i += 256) {
-                const int l = i / DP;
-                const float v = tile[i * CGP + c];
-                dst[i] = bad[l * CG + c] ? qnan : v;
-            }
-        }
-    }
-    // ---- partial results of this line range
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) {
-        const int idx = tid + k * 256;
-        if (idx < DP * CG) {
-            const int b = idx / CG, c = idx % CG;
-            if (s0 + c < S) colsum_part[((long long)split * S + s0 + c) * DP + b] = acc[k];
-        }
-    }
-    if (tid < CG && s0 + tid < S) colcnt_part[split * S + s0 + tid] = cnt;
-}
-
-// ---------------------------------------------------------------------------------------- K0 (pipelined)
-// The same pass as a two-stage software pipeline.  One CTA = CG columns x a line range, tiles of LT lines.
+// ---------------------------------------------------------------------------------------- K0 (4-byte copies)
+// BIL active slab -> column-major copy + valid mask + column sums as a software pipeline (used when the rows are
+// not 8-byte aligned, i.e. odd sample counts; repack_pair_kernel below is the kernel otherwise).  One CTA = CG columns x a line range, tiles of LT lines.
 // Every radiance is moved global -> shared by a 4-byte LDGSTS (cp.async) straight into the TRANSPOSED tile
 // [column][line][band], so the loads of tile i+1 are in flight while tile i is checked and written, and no
 // register is held across the memory latency.  The write side is then pure 16-byte traffic: thread <->
@@ -785,15 +622,15 @@ __global__ void colstats_kernel(const double* __restrict__ stat_part, int nlanes
 // the older single-stage kernel (kept for A/B measurements through tools/).
 struct RepackVariant { int cg, lt, ns; };
 
-#define CMF_REPACK_VARIANTS(X) X(32, 8, 2) X(32, 8, 3) X(32, 4, 3) X(32, 4, 4) X(32, 4, 5) X(32, 4, 6) X(32, 2, 8) X(16, 8, 3) X(16, 4, 2) X(16, 4, 3) X(16, 4, 4)
+#define CMF_REPACK_VARIANTS(X) X(32, 8, 2) X(32, 4, 3) X(32, 4, 4) X(32, 2, 8) X(16, 4, 2)
 
 static RepackVariant repack_variant_requested() {
-    // tuning hook (tools/ only): CMF_REPACK_VARIANT=CG,LT,NS picks another instantiation, "0,0,0" the old kernel
+    // tuning hook (tools/ only): CMF_REPACK_VARIANT=CG,LT,NS picks another instantiation
     static RepackVariant v = [] {
-        const RepackVariant dflt{32, 4, 4};     // measured best on B200 (profiles/r01g_tune_repack.json)
+        const RepackVariant dflt{32, 4, 4};     // measured on B200 (profiles/r01g_ / r01i_tune_repack.json)
         RepackVariant r = dflt;
         if (const char* e = getenv("CMF_REPACK_VARIANT")) sscanf(e, "%d,%d,%d", &r.cg, &r.lt, &r.ns);
-        bool known = r.cg == 0;
+        bool known = false;
 #define CMF_RV(CGv, LTv, NSv) known = known || (r.cg == CGv && r.lt == LTv && r.ns == NSv);
         CMF_REPACK_VARIANTS(CMF_RV)
 #undef CMF_RV
@@ -806,7 +643,7 @@ static RepackVariant repack_variant_requested() {
 // falls back to the two-stage (16, 4) tile
 static RepackVariant repack_variant(int nt) {
     const RepackVariant v = repack_variant_requested();
-    if (v.cg > 0 && (size_t)v.ns * v.cg * (v.lt * 8 * nt + 4) * sizeof(float) > 227 * 1024) return RepackVariant{16, 4, 2};
+    if ((size_t)v.ns * v.cg * (v.lt * 8 * nt + 4) * sizeof(float) > 227 * 1024) return RepackVariant{16, 4, 2};
     return v;
 }
 
@@ -852,12 +689,9 @@ static int repack_pair_resident() {
 template <int NT>
 static int repack_pair_resident_t(const RepackVariant& v) {
     if (v.lt == 4 && v.ns == 4) return repack_pair_resident<NT, 4, 4>();
-    if (v.lt == 4 && v.ns == 5) return repack_pair_resident<NT, 4, 5>();
-    if (v.lt == 4 && v.ns == 6) return repack_pair_resident<NT, 4, 6>();
     if (v.lt == 2 && v.ns == 8) return repack_pair_resident<NT, 2, 8>();
     if (v.lt == 4 && v.ns == 3) return repack_pair_resident<NT, 4, 3>();
     if (v.lt == 8 && v.ns == 2) return repack_pair_resident<NT, 8, 2>();
-    if (v.lt == 8 && v.ns == 3) return repack_pair_resident<NT, 8, 3>();
     return 0;
 }
 
@@ -891,25 +725,17 @@ static int repack_resident_t(const RepackVariant& v) {
 // streams its whole line range, so the ranges are sized to fill the SMs' resident slots once.
 int repack_nsplit(const Dims& d) {
     const RepackVariant v = repack_variant(d.NT);
-    if (v.cg > 0) {
-        int resident = 0, sms = 148, dev = 0;
-        if (repack_use_pair(d, v)) { CMF_NT_SWITCH(d.NT, (resident = repack_pair_resident_t<NTc>(v))); }
-        else { CMF_NT_SWITCH(d.NT, (resident = repack_resident_t<NTc>(v))); }
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (resident > 0) {
-            const int groups = (d.S + v.cg - 1) / v.cg;
-            int ns = (sms * resident) / groups;
-            if (const char* e = getenv("CMF_REPACK_NSPLIT")) ns = atoi(e);      // tuning hook (tools/ only)
-            const int maxsplit = (d.L + 4 * v.lt - 1) / (4 * v.lt);     // at least 4 tiles per CTA
-            if (ns > maxsplit) ns = maxsplit;
-            return ns < 1 ? 1 : ns;
-        }
-    }
-    const int groups = (d.S + kRepackCG - 1) / kRepackCG;
-    int want = (148 * 5 + groups - 1) / groups;                 // ~5 CTAs per SM
-    int maxsplit = (d.L + 4 * kRepackLT - 1) / (4 * kRepackLT); // at least 4 tiles per CTA
-    int ns = want < maxsplit ? want : maxsplit;
+    int resident = 0, sms = 148, dev = 0;
+    if (repack_use_pair(d, v)) { CMF_NT_SWITCH(d.NT, (resident = repack_pair_resident_t<NTc>(v))); }
+    else { CMF_NT_SWITCH(d.NT, (resident = repack_resident_t<NTc>(v))); }
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (resident < 1) resident = 1;
+    const int groups = (d.S + v.cg - 1) / v.cg;
+    int ns = (sms * resident) / groups;
+    if (const char* e = getenv("CMF_REPACK_NSPLIT")) ns = atoi(e);      // tuning hook (tools/ only)
+    const int maxsplit = (d.L + 4 * v.lt - 1) / (4 * v.lt);             // at least 4 tiles per CTA
+    if (ns > maxsplit) ns = maxsplit;
     return ns < 1 ? 1 : ns;
 }
 
@@ -947,7 +773,7 @@ static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t
                 line_base, line_limit, split_base, sel, write_mask);                                              \
             return;                                                                                               \
         }
-        CMF_RP(4, 4) CMF_RP(4, 3) CMF_RP(8, 2) CMF_RP(8, 3) CMF_RP(4, 5) CMF_RP(4, 6) CMF_RP(2, 8)
+        CMF_RP(4, 4) CMF_RP(4, 3) CMF_RP(8, 2) CMF_RP(2, 8)
 #undef CMF_RP
     }
 #define CMF_RV(CGv, LTv, NSv)                                                                                \
@@ -956,15 +782,9 @@ static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t
                                                      line_base, line_limit, split_base, sel, write_mask, st);
     CMF_REPACK_VARIANTS(CMF_RV)
 #undef CMF_RV
-    constexpr int DP = 8 * NT;
-    const size_t smem = (size_t)kRepackLT * DP * (kRepackCG + 1) * sizeof(float);
-    cudaFuncSetAttribute(repack_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int nblk = (line_limit - line_base + lps - 1) / lps;
-    if (nblk <= 0) return;
-    dim3 grid((d.S + kRepackCG - 1) / kRepackCG, nblk);
-    repack_kernel<NT><<<grid, 256, smem, st>>>(slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, d.vec2, xt,
-                                               mask, colsum_part, colcnt_part, lps, line_base, line_limit,
-                                               split_base, sel, write_mask);
+    // repack_variant() only returns instantiated shapes
+    launch_repack_pipe<NT, 16, 4, 2>(d, slab, xt, mask, colsum_part, colcnt_part, lps, line_base, line_limit,
+                                     split_base, sel, write_mask, st);
 }
 
 int repack_lines_per_split(const Dims& d, int nsplit) {

@@ -1,5 +1,5 @@
-"""Tuning sweep of the repack pass (GPU box): one subprocess per CMF_REPACK_VARIANT ("0,0,0" = the single-stage
-kernel; "CG,LT,NS:nsplit" also forces the number of line ranges).  Every variant must give the same masks / alpha indices, and scores equal to ~1e-9 sigma."""
+"""Tuning sweep of the repack pass (GPU box): one subprocess per CMF_REPACK_VARIANT ("CG,LT,NS:nsplit" also forces the number of line ranges;
+CMF_REPACK_PAIR=0 in the environment keeps the 4-byte copy kernel).  Every variant must give the same masks / alpha indices, and scores equal to ~1e-9 sigma."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = r'''
@@ -25,7 +25,7 @@ with ColumnwiseMF(L, 425, S, active, ab) as eng:
                       "colstd_sum": float(cs[2].sum()), "colavg_absmax": float(np.abs(cs[1]).max())}))
 ''' % ROOT
 out = {}
-VARIANTS = ["0,0,0", "32,8,2", "32,8,3", "32,4,3", "32,4,4", "16,8,3", "16,4,2", "16,4,3", "16,4,4"]
+VARIANTS = ["32,4,4", "32,8,2", "32,4,3", "32,2,8", "16,4,2"]
 for v in sys.argv[1:] or VARIANTS:
     env = dict(os.environ, CMF_REPACK_VARIANT=v.split(":")[0])
     if ":" in v:
