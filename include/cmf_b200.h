@@ -100,6 +100,14 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p);
 /* Host cube (L,B,S) float32 BIL -> device: only the active band window is transferred
  * (one strided H2D copy; pinned memory makes it asynchronous).  Replaces the memmap gather at :298. */
 int cmf_upload_bil(cmf_ctx* ctx, const float* host_cube);
+/* The same in blocks of lines, for inputs that are read from disk while they are uploaded:
+ * host_block points at element (line line0, band band_first, sample 0) of a BIL block of `nlines` lines with
+ * `block_bands` bands per line (the whole band axis: band_first = 1, block_bands = bands; or only the active window:
+ * band_first = band_lo, block_bands = band_hi - band_lo + 1).  The copy is asynchronous on the context stream when
+ * the block is pinned (cmf_host_alloc): the caller fills the next block while this one is on the PCIe link, and must
+ * cmf_sync() before overwriting a block it has handed in.  The input is complete once every line has been given. */
+int cmf_upload_lines(cmf_ctx* ctx, const float* host_block, int32_t line0, int32_t nlines, int32_t band_first,
+                     int32_t block_bands);
 /* Input already on the device: pointer to element (line 0, band band_lo, sample 0); consecutive lines are
  * line_pitch floats apart, consecutive bands band_pitch floats apart (a full BIL cube: B*S and S). */
 int cmf_bind_device_slab(cmf_ctx* ctx, const float* dev_slab, int64_t line_pitch, int32_t band_pitch);

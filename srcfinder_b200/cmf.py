@@ -94,6 +94,36 @@ class ColumnwiseMF(object):
         self._keep = cube
         self._check(self._lib.cmf_upload_bil(self._ctx, C.c_void_p(cube.ctypes.data)))
 
+    def upload_stream(self, cube_lbs, block_lines=256):
+        """Upload a (L, B, S) float32 BIL cube that lives on disk (``numpy.memmap``) block by block: the active window
+        of the next ``block_lines`` lines is read into one of two pinned staging buffers while the previous block
+        is on the PCIe link, so disk and PCIe overlap.  Only the active window is read."""
+        if cube_lbs.shape != (self.L, self.B, self.S):
+            raise CmfError("cube shape %r != %r" % (cube_lbs.shape, (self.L, self.B, self.S)))
+        lo, hi = self.active
+        nb = int(max(1, min(block_lines, self.L)))
+        nbytes = nb * self.D * self.S * 4
+        ptrs = [self._lib.cmf_host_alloc(nbytes) for _ in range(2)]
+        if not all(ptrs):
+            for p in ptrs:
+                if p:
+                    self._lib.cmf_host_free(C.c_void_p(p))
+            raise CmfError("pinned staging buffers (%d bytes each) could not be allocated" % nbytes)
+        try:
+            views = [np.ctypeslib.as_array((C.c_float * (nb * self.D * self.S)).from_address(p)).reshape(nb, self.D, self.S)
+                     for p in ptrs]
+            for i, l0 in enumerate(range(0, self.L, nb)):
+                l1 = min(self.L, l0 + nb)
+                k = i % 2
+                if i >= 2:
+                    self.sync()                      # the copy that last used this buffer has finished
+                np.copyto(views[k][:l1 - l0], cube_lbs[l0:l1, lo - 1:hi, :], casting="same_kind")
+                self._check(self._lib.cmf_upload_lines(self._ctx, C.c_void_p(ptrs[k]), l0, l1 - l0, lo, self.D))
+            self.sync()
+        finally:
+            for p in ptrs:
+                self._lib.cmf_host_free(C.c_void_p(p))
+
     def bind_device(self, dev_ptr, line_pitch=None, band_pitch=None):
         """Device-resident slab: pointer to (line 0, band active[0], sample 0)."""
         lp = self.D * self.S if line_pitch is None else int(line_pitch)

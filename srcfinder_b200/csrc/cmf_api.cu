@@ -566,6 +566,27 @@ int cmf_upload_bil(cmf_ctx* ctx, const float* host_cube) {
     return CMF_OK;
 }
 
+int cmf_upload_lines(cmf_ctx* ctx, const float* host_block, int32_t line0, int32_t nlines, int32_t band_first,
+                     int32_t block_bands) {
+    if (!ctx || !host_block) return CMF_E_ARG;
+    if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_upload_lines before cmf_set_problem");
+    const Dims& d0 = ctx->d;
+    if (line0 < 0 || nlines <= 0 || line0 + nlines > d0.L) return fail(ctx, CMF_E_ARG, "line block outside the cube");
+    if (band_first < 1 || band_first > ctx->band_lo || band_first + block_bands - 1 < ctx->band_hi)
+        return fail(ctx, CMF_E_ARG, "the block does not hold the active window");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_own_slab(ctx);
+    if (rc) return rc;
+    const Dims& d = ctx->d;
+    const size_t width = (size_t)d.D * d.S * sizeof(float);
+    const float* src = host_block + (size_t)(ctx->band_lo - band_first) * d.S;
+    CK(cudaMemcpy2DAsync(ctx->slab_own + (size_t)line0 * d.D * d.S, width, src,
+                         (size_t)block_bands * d.S * sizeof(float), width, (size_t)nlines, cudaMemcpyHostToDevice,
+                         ctx->stream));
+    ctx->have_input = true;     // the caller is responsible for handing in every line before cmf_run()
+    return CMF_OK;
+}
+
 int cmf_bind_device_slab(cmf_ctx* ctx, const float* dev_slab, int64_t line_pitch, int32_t band_pitch) {
     if (!ctx || !dev_slab) return CMF_E_ARG;
     if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_bind_device_slab before cmf_set_problem");

@@ -135,11 +135,14 @@ def run(args, log=print):
 
     log("starting columnwise processing (%d columns)" % S)
     t0 = time.time()
-    cube = np.ascontiguousarray(img, dtype=np.float32) if img.dtype != np.float32 or not img.flags.c_contiguous \
-        else img
+    streamed = img.dtype == np.float32 and not args.exclude
+    cube = None if streamed else np.ascontiguousarray(img, dtype=np.float32)
     with ColumnwiseMF(L, B, S, active, abscf, model=args.model, reflectance=args.reflectance,
                       alphas=alpha_grid(), nodata=nodata, device=args.device) as eng:
-        eng.upload(cube)
+        if streamed:
+            eng.upload_stream(img)       # disk -> pinned blocks -> device, active window only (:298)
+        else:
+            eng.upload(cube)
         if args.exclude:
             if args.kmeans > 1:
                 raise CmfError("--exclude applies to unimodal runs only")

@@ -18,6 +18,9 @@ TOL_SIGMA = 1e-3        # the contract
 TIGHT_SIGMA = 1e-7      # what the FP64 path delivers
 
 
+ACTIVE = [351, 422]
+
+
 def _abscf(active):
     return synth.load_ch4_library()[active[0] - 1:active[1], 2]
 
@@ -283,6 +286,27 @@ def test_async_host_calls_on_two_contexts():
     for (mf, ai), (gmf, gai) in zip(want, outs):
         assert np.array_equal(gmf.numpy(), mf, equal_nan=True)
         assert np.array_equal(gai.numpy(), ai)
+
+
+def test_streamed_upload_from_a_memmap(tmp_path):
+    """upload_stream(): a cube on disk goes through two pinned staging blocks (active window only, ragged last
+    block) and must give bitwise the results of the one-shot upload."""
+    L, S = 333, 10
+    cube = synth.make_cube(L, S, seed=81, bad_pixels=True)
+    path = str(tmp_path / "cube.bil")
+    cube.tofile(path)
+    mm = np.memmap(path, dtype=np.float32, mode="r", shape=cube.shape)
+    ab = _abscf(ACTIVE)
+    with ColumnwiseMF(L, 425, S, ACTIVE, ab) as eng:
+        eng.upload(cube)
+        eng.run()
+        want = eng.results()
+    with ColumnwiseMF(L, 425, S, ACTIVE, ab) as eng:
+        eng.upload_stream(mm, block_lines=64)
+        eng.run()
+        got = eng.results()
+    for key in ("mf", "mask", "alpha_index", "colstd", "colavg", "colnum"):
+        assert np.array_equal(got[key], want[key], equal_nan=True), key
 
 
 def test_no_read_of_unwritten_work_memory():
