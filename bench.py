@@ -351,7 +351,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     kt = eng.kernel_times()                       # mean per-kernel ms over the timed steps (same stream)
-    launches = eng.launch_count() * args.steps + (args.steps if world > 1 else 0)
+    launches = eng.launch_count() * args.steps        # this library's kernels only (per rank); NCCL / torch copies not counted
     value = world * L * S * args.steps / (ms * 1e-3) / 1e6
 
     # ---- end to end through the host API (rank-local; every rank does the same work)
