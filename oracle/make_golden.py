@@ -60,6 +60,12 @@ CASES = [
          flags=["-k", "3", "-r", "-f", "-m"], lib="ang_ch4_unit.txt", np_seed=9, bright_lines=(300, 340)),
     dict(name="modes_k2f_500x3", L=500, S=3, seed=24, kw={}, flags=["-k", "2", "-f", "-m"],
          lib="ang_ch4_unit.txt", np_seed=11),
+    # -R with the CH4 library: active window [5, 420] = 416 bands (:186-187), target = abscf - mu, no ppm
+    # scaling (:379, :383).  At this width det(G) under/overflows for most alphas (:111-113), which the
+    # wide-window kernel set has to reproduce.  Slow in the reference (~1 min per column).
+    dict(name="reflectance_700x2", L=700, S=2, seed=31, kw={}, flags=["-R", "-m"], lib="ang_ch4_unit.txt"),
+    dict(name="reflectance_1500x3", L=1500, S=3, seed=32, kw=dict(bad_pixels=True), flags=["-R", "-m"],
+         lib="ang_ch4_unit.txt"),
 ]
 
 

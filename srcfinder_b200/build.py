@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libcmf_b200.so")
-SOURCES = ["k_stream.cu", "k_gram.cu", "k_eigen.cu", "k_loo.cu", "k_screen.cu", "k_screen5.cu", "k_modes.cu", "k_cluster.cu", "k_products.cu", "cmf_api.cu", "microbench.cu"]
+SOURCES = ["k_stream.cu", "k_gram.cu", "k_eigen.cu", "k_loo.cu", "k_screen.cu", "k_screen5.cu", "k_wide.cu", "k_gram8.cu", "k_modes.cu", "k_cluster.cu", "k_products.cu", "cmf_api.cu", "microbench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -94,6 +94,16 @@ struct cmf_ctx {
     // opt-in exclusion of pixels from the background statistics (cmf_set_exclusion): 1 = pixel takes part
     bool have_excl = false;
     uint8_t* excl_sel = nullptr;
+    // wide-window kernel set (k_wide.cu, k_gram8.cu): windows wider than 8 * kMaxNT bands (-R, robust_mf.py:186-187)
+    bool wide = false, use_gram8 = false;
+    int APW = 0, zbatch = 1, wsplit = 1, wlps = 1;
+    float *lo_part = nullptr, *hi_part = nullptr;
+    int* qexp = nullptr;
+    int8_t* img = nullptr;
+    double *wgram = nullptr, *wwork = nullptr, *wdinv = nullptr, *wdvec = nullptr, *wevec = nullptr, *Wtab = nullptr,
+           *Zbuf = nullptr;
+    double2* rot = nullptr;
+    int2* iters = nullptr;
 };
 
 namespace {
@@ -205,6 +215,55 @@ void fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* sel, const int* nloo
     ctx->screened = screen;
 }
 
+// The same for a wide active window (unimodal): every step is blocked, the per-column matrices live in global memory.
+// exact = true takes the FP64 tensor (DMMA) Gram pass instead of the integer tcgen05 pass (cross-check).
+template <class Mark>
+void wide_fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* excl, Mark mark) {
+    const Dims& d = ctx->d;
+    cudaStream_t st = ctx->stream;
+    const bool g8 = ctx->use_gram8 && !exact;
+    launch_wide_stats(d, ctx->slab, ctx->mask, excl, 1, ctx->wsplit, ctx->wlps, ctx->colsum_part, ctx->colcnt_part,
+                      ctx->lo_part, ctx->hi_part, ctx->mu, ctx->n, ctx->ctr, ctx->qexp, st);
+    launch_wide_pack(d, ctx->slab, ctx->mask, excl, ctx->ctr, ctx->qexp, ctx->xt, g8 ? ctx->img : nullptr, st);
+    mark(1);
+    mark(2);
+    if (g8) launch_wide_gram8(d, ctx->img, ctx->wgram, st);
+    else launch_wide_gram64(d, ctx->xt, ctx->ctr, ctx->wgram, st);
+    mark(3);
+    launch_wide_eigen(d, ctx->wgram, ctx->n, ctx->mu, ctx->ctr, g8 ? ctx->qexp : nullptr, 0, ctx->wwork, ctx->wdinv,
+                      ctx->wdvec, ctx->wevec, ctx->rot, ctx->iters, ctx->sweeps, ctx->P, ctx->lam, ctx->slogT,
+                      ctx->status, st);
+    mark(4);
+    ctx->launches += 10;
+    const bool loo = ctx->model == CMF_MODEL_LOOSHRINKAGE;
+    if (loo) {
+        launch_wide_tables(d, ctx->APW, ctx->n, nullptr, ctx->alphas_d, ctx->model, ctx->lam, ctx->slogT, ctx->logdet,
+                           ctx->beta, ctx->rsum, ctx->Wtab, st);
+        ++ctx->launches;
+    }
+    mark(5);
+    mark(6);
+    mark(7);
+    if (loo) {
+        for (int s0 = 0; s0 < d.S; s0 += ctx->zbatch) {
+            const int ns = std::min(ctx->zbatch, d.S - s0);
+            launch_wide_loo(d, ctx->APW, ctx->xt, ctx->mu, ctx->P, ctx->Wtab, ctx->beta, ctx->n, s0, ns, ctx->nchunk_loo,
+                            ctx->Zbuf, ctx->fpart, st);
+            ctx->launches += 2;
+        }
+    }
+    mark(8);
+    launch_finalize(d, ctx->fpart, ctx->nchunk_loo, ctx->logdet, ctx->n, ctx->alphas_d, ctx->P, ctx->lam, ctx->mu,
+                    ctx->abscf_d, ctx->model, ctx->reflectance, ctx->scale, ctx->nll, ctx->mindex, ctx->w, ctx->wT,
+                    ctx->c0, ctx->status, nullptr, nullptr, nullptr, st);
+    mark(9);
+    launch_score(d, ctx->slab, ctx->mask, ctx->wT, ctx->c0, ctx->status, ctx->nodata, ctx->mf, ctx->stat_part,
+                 ctx->nlanes, ctx->score_lpc, nullptr, ctx->mindex, ctx->alpha_img, st);
+    mark(10);
+    ctx->launches += 2;
+    ctx->screened = false;
+}
+
 // Launch the whole column loop on the context stream.  When `blocks_ready` is given, the first repack pass
 // runs block by block, each block waiting on the event that marks its upload as complete.
 int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t>* blocks_ready,
@@ -231,6 +290,22 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
     // ---- pass over every valid pixel: validity mask, column-major copy, column sums
     const bool chased = blocks_ready != nullptr && !modes;
     const uint8_t* excl = (!modes && ctx->have_excl) ? ctx->excl_sel : nullptr;
+    if (ctx->wide) {
+        if (blocks_ready) for (cudaEvent_t e : *blocks_ready) cudaStreamWaitEvent(st, e, 0);
+        wide_fit_and_score(ctx, exact, excl, mark);
+        if (excl) {
+            launch_count_mask(d, ctx->mask, ctx->nuse, st);
+            launch_colstats_modes(d, ctx->mf, ctx->mask, ctx->nuse, ctx->nodata, ctx->colstats, st);
+            ctx->launches += 2;
+        } else {
+            launch_colstats(d, ctx->stat_part, ctx->nlanes, ctx->n, ctx->nodata, ctx->colstats, st);
+            ++ctx->launches;
+        }
+        mark(11);
+        ctx->timed = timing;
+        CK(cudaGetLastError());
+        return CMF_OK;
+    }
     if (blocks_ready) {
         // one block = one Gram chunk: its repack and (unimodal) its Gram partial run as soon as its copy lands
         int line = 0;
@@ -439,8 +514,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     if (!p->abscf) return fail(ctx, CMF_E_ARG, "abscf is NULL");
     const int D = p->band_hi - p->band_lo + 1;
     const int NT = (D + 7) / 8;
-    if (NT > kMaxNT)
-        return fail(ctx, CMF_E_ARG, "active window wider than 96 bands is not supported by this build");
+    const bool wide = NT > kMaxNT;
     const bool loo = p->model == CMF_MODEL_LOOSHRINKAGE;
     if (!loo && p->model != CMF_MODEL_EMPIRICAL) return fail(ctx, CMF_E_ARG, "unknown model");
     if (loo && (p->num_alphas < 1 || p->num_alphas > 4096 || !p->alphas))
@@ -465,6 +539,24 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     ctx->reflectance = p->reflectance; ctx->model = p->model; ctx->nodata = p->nodata;
     ctx->scale = p->reflectance ? 1.0 : 1.0e5;   // ppmscaling, robust_mf.py:38,:383-386
 
+    ctx->wide = wide;
+    if (wide) {
+        if (!wide_eigen_fits(d)) return fail(ctx, CMF_E_ARG, "active window too wide for the eigen-solver's shared-memory plan");
+        ctx->wsplit = std::max(1, std::min(8, d.L / 256));
+        ctx->wlps = (d.L + ctx->wsplit - 1) / ctx->wsplit;
+        ctx->wsplit = (d.L + ctx->wlps - 1) / ctx->wlps;
+        ctx->nsplit = ctx->wsplit; ctx->lps = ctx->wlps; ctx->spc = 1; ctx->lpc_gram = d.L; ctx->nchunk_gram = 1;
+        ctx->APW = (d.AP + 63) / 64 * 64;
+        ctx->nchunk_loo = std::max(1, std::min(16, d.L / 1024));
+        ctx->nchunk_screen = 1;
+        ctx->can_screen = false; ctx->use_screen5 = false;
+        // the integer Gram accumulates 32-bit sums of products of balanced base-256 digits: fewer than 2^17 lines
+        ctx->use_gram8 = d.L < (1 << 17);
+        if (const char* e = getenv("CMF_WIDE_GRAM")) if (strcmp(e, "fp64") == 0) ctx->use_gram8 = false;
+        const size_t zcol = (size_t)d.L * d.DP * sizeof(double);
+        ctx->zbatch = (int)std::max<size_t>(1, std::min<size_t>((size_t)d.S, ((size_t)4 << 30) / zcol));
+        ctx->nlanes = score_plan(d, ctx->sm_count, &ctx->score_lpc);
+    } else {
     ctx->nsplit = repack_nsplit(d);
     ctx->lps = repack_lines_per_split(d, ctx->nsplit);
     ctx->nsplit = (d.L + ctx->lps - 1) / ctx->lps;
@@ -484,6 +576,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     ctx->use_screen5 = ctx->can_screen && screen5_supported(d);
     if (const char* e = getenv("CMF_SCREEN_IMPL")) if (strcmp(e, "legacy") == 0) ctx->use_screen5 = false;
     if (const char* e = getenv("CMF_EIGEN")) ctx->eigen_method = (strcmp(e, "jacobi") == 0) ? 1 : 0;
+    }
 
     const size_t LS = (size_t)d.L * d.S;
     const int Sp = (d.S + 1) & ~1;
@@ -497,10 +590,29 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     A_(dalloc(ctx, &ctx->mu, (size_t)d.S * d.DP));
     A_(dalloc(ctx, &ctx->ctr, (size_t)d.S * d.DP));
     A_(dalloc(ctx, &ctx->n, (size_t)d.S));
-    A_(dalloc(ctx, &ctx->gram_part, gram_part_elems(d, ctx->nchunk_gram)));
     A_(dalloc(ctx, &ctx->P, (size_t)d.S * d.DP * d.DP));
-    A_(dalloc(ctx, &ctx->Pf, (size_t)d.S * frag * d.NT));
-    A_(dalloc(ctx, &ctx->Wf, (size_t)d.S * frag * d.NT2));
+    if (!wide) {
+        A_(dalloc(ctx, &ctx->gram_part, gram_part_elems(d, ctx->nchunk_gram)));
+        A_(dalloc(ctx, &ctx->Pf, (size_t)d.S * frag * d.NT));
+        A_(dalloc(ctx, &ctx->Wf, (size_t)d.S * frag * d.NT2));
+    } else {
+        const size_t SDD = (size_t)d.S * d.DP * d.DP;
+        A_(dalloc(ctx, &ctx->lo_part, (size_t)ctx->nsplit * d.S * d.DP));
+        A_(dalloc(ctx, &ctx->hi_part, (size_t)ctx->nsplit * d.S * d.DP));
+        A_(dalloc(ctx, &ctx->qexp, (size_t)d.S * d.DP));
+        if (ctx->use_gram8) A_(dalloc(ctx, &ctx->img, wide_img_bytes(d)));
+        A_(dalloc(ctx, &ctx->wgram, SDD));
+        A_(dalloc(ctx, &ctx->wwork, SDD));
+        A_(dalloc(ctx, &ctx->wdinv, (size_t)d.S * d.DP));
+        A_(dalloc(ctx, &ctx->wdvec, (size_t)d.S * d.DP));
+        A_(dalloc(ctx, &ctx->wevec, (size_t)d.S * d.DP));
+        A_(dalloc(ctx, &ctx->rot, (size_t)d.S * wide_rot_cap(d)));
+        A_(dalloc(ctx, &ctx->iters, (size_t)d.S * wide_iter_cap(d)));
+        if (loo) {
+            A_(dalloc(ctx, &ctx->Wtab, (size_t)d.S * d.DP * ctx->APW));
+            A_(dalloc(ctx, &ctx->Zbuf, (size_t)ctx->zbatch * d.L * d.DP));
+        }
+    }
     A_(dalloc(ctx, &ctx->lam, (size_t)d.S * d.DP));
     A_(dalloc(ctx, &ctx->logdet, (size_t)d.S * d.AP));
     A_(dalloc(ctx, &ctx->beta, (size_t)d.S * d.AP));
@@ -607,6 +719,7 @@ int cmf_set_labels(cmf_ctx* ctx, const int32_t* labels, int kmodes, int reject_m
     if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_set_labels before cmf_set_problem");
     CK(cudaSetDevice(ctx->device));
     if (labels == nullptr) { ctx->have_labels = false; ctx->auto_cluster = false; return CMF_OK; }
+    if (ctx->wide) return fail(ctx, CMF_E_ARG, "background modes are not supported for active windows wider than 96 bands");
     if (kmodes < 1 || kmodes > kMaxLabels) return fail(ctx, CMF_E_ARG, "kmodes must be 1..32");
     const Dims& d = ctx->d;
     const size_t LS = (size_t)d.L * d.S;
@@ -629,6 +742,7 @@ int cmf_set_clustering(cmf_ctx* ctx, int kmodes, int pcadim, int reject_min, int
     if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_set_clustering before cmf_set_problem");
     CK(cudaSetDevice(ctx->device));
     if (kmodes <= 1) { ctx->auto_cluster = false; ctx->have_labels = false; return CMF_OK; }
+    if (ctx->wide) return fail(ctx, CMF_E_ARG, "background modes are not supported for active windows wider than 96 bands");
     if (kmodes > kMaxLabels) return fail(ctx, CMF_E_ARG, "kmodes must be 1..32");
     const Dims& d = ctx->d;
     if (pcadim < 1 || pcadim > kMaxPcaDim || pcadim > d.D)
@@ -665,7 +779,7 @@ int cmf_set_regfull(cmf_ctx* ctx, int enable) {
     if (!ctx) return CMF_E_ARG;
     if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_set_regfull before cmf_set_problem");
     CK(cudaSetDevice(ctx->device));
-    if (enable) {
+    if (enable && !ctx->wide) {
         int rc = ensure_full_gram(ctx);
         if (rc) return rc;
     }

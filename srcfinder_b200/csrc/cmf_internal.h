@@ -13,6 +13,7 @@ constexpr int kScoreLines = 8;      // lines per thread in the scoring pass (sca
 constexpr int kMaxLabels = 32;      // background-mode labels are 0 .. kMaxLabels-1
 constexpr int kModeNone = 127;      // mode-list slot past the end of a column's list
 constexpr int kMaxPcaDim = 16;      // --pcadim upper bound of the on-device partition
+constexpr int kScoreTiledMaxD = 192; // the tiled scoring kernel keeps D x 64 weight pairs in shared memory
 
 // column status bits (per cross-track column)
 enum : int {
@@ -108,6 +109,33 @@ void launch_colstats_modes(const Dims& d, const double* mf, const uint8_t* inlie
 int score_plan(const Dims& d, int sm_count, int* lines_per_cta);
 void launch_colstats(const Dims& d, const double* stat_part, int nlanes, const int* n, double nodata,
                      double* colstats, cudaStream_t st);
+
+// ---- wide-window kernel set (k_wide.cu, k_gram8.cu): active windows wider than 8 * kMaxNT bands
+void launch_wide_stats(const Dims& d, const float* slab, uint8_t* mask, const uint8_t* sel, int write_mask,
+                       int nsplit, int lps, double* colsum_part, int* colcnt_part, float* lo_part, float* hi_part,
+                       double* mu, int* n, double* ctr, int* qexp, cudaStream_t st);
+void launch_wide_pack(const Dims& d, const float* slab, const uint8_t* mask, const uint8_t* sel, const double* ctr,
+                      const int* qexp, float* xt, int8_t* img, cudaStream_t st);
+void launch_wide_gram64(const Dims& d, const float* xt, const double* ctr, double* gram, cudaStream_t st);
+void launch_wide_gram64_f64(int L, int DP, int S, const double* x, const double* ctr, double* gram, cudaStream_t st);
+size_t wide_img_bytes(const Dims& d);
+void launch_wide_gram8(const Dims& d, const int8_t* img, double* gram, cudaStream_t st);
+size_t wide_rot_cap(const Dims& d);
+int wide_iter_cap(const Dims& d);
+bool wide_eigen_fits(const Dims& d);
+void launch_wide_eigen(const Dims& d, const double* gram, const int* n, const double* mu, const double* ctr,
+                       const int* qexp, int mode, double* work, double* dinv, double* dvec, double* evec,
+                       double2* rot, int2* iters, int* niter, double* P, double* lam, double* slogT, int* status,
+                       cudaStream_t st);
+void launch_wide_tables(const Dims& d, int APW, const int* n, const int* nloo, const double* alphas, int model,
+                        const double* lam, const double* slogT, double* logdet, double* beta, double* rsum, double* W,
+                        cudaStream_t st);
+void launch_wide_loo(const Dims& d, int APW, const float* xt, const double* mu, const double* P, const double* W,
+                     const double* beta, const int* n, int s0, int ns, int nchunk, double* Z, double* fpart,
+                     cudaStream_t st);
+void launch_wide_loo_f64(int L, int D, int DP, int AP, int APW, const double* x, const double* zero_mu,
+                         const double* P, const double* W, const double* beta, const int* n, double* Z,
+                         double* fpart, cudaStream_t st);
 
 size_t gram_part_elems(const Dims& d, int nchunk);
 int repack_nsplit(const Dims& d);

@@ -31,6 +31,7 @@
 
 #include "cmf_common.cuh"
 #include "cmf_internal.h"
+#include "cmf_tc5.cuh"
 
 namespace cmf {
 
@@ -39,89 +40,6 @@ namespace {
 constexpr int kT5Threads = 512;
 constexpr int kT5Stages = 3;       // 64-row half tiles in flight
 constexpr int kT5HalfRows = 64;
-
-// ------------------------------------------------------------------ tcgen05 primitives
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// mbarrier wait that traps instead of hanging the GPU when a protocol error leaves it unsignalled
-__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-#pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
-        uint32_t ok;
-        asm volatile(
-            "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (ok) return;
-    }
-    __trap();
-}
-
-// D[tmem] (+)= A[tmem] . B[smem]^T, kind::tf32, issued by one thread for the CTA
-__device__ __forceinline__ void mma_ts_tf32(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-// instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, TF32 x TF32, K-major A and B, M = 128
-__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
-}
-
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major, no swizzle: element (row, 16-byte
-// K chunk c) lives at start + (row % 8) * 16 + (row / 8) * SBO + c * LBO
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    const uint32_t lo = ((addr >> 4) & 0x3fffu) | (((lbo_bytes >> 4) & 0x3fffu) << 16);
-    const uint32_t hi = ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14);       // version 1 (Blackwell)
-    return ((uint64_t)hi << 32) | lo;
-}
-
-__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(addr));
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(addr));
-}
-
-__device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(v[0]),
-                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
-
-// FP32 -> TF32 on the integer pipe (cvt.rna.tf32.f32 issues on the 16-lane XU pipe and was the busiest
-// pipe of the first version): round-half-away on the 13 dropped bits for the hi part, truncation for the lo
-// part (its error is 2^-22 of the value).  Inputs are finite.
-__device__ __forceinline__ uint32_t tf32_round(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
-__device__ __forceinline__ uint32_t tf32_trunc(float x) { return __float_as_uint(x) & 0xffffe000u; }
 
 // The epilogue sums g = h + u per alpha, where h = log(1-u) + r u/(1-u) and u = beta r (log q + r/q = r + h):
 //     g = sum_{k>=2} u^k (1/beta - 1/k)

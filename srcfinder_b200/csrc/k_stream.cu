@@ -822,7 +822,7 @@ static ScoreVariant score_variant() {
 }
 
 int score_plan(const Dims& d, int sm_count, int* lines_per_cta) {
-    if (d.vec2) {
+    if (d.vec2 && d.D <= kScoreTiledMaxD) {
         const ScoreVariant v = score_variant();
         const int ntiles = (d.S + kScoreTile - 1) / kScoreTile;
         const int step = kScoreSlots * v.nl;
@@ -861,7 +861,7 @@ void launch_score(const Dims& d, const float* slab, const uint8_t* mask, const d
                   int lines_per_cta, const uint8_t* sel, const int* mindex, int16_t* alpha_img,
                   cudaStream_t st) {
     const int Sp = (d.S + 1) & ~1;
-    if (d.vec2) {
+    if (d.vec2 && d.D <= kScoreTiledMaxD) {
         const ScoreVariant v = score_variant();
 #define CMF_SV(NL, BC, MB)                                                                              \
     if (v.nl == NL && v.bc == BC && v.minb == MB)                                                       \
@@ -871,6 +871,13 @@ void launch_score(const Dims& d, const float* slab, const uint8_t* mask, const d
 #undef CMF_SV
         return launch_score_tiled<2, 18, 2>(d, slab, mask, wT, c0, status, nodata, mf, stat_part, nlanes,
                                             lines_per_cta, sel, mindex, alpha_img, st);
+    }
+    if (d.vec2) {      // wide windows: weights from global memory / L1, column pairs
+        const long long total = (long long)((d.S + 1) / 2) * nlanes;
+        score_kernel<2><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, mask, wT, Sp, c0, status, nodata, mf, stat_part,
+            nlanes, sel, mindex, alpha_img);
+        return;
     }
     const long long total = (long long)d.S * nlanes;
     score_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(

@@ -215,9 +215,9 @@ def test_empirical_and_co2_window():
 
 
 def test_reflectance_target():
-    """-R (cmf/robust_mf.py:379, :383-384): target = abscf - mu and no ppm scaling.  The reference pairs -R with the
-    416-band window [5, 420] (:187), wider than this build's 96-band limit, so the formula is
-    checked on the CH4 and CO2 windows; the wide window itself must fail loudly, never fall back."""
+    """-R (cmf/robust_mf.py:379, :383-384): target = abscf - mu and no ppm scaling, on the narrow windows (the
+    416-band window the reference pairs with -R, :187, is covered by tests/test_gpu_wide.py and the
+    reflectance_* goldens)."""
     cube = synth.make_cube(500, 5, seed=43, bad_pixels=True)
     for active, model in (([351, 422], "looshrinkage"), ([309, 391], "empirical")):
         ab = _abscf(active)
@@ -225,9 +225,6 @@ def test_reflectance_target():
         got = cmf_cube(cube, ab, active, model=model, reflectance=True)
         aidx = ref["alpha_index"] if model == "looshrinkage" else None
         _check_against(got, ref["mf"], ref["mask"], aidx, ref["colstd"])
-    from srcfinder_b200 import CmfError
-    with pytest.raises(CmfError, match="wider than 96 bands"):
-        ColumnwiseMF(16, 425, 4, [5, 420], np.zeros(416), reflectance=True)
 
 
 def test_device_resident_full_cube_and_run_host():
@@ -341,8 +338,10 @@ def test_error_paths():
         ColumnwiseMF(16, 425, 4, [351, 422], ab, nodata=5.0)          # nodata > 0 (:233-234)
     with pytest.raises(CmfError):
         ColumnwiseMF(16, 425, 4, [351, 430], np.zeros(80))            # window outside the cube
+    wide = ColumnwiseMF(16, 425, 4, [5, 420], np.zeros(416))          # -R window: the wide-window kernel set
     with pytest.raises(CmfError):
-        ColumnwiseMF(16, 425, 4, [5, 420], np.zeros(416))             # wider than this build supports
+        wide.set_clustering(3)                                        # background modes: narrow windows only
+    wide.close()
     eng = ColumnwiseMF(16, 425, 4, [351, 422], ab)
     with pytest.raises(CmfError):
         eng.run()                                                     # no input bound yet
