@@ -164,6 +164,18 @@ int cmf_download(cmf_ctx* ctx, int what, void* host_dst, size_t bytes);   /* syn
 void* cmf_device_ptr(cmf_ctx* ctx, int what);                            /* NULL if not available */
 size_t cmf_output_bytes(const cmf_ctx* ctx, int what);
 
+/* Drop-in for the importable looshrinkage(I_zm, alphas, nll, n, I_reg=[]) -> (C, mindex) of the reference
+ * (cmf/robust_mf.py:92-136), for one sample matrix: I_zm is double [rows][D] row-major (mean-removed samples), n the
+ * sample count the caller passes (:355-356).  nll_out[A] receives the leave-one-out negative log likelihood of every
+ * alpha (inf where det(G) under/overflows, :111-113), mindex_out the argmin (-1 when every entry is inf, :121-127),
+ * C_out double [D][D] the shrunk covariance (1 - alpha) S + alpha diag(S) (:130-134).  Every alpha is evaluated in
+ * FP64 on the device (blocked kernels of csrc/k_wide.cu, any D up to 425+).  I_reg (the -f target, :100) must be
+ * NULL / reg_rows 0 here: -f is served by the column path (cmf_set_regfull).  Independent of cmf_set_problem.
+ * Synchronous. */
+int cmf_looshrinkage(cmf_ctx* ctx, const double* I_zm, int32_t rows, int32_t D, const double* alphas, int32_t A,
+                     int32_t n, const double* I_reg, int32_t reg_rows, double* nll_out, double* C_out,
+                     int32_t* mindex_out);
+
 /* ---- the steps either side of the filter ---- */
 
 /* Per-pixel spectrometer flags of a radiance cube: the per-pixel tests of spectrometer_masks/masks_sds.py
@@ -200,6 +212,28 @@ int cmf_column_profile(cmf_ctx* ctx, int robust, double p, double* out_host);
  * `nodata` the product's 'data ignore value'.  Independent of cmf_set_problem.  Synchronous. */
 int cmf_column_profile_image(cmf_ctx* ctx, const double* mf_host, int32_t lines, int32_t samples, double nodata,
                              int robust, double p, double* out_host);
+
+/* Detection pre-filter: the per-pixel head of srcfinder_util.filtdet (:1428-1436) with kde (:1383-1387) on a score
+ * image.  weights[2*radius+1] is the normalised, symmetric 1-D kernel the reference builds with
+ * scipy.ndimage.gaussian_filter(sigma = k = 50, truncate = 1) (radius = int(k + 0.5); srcfinder_b200/detect.py
+ * builds it with the same numpy expression); it is applied along the lines, then along the samples, with 'reflect'
+ * borders and scipy's summation order.  Then imgkde is scaled to [0, 1] by its min / max, detkde = mf * imgkde,
+ *   detkde_host  double [lines][samples]  clip((detkde - mfmin) / (mfmax - mfmin), 0, 1)    (mfmin, mfmax = 500, 1500)
+ *   ch4min_host  uint8  [lines][samples]  mf >= mfmin                                        (may be NULL)
+ *   detmask_host uint8  [lines][samples]  detkde > 0, the candidate mask                      (may be NULL)
+ * The connected-component filtering that follows in the reference (:1437-1470) is image morphology and stays with
+ * the caller.  mf_host == NULL takes the scores of the last run, which are already on the device (lines / samples
+ * ignored).  Synchronous. */
+int cmf_detection_prefilter(cmf_ctx* ctx, const double* mf_host, int32_t lines, int32_t samples,
+                            const double* weights, int32_t radius, double mfmin, double mfmax, double* detkde_host,
+                            uint8_t* ch4min_host, uint8_t* detmask_host);
+
+/* CNN input normalisation (cnn/cnn_pred_pipeline.py:19-30, 126-157): ClampCH4(vmin, vmax) followed by
+ * transforms.Normalize(mean, std) in float32: out = (clamp((float)mf, vmin, vmax) - mean) / std; no-data pixels are
+ * clamped like every other value, as in the reference.  out_host: float [lines][samples].  mf_host == NULL takes the
+ * scores of the last run.  Synchronous. */
+int cmf_cnn_input(cmf_ctx* ctx, const double* mf_host, int32_t lines, int32_t samples, float vmin, float vmax,
+                  float mean, float stdv, float* out_host);
 
 /* ---- instrumentation ---- */
 int cmf_kernel_count(void);

@@ -132,8 +132,28 @@ def run_case(case, tmp):
         np.isfinite(rec["stdout_avg"]).sum()))
 
 
+def looshrinkage_cases():
+    """The reference's importable looshrinkage(I_zm, alphas, nll, n, I_reg=[]) (:92-136), called directly."""
+    ref = ref_shim.import_reference_functions()
+    alphas = 10.0 ** np.arange(-10, 0.05, 0.05)
+    for name, L, seed, window, n_extra in (("looshrinkage_600x72", 600, 41, (351, 422), 0),
+                                           ("looshrinkage_250x83", 250, 42, (309, 391), 37),
+                                           ("looshrinkage_900x160", 900, 43, (200, 359), 0)):
+        cube = synth.make_cube(L, 1, seed=seed)
+        x = np.float64(cube[:, window[0] - 1:window[1], 0])
+        izm = x - x.mean(axis=0)
+        nll = np.zeros(len(alphas))
+        n = L + n_extra                      # the reference passes the column count for a cluster subset (:355-356)
+        C, mindex = ref.looshrinkage(izm, alphas, nll, n)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), I_zm=izm, alphas=alphas, n=n, nll=nll, C=C,
+                            mindex=mindex)
+        print("%-22s mindex %d  finite nll %d" % (name, mindex, np.isfinite(nll).sum()))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    if sys.argv[1:] == ["looshrinkage"]:
+        return looshrinkage_cases()
     lib = np.loadtxt(REF_LIB)
     np.save(os.path.join(ROOT, "srcfinder_b200", "data", "ch4_unit_425.npy"), lib)
     only = sys.argv[1:]

@@ -1,14 +1,17 @@
-"""TEST INFRASTRUCTURE ONLY (never imported by srcfinder_b200/): CPU restatement of the two steps either side of
+"""TEST INFRASTRUCTURE ONLY (never imported by srcfinder_b200/): CPU restatement of the steps either side of
 the matched filter that SURVEY.md 8(f) ranks next.
 
-* ``pixel_flags``  -- the per-pixel tests of spectrometer_masks/masks_sds.py: get_saturation_mask (:133-150),
-  get_spec_mask (:152-163), get_dark_mask (:165-180), get_cloud_mask (:182-230), same numpy expressions on a
-  (lines, samples, bands) view.  The reference script cannot be imported (it parses sys.argv and opens files at
-  import time, and needs spectral/skimage), so this part is "parity unpinned": it restates the expressions line
-  for line.
-* ``column_profile`` -- triage/cmf_profile.py:110-140, the same numpy calls (float32 image, nanmean / nanstd /
-  nanmin / nanmax or nanmedian / nearest-rank nanpercentile); ``extrema`` is srcfinder_util.py:647-658.  numpy
-  itself is the arithmetic, so the oracle is the reference's computation on this container's numpy 2.3.
+Pinning: the reference modules cannot be imported (argv parsing / file I/O at import time, GDAL, rasterio), so
+``oracle/make_product_golden.py`` cuts the functions named below out of the reference sources with ``ast`` and
+executes their UNMODIFIED text on seeded inputs; ``tests/golden/{flags,profile,filtdet,cnnnorm}_*.npz`` hold those
+outputs and ``tests/test_products_oracle.py`` checks every restatement here against them.
+
+* ``pixel_flags``  -- spectrometer_masks/masks_sds.py: get_saturation_mask (:133-150), get_spec_mask (:152-163),
+  get_dark_mask (:165-180), get_cloud_mask (:182-230), same numpy expressions on a (lines, samples, bands) view.
+* ``column_profile`` -- triage/cmf_profile.py:110-133, the same numpy calls (float32 image, nanmean / nanstd /
+  nanmin / nanmax or nanmedian / nearest-rank nanpercentile); ``extrema`` is srcfinder_util.py:647-658.
+* ``detection_prefilter`` -- srcfinder_util.py: kde (:1383-1387) and the head of filtdet (:1428-1436).
+* ``cnn_input`` -- cnn/cnn_pred_pipeline.py: ClampCH4 (:19-30) + transforms.Normalize (:126-157), float32.
 """
 import warnings
 
@@ -80,3 +83,22 @@ def column_profile(mf_ls, nodata=-9999, use_robust_stats=False):
             colmax = np.nanmax(cmf, axis=0)
             names = ("npix", "avg", "std", "min", "max")
     return dict(zip(names, (colnum, colavg, colstd, colmin, colmax)))
+
+
+def detection_prefilter(ch4mf, k=50, mfmin=500, mfmax=1500):
+    """srcfinder_util.py:1383-1387 (kde) and :1428-1436 (filtdet head): (detkde, ch4min, detmask)."""
+    from scipy.ndimage import gaussian_filter
+    detkde = ch4mf.copy()
+    ch4min = ch4mf >= mfmin
+    imgkde = gaussian_filter(detkde, sigma=k, truncate=1)
+    imgkde = (imgkde - imgkde.min()) / (imgkde.max() - imgkde.min())
+    detkde = detkde * imgkde
+    detkde = np.clip((detkde - mfmin) / (mfmax - mfmin), 0.0, 1.0)
+    return detkde, ch4min, detkde > 0
+
+
+def cnn_input(ch4mf, vmin=0, vmax=4000, mean=110.6390, std=183.9152):
+    """cnn/cnn_pred_pipeline.py:19-30, 126-157 in float32 (torch.clamp, then sub / div as torchvision does)."""
+    x = np.float32(ch4mf)
+    c = np.where(np.isnan(x), x, np.minimum(np.maximum(x, np.float32(vmin)), np.float32(vmax)))
+    return (c - np.float32(mean)) / np.float32(std)

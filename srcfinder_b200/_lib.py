@@ -16,6 +16,7 @@ SYMBOLS = [
     "cmf_device_ptr", "cmf_output_bytes", "cmf_kernel_count", "cmf_kernel_name", "cmf_kernel_times",
     "cmf_launch_count", "cmf_screen_kernel", "cmf_host_alloc", "cmf_host_free", "cmf_host_register", "cmf_host_unregister",
     "cmf_microbench", "cmf_pixel_flags", "cmf_column_profile", "cmf_column_profile_image",
+    "cmf_detection_prefilter", "cmf_cnn_input", "cmf_looshrinkage",
 ]
 
 OUT_MF, OUT_MASK, OUT_COLSTATS, OUT_ALPHA_INDEX, OUT_NLL, OUT_MU, OUT_WEIGHTS, OUT_STATUS, OUT_NVALID, \
@@ -92,6 +93,9 @@ def load():
         "cmf_pixel_flags": (C.c_int, [vp, vp, C.c_int, i32, i32, i32, C.POINTER(FlagSpec), vp]),
         "cmf_column_profile": (C.c_int, [vp, C.c_int, C.c_double, vp]),
         "cmf_column_profile_image": (C.c_int, [vp, vp, i32, i32, C.c_double, C.c_int, C.c_double, vp]),
+        "cmf_detection_prefilter": (C.c_int, [vp, vp, i32, i32, vp, i32, C.c_double, C.c_double, vp, vp, vp]),
+        "cmf_looshrinkage": (C.c_int, [vp, vp, i32, i32, vp, i32, i32, vp, i32, vp, vp, vp]),
+        "cmf_cnn_input": (C.c_int, [vp, vp, i32, i32, C.c_float, C.c_float, C.c_float, C.c_float, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

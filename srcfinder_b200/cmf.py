@@ -326,3 +326,36 @@ def cmf_cube(cube_lbs, abscf, active, model="looshrinkage", reflectance=False, a
         if model == "looshrinkage":
             res["nll"] = eng.nll()
         return res
+
+
+_LOO_CTX = {}
+
+
+def looshrinkage(I_zm, alphas, nll, n, I_reg=[], device=0):
+    """Drop-in for the reference's importable ``looshrinkage(I_zm, alphas, nll, n, I_reg=[])``
+    (cmf/robust_mf.py:92-136): fills ``nll`` in place and returns ``(C, mindex)``.  Every alpha is evaluated in FP64
+    on the GPU (``cmf_looshrinkage``); ``I_reg`` (the ``-f`` target) is served by the column path
+    (``ColumnwiseMF.set_regfull``) and raises here."""
+    lib = _lib.load()
+    if len(I_reg) != 0:
+        raise CmfError("looshrinkage: I_reg is handled by ColumnwiseMF.set_regfull (the column path), not by this entry")
+    ctx = _LOO_CTX.get(int(device))
+    if ctx is None:
+        ctx = C.c_void_p()
+        rc = lib.cmf_create(C.byref(ctx), int(device))
+        if rc != 0:
+            raise CmfError("cmf_create failed (%d): %s" % (rc, lib.cmf_last_error(None).decode()))
+        _LOO_CTX[int(device)] = ctx
+    x = np.ascontiguousarray(I_zm, dtype=np.float64)
+    al = np.ascontiguousarray(alphas, dtype=np.float64)
+    rows, D = x.shape
+    if nll.dtype != np.float64 or not nll.flags.c_contiguous or nll.shape != al.shape:
+        raise CmfError("nll must be a contiguous float64 array of the same length as alphas")
+    Cm = np.empty((D, D), dtype=np.float64)
+    mi = C.c_int32(0)
+    rc = lib.cmf_looshrinkage(ctx, C.c_void_p(x.ctypes.data), rows, D, C.c_void_p(al.ctypes.data), len(al), int(n),
+                              C.c_void_p(None), 0, C.c_void_p(nll.ctypes.data), C.c_void_p(Cm.ctypes.data),
+                              C.byref(mi))
+    if rc != 0:
+        raise CmfError("cmf_looshrinkage failed (%d): %s" % (rc, lib.cmf_last_error(ctx).decode()))
+    return Cm, int(mi.value)

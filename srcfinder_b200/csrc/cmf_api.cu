@@ -1004,6 +1004,156 @@ int cmf_column_profile_image(cmf_ctx* ctx, const double* mf_host, int32_t lines,
     return rc;
 }
 
+
+// ---- detection pre-filter and CNN input ----
+int cmf_detection_prefilter(cmf_ctx* ctx, const double* mf_host, int32_t lines, int32_t samples,
+                            const double* weights, int32_t radius, double mfmin, double mfmax, double* detkde_host,
+                            uint8_t* ch4min_host, uint8_t* detmask_host) {
+    if (!ctx || !weights || !detkde_host) return CMF_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const double* src = nullptr;
+    int L = lines, S = samples;
+    if (mf_host == nullptr) {            // the scores of the last run, already on the device
+        if (!ctx->have_problem || !ctx->mf) return fail(ctx, CMF_E_STATE, "cmf_detection_prefilter: no scores on the device");
+        L = ctx->d.L; S = ctx->d.S; src = ctx->mf;
+    }
+    if (L <= 0 || S <= 0 || radius < 0 || radius > 4096) return fail(ctx, CMF_E_ARG, "bad image shape or filter radius");
+    if (!(mfmax > mfmin)) return fail(ctx, CMF_E_ARG, "mfmax must exceed mfmin");
+    const size_t n = (size_t)L * S;
+    const int nparts = 296;
+    void* blk = nullptr;
+    // one allocation: [image (host input only)] tmp, blur, detkde, partials, weights, the two byte masks
+    const size_t dbl = (mf_host ? n : 0) + 3 * n + 3 * nparts + (size_t)(2 * radius + 1);
+    if (cudaMalloc(&blk, dbl * sizeof(double) + 2 * n) != cudaSuccess) { cudaGetLastError(); return fail(ctx, CMF_E_NOMEM, "pre-filter scratch allocation failed"); }
+    double* p = reinterpret_cast<double*>(blk);
+    double* img = nullptr;
+    if (mf_host) { img = p; p += n; }
+    double *tmp = p, *blur = p + n, *det = p + 2 * n, *part = p + 3 * n, *wd = part + 3 * nparts;
+    uint8_t* m1 = reinterpret_cast<uint8_t*>(wd + (2 * radius + 1));
+    uint8_t* m2 = m1 + n;
+    cudaError_t e = cudaMemcpyAsync(wd, weights, (size_t)(2 * radius + 1) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && mf_host) {
+        e = cudaMemcpyAsync(img, mf_host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        src = img;
+    }
+    if (e == cudaSuccess) {
+        launch_detection_prefilter(src, L, S, radius, wd, mfmin, mfmax, tmp, blur, part, det, m1, m2, ctx->stream);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(detkde_host, det, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && ch4min_host) e = cudaMemcpyAsync(ch4min_host, m1, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && detmask_host) e = cudaMemcpyAsync(detmask_host, m2, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(blk);
+    if (e != cudaSuccess) return fail(ctx, CMF_E_CUDA, std::string("cmf_detection_prefilter: ") + cudaGetErrorString(e));
+    return CMF_OK;
+}
+
+int cmf_cnn_input(cmf_ctx* ctx, const double* mf_host, int32_t lines, int32_t samples, float vmin, float vmax,
+                  float mean, float stdv, float* out_host) {
+    if (!ctx || !out_host) return CMF_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const double* src = nullptr;
+    int L = lines, S = samples;
+    if (mf_host == nullptr) {
+        if (!ctx->have_problem || !ctx->mf) return fail(ctx, CMF_E_STATE, "cmf_cnn_input: no scores on the device");
+        L = ctx->d.L; S = ctx->d.S; src = ctx->mf;
+    }
+    if (L <= 0 || S <= 0) return fail(ctx, CMF_E_ARG, "bad image shape");
+    if (!(vmax > vmin)) return fail(ctx, CMF_E_ARG, "vmax must exceed vmin (ClampCH4)");
+    const size_t n = (size_t)L * S;
+    const size_t out_bytes = (n * sizeof(float) + 15) & ~(size_t)15;
+    void* blk = nullptr;
+    if (cudaMalloc(&blk, out_bytes + (mf_host ? n * sizeof(double) : 0)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, CMF_E_NOMEM, "CNN input scratch allocation failed");
+    }
+    float* out = reinterpret_cast<float*>(blk);
+    cudaError_t e = cudaSuccess;
+    if (mf_host) {
+        double* img = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(blk) + out_bytes);
+        e = cudaMemcpyAsync(img, mf_host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        src = img;
+    }
+    if (e == cudaSuccess) {
+        launch_cnn_input(src, nullptr, (long long)n, vmin, vmax, mean, stdv, out, ctx->stream);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(blk);
+    if (e != cudaSuccess) return fail(ctx, CMF_E_CUDA, std::string("cmf_cnn_input: ") + cudaGetErrorString(e));
+    return CMF_OK;
+}
+
+// ---- the importable looshrinkage(I_zm, alphas, nll, n, I_reg = []) of the reference (cmf/robust_mf.py:92-136) ----
+int cmf_looshrinkage(cmf_ctx* ctx, const double* I_zm, int32_t rows, int32_t D, const double* alphas, int32_t A,
+                     int32_t n, const double* I_reg, int32_t reg_rows, double* nll_out, double* C_out,
+                     int32_t* mindex_out) {
+    if (!ctx || !I_zm || !alphas || !nll_out || !C_out || !mindex_out) return CMF_E_ARG;
+    if (rows < 1 || D < 1 || D > 1024 || A < 1 || A > 4096) return fail(ctx, CMF_E_ARG, "cmf_looshrinkage: bad shape");
+    if (I_reg != nullptr && reg_rows > 0)
+        return fail(ctx, CMF_E_ARG, "cmf_looshrinkage: I_reg (the -f target) is served by the column path "
+                                    "(cmf_set_regfull), not by the one-column entry");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    Dims d{};
+    d.L = rows; d.S = 1; d.D = D; d.NT = (D + 7) / 8; d.DP = 8 * d.NT;
+    d.A = A; d.NT2 = (A + 7) / 8; d.AP = d.NT2 * 8; d.NT16 = (A + 15) / 16; d.AP16 = d.NT16 * 16;
+    if (!wide_eigen_fits(d)) return fail(ctx, CMF_E_ARG, "cmf_looshrinkage: too many bands for the eigen-solver");
+    const int DP = d.DP, APW = (d.AP + 63) / 64 * 64;
+    const size_t DD = (size_t)DP * DP;
+    // one scratch block; doubles first
+    size_t nd = (size_t)rows * DP /*x*/ + (size_t)rows * DP /*Z*/ + 3 * DD /*gram, work, P*/ + 8 * (size_t)DP + 5 * (size_t)d.AP +
+                (size_t)DP * APW /*W*/ + (size_t)A /*alphas*/ + (size_t)A /*nll*/ + (size_t)D * D /*C*/ + 3 * (size_t)DP /*w, wT*/ + 8;
+    const size_t rot_cap = wide_rot_cap(d);
+    const int iter_cap = wide_iter_cap(d);
+    const size_t bytes = nd * sizeof(double) + rot_cap * sizeof(double2) + (size_t)iter_cap * sizeof(int2) + 16 * sizeof(int);
+    void* blk = nullptr;
+    if (cudaMalloc(&blk, bytes) != cudaSuccess) { cudaGetLastError(); return fail(ctx, CMF_E_NOMEM, "cmf_looshrinkage: scratch allocation failed"); }
+    cudaError_t e = cudaMemsetAsync(blk, 0, bytes, st);
+    double* p = reinterpret_cast<double*>(blk);
+    auto take = [&](size_t k) { double* q = p; p += k; return q; };
+    double *x = take((size_t)rows * DP), *Z = take((size_t)rows * DP), *gram = take(DD), *work = take(DD), *P = take(DD);
+    double *mean = take(DP), *zero = take(DP), *dinv = take(DP), *dvec = take(DP), *evec = take(DP), *lam = take(DP),
+           *abscf = take(DP), *mu0 = take(DP);
+    double *logdet = take(d.AP), *beta = take(d.AP), *rsum = take(d.AP), *fpart = take(d.AP), *spare = take(d.AP);
+    double *W = take((size_t)DP * APW), *al_d = take(A), *nll_d = take(A), *C_d = take((size_t)D * D), *w = take(DP),
+           *wT = take(2 * (size_t)DP), *slogT = take(1), *c0 = take(3);
+    (void)spare; (void)zero;
+    if (reinterpret_cast<uintptr_t>(p) & 15) ++p;                       // double2 alignment
+    double2* rot = reinterpret_cast<double2*>(p);
+    int2* iters = reinterpret_cast<int2*>(rot + rot_cap);
+    int* ints = reinterpret_cast<int*>(iters + iter_cap);
+    int *n_rows = ints, *n_loo = ints + 1, *status = ints + 2, *niter = ints + 3, *mindex = ints + 4;
+    const int hv[2] = {rows, n};
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(x, (size_t)DP * sizeof(double), I_zm, (size_t)D * sizeof(double),
+                                                (size_t)D * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(al_d, alphas, (size_t)A * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ints, hv, sizeof(hv), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        launch_wide_mean64(x, rows, D, DP, mean, st);                       // numpy.cov re-centres (:68)
+        launch_wide_gram64_f64(rows, DP, 1, x, mean, gram, st);             // sum (x - mean)(x - mean)^T
+        // S = G / (m - 1), T = diag(S); the x100 stability scaling enters log det only (:94-99)
+        launch_wide_eigen(d, gram, n_rows, mean, mean, nullptr, 0, work, dinv, dvec, evec, rot, iters, niter, P, lam,
+                          slogT, status, st);
+        launch_wide_tables(d, APW, n_rows, n_loo, al_d, 0, lam, slogT, logdet, beta, rsum, W, st);
+        // r_k = x_k^T G^-1 x_k uses the samples as given, not re-centred (:114)
+        launch_wide_loo_f64(rows, D, DP, d.AP, APW, x, mu0, P, W, beta, n_rows, Z, fpart, st);
+        launch_finalize(d, fpart, 1, logdet, n_rows, al_d, P, lam, mu0, abscf, 0, 1, 1.0, nll_d, mindex, w, wT, c0, status,
+                        nullptr, nullptr, n_loo, st);
+        launch_wide_cmat(gram, rows, D, DP, mindex, al_d, C_d, st);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nll_out, nll_d, (size_t)A * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(C_out, C_d, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mindex_out, mindex, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(blk);
+    if (e != cudaSuccess) return fail(ctx, CMF_E_CUDA, std::string("cmf_looshrinkage: ") + cudaGetErrorString(e));
+    return CMF_OK;
+}
+
 int cmf_kernel_count(void) { return K_COUNT; }
 const char* cmf_kernel_name(int i) { return (i >= 0 && i < K_COUNT) ? kKernelNames[i] : ""; }
 

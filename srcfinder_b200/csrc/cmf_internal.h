@@ -50,6 +50,13 @@ void launch_pixel_flags(const float* cube, long long line_pitch, int band_pitch,
 void launch_column_profile(const double* mf, int L, int S, double nodata, int robust, double qlo, double qhi,
                            float* colv, double* out, cudaStream_t st);
 
+// detection pre-filter (srcfinder_util.py:1383-1387, 1428-1436) and CNN input normalisation (cnn_pred_pipeline.py:19-30)
+void launch_detection_prefilter(const double* mf, int L, int S, int radius, const double* w_dev, double mfmin,
+                                double mfmax, double* tmp, double* blur, double* part, double* detkde,
+                                uint8_t* ch4min, uint8_t* detmask, cudaStream_t st);
+void launch_cnn_input(const double* mf64, const float* mf32, long long n, float vmin, float vmax, float mean,
+                      float stdv, float* out, cudaStream_t st);
+
 inline int ntri(int nt) { return nt * (nt + 1) / 2; }
 
 void launch_repack(const Dims& d, const float* slab, float* xt, uint8_t* mask, double* colsum_part,
@@ -136,6 +143,10 @@ void launch_wide_loo(const Dims& d, int APW, const float* xt, const double* mu, 
 void launch_wide_loo_f64(int L, int D, int DP, int AP, int APW, const double* x, const double* zero_mu,
                          const double* P, const double* W, const double* beta, const int* n, double* Z,
                          double* fpart, cudaStream_t st);
+
+void launch_wide_mean64(const double* x, int rows, int D, int DP, double* mean, cudaStream_t st);
+void launch_wide_cmat(const double* gram, int m, int D, int DP, const int* mindex, const double* alphas, double* C,
+                      cudaStream_t st);
 
 size_t gram_part_elems(const Dims& d, int nchunk);
 int repack_nsplit(const Dims& d);

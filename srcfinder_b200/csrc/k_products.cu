@@ -266,4 +266,120 @@ void launch_column_profile(const double* mf, int L, int S, double nodata, int ro
     else profile_plain_kernel<<<S, 256, 0, st>>>(colv, L, S, out);
 }
 
+
+// ---------------------------------------------------------------------------------------- detection pre-filter
+// The per-pixel head of filtdet (srcfinder_util.py:1428-1436) with kde (:1383-1387):
+//     imgkde = gaussian_filter(mf, sigma = k, truncate = 1)        separable, radius int(k + 0.5), 'reflect' borders,
+//                                                                   axis 0 (lines) first, then axis 1 (samples)
+//     imgkde = (imgkde - min) / (max - min);  detkde = mf * imgkde
+//     detkde = clip((detkde - mfmin) / (mfmax - mfmin), 0, 1);  ch4min = mf >= mfmin;  detmask = detkde > 0
+// Same FP64 evaluation order as scipy's correlate1d for a symmetric filter (centre tap first, then the pairs from
+// the outermost inwards, no fused multiply-add), so the result equals the reference's to the last bit when the
+// C library is compiled without contraction.  The connected-component steps that follow (:1437-1470) are image
+// morphology and not part of this call.
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    // scipy 'reflect' (d c b a | a b c d | d c b a): period 2n
+    const int p = 2 * n;
+    int m = i % p;
+    if (m < 0) m += p;
+    return m < n ? m : p - 1 - m;
+}
+
+__global__ void __launch_bounds__(256)
+    kde_blur_kernel(const double* __restrict__ in, int L, int S, int axis, int radius, const double* __restrict__ w,
+                    double* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)L * S) return;
+    const int l = (int)(idx / S), s = (int)(idx % S);
+    const int n = axis == 0 ? L : S, pos = axis == 0 ? l : s;
+    const long long stride = axis == 0 ? S : 1;
+    const double* line = in + (axis == 0 ? (long long)s : (long long)l * S);
+    double acc = __dmul_rn(line[(long long)pos * stride], w[radius]);
+    const bool interior = pos - radius >= 0 && pos + radius < n;
+    for (int jj = -radius; jj < 0; ++jj) {
+        const int a = interior ? pos + jj : reflect_index(pos + jj, n);
+        const int b = interior ? pos - jj : reflect_index(pos - jj, n);
+        const double pair = __dadd_rn(line[(long long)a * stride], line[(long long)b * stride]);
+        acc = __dadd_rn(acc, __dmul_rn(pair, w[radius + jj]));
+    }
+    out[idx] = acc;
+}
+
+// block partials of min / max with numpy's NaN propagation (any NaN -> NaN)
+__global__ void __launch_bounds__(256)
+    kde_minmax_kernel(const double* __restrict__ v, long long n, double* __restrict__ part) {
+    __shared__ double smin[8], smax[8];
+    __shared__ int snan[8];
+    double lo = __longlong_as_double(0x7ff0000000000000LL), hi = -lo;
+    int nan = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double x = v[i];
+        if (x != x) nan = 1;
+        lo = fmin(lo, x); hi = fmax(hi, x);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+    }
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; snan[threadIdx.x >> 5] = nan; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) { lo = fmin(lo, smin[i]); hi = fmax(hi, smax[i]); nan |= snan[i]; }
+        lo = fmin(lo, smin[0]); hi = fmax(hi, smax[0]); nan |= snan[0];
+        part[3 * blockIdx.x] = lo; part[3 * blockIdx.x + 1] = hi; part[3 * blockIdx.x + 2] = nan ? 1.0 : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    kde_finish_kernel(const double* __restrict__ mf, const double* __restrict__ blur, long long n,
+                      const double* __restrict__ part, int nparts, double mfmin, double mfmax,
+                      double* __restrict__ detkde, uint8_t* __restrict__ ch4min, uint8_t* __restrict__ detmask) {
+    double lo = part[0], hi = part[1];
+    bool nan = part[2] != 0.0;
+    for (int i = 1; i < nparts; ++i) { lo = fmin(lo, part[3 * i]); hi = fmax(hi, part[3 * i + 1]); nan = nan || part[3 * i + 2] != 0.0; }
+    if (nan) { lo = __longlong_as_double(0x7ff8000000000000LL); hi = lo; }
+    const double range = __dsub_rn(hi, lo), den = __dsub_rn(mfmax, mfmin);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double x = mf[i];
+        const double k01 = __ddiv_rn(__dsub_rn(blur[i], lo), range);
+        double d = __ddiv_rn(__dsub_rn(__dmul_rn(x, k01), mfmin), den);
+        d = (d != d) ? d : fmin(fmax(d, 0.0), 1.0);          // np.clip keeps NaN
+        detkde[i] = d;
+        if (ch4min) ch4min[i] = x >= mfmin ? 1 : 0;
+        if (detmask) detmask[i] = d > 0.0 ? 1 : 0;
+    }
+}
+
+void launch_detection_prefilter(const double* mf, int L, int S, int radius, const double* w_dev, double mfmin,
+                                double mfmax, double* tmp, double* blur, double* part, double* detkde,
+                                uint8_t* ch4min, uint8_t* detmask, cudaStream_t st) {
+    const long long n = (long long)L * S;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    kde_blur_kernel<<<blocks, 256, 0, st>>>(mf, L, S, 0, radius, w_dev, tmp);
+    kde_blur_kernel<<<blocks, 256, 0, st>>>(tmp, L, S, 1, radius, w_dev, blur);
+    const int nparts = 296;
+    kde_minmax_kernel<<<nparts, 256, 0, st>>>(blur, n, part);
+    kde_finish_kernel<<<1184, 256, 0, st>>>(mf, blur, n, part, nparts, mfmin, mfmax, detkde, ch4min, detmask);
+}
+
+// ---------------------------------------------------------------------------------------- CNN input
+// cnn/cnn_pred_pipeline.py:19-30, 126-157: ClampCH4(vmin, vmax) then transforms.Normalize(mean, std) on the float32
+// score image (torch.clamp, then (x - mean) / std in float32; no-data pixels are clamped like any other value).
+__global__ void __launch_bounds__(256)
+    cnn_input_kernel(const double* __restrict__ mf64, const float* __restrict__ mf32, long long n, float vmin,
+                     float vmax, float mean, float stdv, float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float x = mf32 ? mf32[i] : (float)mf64[i];
+        float c = x;
+        if (x == x) c = fminf(fmaxf(x, vmin), vmax);          // torch.clamp propagates NaN
+        out[i] = __fdiv_rn(__fsub_rn(c, mean), stdv);
+    }
+}
+
+void launch_cnn_input(const double* mf64, const float* mf32, long long n, float vmin, float vmax, float mean,
+                      float stdv, float* out, cudaStream_t st) {
+    cnn_input_kernel<<<1184, 256, 0, st>>>(mf64, mf32, n, vmin, vmax, mean, stdv, out);
+}
+
 }  // namespace cmf

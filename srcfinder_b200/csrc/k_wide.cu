@@ -997,4 +997,40 @@ void launch_wide_loo_f64(int L, int D, int DP, int AP, int APW, const double* x,
     wide_loo_kernel<<<g2, 128, 0, st>>>(Z, W, beta, n, L, D, DP, AP, APW, 0, lpc, 1, fpart);
 }
 
+
+// ---------------------------------------------------------------------------------------- one-column helpers
+// (cmf_looshrinkage: the importable looshrinkage(I_zm, alphas, nll, n, I_reg) of the reference, :92-136)
+// column means of an FP64 sample matrix [rows][DP] (numpy.cov re-centres its input, :68): thread <-> band, rows in order
+__global__ void __launch_bounds__(128) wide_mean64_kernel(const double* __restrict__ x, int rows, int D, int DP,
+                                                          double* __restrict__ mean) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= DP) return;
+    double a = 0.0;
+    if (b < D) for (int r = 0; r < rows; ++r) a += x[(long long)r * DP + b];
+    mean[b] = (b < D && rows > 0) ? a / (double)rows : 0.0;
+}
+
+// C = (1 - alpha) S + alpha T, S = cov = G / (m - 1), T = diag(diag(S))  (:130-134); alpha = 0 when mindex = -1
+__global__ void __launch_bounds__(256) wide_cmat_kernel(const double* __restrict__ gram, int m, int D, int DP,
+                                                        const int* __restrict__ mindex, const double* __restrict__ alphas,
+                                                        double* __restrict__ C) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= D * D) return;
+    const int r = idx / D, c = idx % D;
+    const int mi = mindex[0];
+    const double al = mi >= 0 ? alphas[mi] : 0.0;
+    const double inv = 1.0 / (double)(m - 1);
+    const double sv = gram[(long long)max(r, c) * DP + min(r, c)] * inv;
+    const double tv = (r == c) ? sv : 0.0;
+    C[idx] = (1.0 - al) * sv + al * tv;
+}
+
+void launch_wide_mean64(const double* x, int rows, int D, int DP, double* mean, cudaStream_t st) {
+    wide_mean64_kernel<<<(DP + 127) / 128, 128, 0, st>>>(x, rows, D, DP, mean);
+}
+void launch_wide_cmat(const double* gram, int m, int D, int DP, const int* mindex, const double* alphas, double* C,
+                      cudaStream_t st) {
+    wide_cmat_kernel<<<(D * D + 255) / 256, 256, 0, st>>>(gram, m, D, DP, mindex, alphas, C);
+}
+
 }  // namespace cmf

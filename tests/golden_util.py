@@ -8,8 +8,14 @@ import numpy as np
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+# fixtures of other steps (oracle/make_product_golden.py, make_golden.py looshrinkage) live beside the CLI runs
+_OTHER = ("flags_", "profile_", "filtdet_", "cnnnorm_", "looshrinkage_")
+
+
 def case_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    """Golden runs of the reference CLI (oracle/make_golden.py CASES)."""
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    return [n for n in names if not n.startswith(_OTHER)]
 
 
 def load_case(name):

@@ -165,3 +165,72 @@ def test_exclusion_from_background_statistics():
         assert got["colnum"][c] == len(use)
         assert got["colavg"][c] == pytest.approx(np.mean(want), abs=1e-6 * sd)
         assert got["colstd"][c] == pytest.approx(sd, rel=1e-8)
+
+
+# ---- against the reference's own functions, executed by oracle/make_product_golden.py (tests/golden/*.npz) ----
+import glob
+import os
+
+from tests.test_products_oracle import GOLDEN, load_flag_case
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "flags_*.npz"))))
+def test_pixel_flags_against_reference_fixture(path):
+    """masks_sds.py:133-233 executed unmodified -> fixture; the CUDA flags must equal it bit for bit."""
+    cube, wave, want, _ = load_flag_case(path)
+    assert np.array_equal(masks.pixel_flags(cube, wave), want)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "profile_*.npz"))))
+def test_column_profile_against_reference_fixture(path):
+    """triage/cmf_profile.py:110-133 + srcfinder_util.extrema executed unmodified -> fixture (float32, bit-exact)."""
+    z = np.load(path)
+    for robust, tag in ((False, "plain"), (True, "robust")):
+        got = cmf_profile.column_profile_image(z["mf"], nodata=-9999.0, robust=robust)
+        names = ("npix", "med", "mad", "p05", "p95") if robust else ("npix", "avg", "std", "min", "max")
+        for key, name in zip(("colnum", "colavg", "colstd", "colmin", "colmax"), names):
+            want = np.asarray(z["%s_%s" % (tag, key)], dtype=np.float64)
+            assert np.array_equal(np.asarray(got[name], dtype=np.float64), want, equal_nan=True), (tag, key)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "filtdet_*.npz"))))
+def test_detection_prefilter_against_reference_fixture(path):
+    """srcfinder_util.kde + the head of filtdet executed unmodified -> fixture.  Same summation order as scipy's
+    correlate1d without fused multiply-adds: masks identical, detkde to 1e-12 (it is bit-identical unless the
+    host C library contracted an operation)."""
+    from srcfinder_b200 import detect
+    z = np.load(path)
+    det, cmin, dmask = detect.filtdet_prefilter(z["mf"], k=int(z["k"]), mfmin=int(z["mfmin"]), mfmax=int(z["mfmax"]))
+    assert np.array_equal(cmin, z["ch4min"])
+    assert np.array_equal(dmask, z["detmask"])
+    assert np.max(np.abs(det - z["detkde"])) <= 1e-12
+    assert np.mean(det == z["detkde"]) > 0.99
+
+
+def test_cnn_input_against_reference_fixture():
+    """ClampCH4 + transforms.Normalize executed from cnn/cnn_pred_pipeline.py -> fixture, float32 bit-exact."""
+    from srcfinder_b200 import detect
+    z = np.load(os.path.join(GOLDEN, "cnnnorm_70x33.npz"))
+    for name in z["names"]:
+        got = detect.cnn_input(np.float64(z["x"]), model=str(name))
+        assert got.dtype == np.float32
+        assert np.array_equal(got, z["out_" + str(name)])
+
+
+def test_prefilter_and_cnn_input_from_device_scores():
+    """Both steps can read the scores where the filter left them (no host round trip): same result as via the host."""
+    from srcfinder_b200 import detect
+    cube = synth.make_cube(300, 40, seed=27)
+    ab = synth.load_ch4_library()[ACTIVE[0] - 1:ACTIVE[1], 2]
+    L, B, S = cube.shape
+    with ColumnwiseMF(L, B, S, ACTIVE, ab) as eng:
+        eng.upload(cube)
+        eng.run()
+        mf = eng.mf()
+        a = detect.filtdet_prefilter(None, engine=eng)
+        x = detect.cnn_input(None, engine=eng)
+    b = detect.filtdet_prefilter(mf)
+    assert all(np.array_equal(p, q) for p, q in zip(a, b))
+    assert np.array_equal(x, detect.cnn_input(mf))
+    ref = po.detection_prefilter(mf)
+    assert np.array_equal(a[2], ref[2]) and np.max(np.abs(a[0] - ref[0])) <= 1e-12

@@ -93,3 +93,28 @@ def test_wide_window_determinism_and_run_host():
     assert np.array_equal(a["mf"], b["mf"], equal_nan=True)
     assert np.array_equal(a["mf"], mf, equal_nan=True)
     assert np.array_equal(a["alpha_index"], ai)
+
+
+# ---- the importable looshrinkage() of the reference (cmf/robust_mf.py:92-136) ----
+import glob
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "looshrinkage_*.npz"))))
+def test_looshrinkage_drop_in(path):
+    """srcfinder_b200.looshrinkage(I_zm, alphas, nll, n) against the reference function's own output (fixture made
+    by oracle/make_golden.py looshrinkage): same (C, mindex), nll filled in place."""
+    from srcfinder_b200 import looshrinkage
+    z = np.load(path)
+    nll = np.zeros(len(z["alphas"]))
+    C, mindex = looshrinkage(z["I_zm"], z["alphas"], nll, int(z["n"]))
+    assert mindex == int(z["mindex"])
+    assert np.array_equal(np.isfinite(nll), np.isfinite(z["nll"]))
+    fin = np.isfinite(z["nll"])
+    assert np.max(np.abs(nll[fin] - z["nll"][fin])) <= 1e-8 * np.max(np.abs(z["nll"][fin]))
+    assert np.max(np.abs(C - z["C"])) <= 1e-12 * np.max(np.abs(z["C"]))
+    assert np.array_equal(C, C.T)
+    with pytest.raises(Exception):
+        looshrinkage(z["I_zm"], z["alphas"], nll, int(z["n"]), I_reg=z["I_zm"])

@@ -69,3 +69,68 @@ def test_profile_cli_parser_matches_reference_flags():
     assert a.robust and a.outdir == "x" and a.cmffiles == ["a_cmf", "b_cmf"] and a.jobs == 4
     assert cmf_profile.PLAIN_COLS == ["npix", "avg", "std", "min", "max"]
     assert cmf_profile.ROBUST_COLS == ["npix", "med", "mad", "p05", "p95"]
+
+
+# ---- the restatements against the reference's own code, executed by oracle/make_product_golden.py ----
+import glob
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _fixtures(prefix):
+    return sorted(glob.glob(os.path.join(GOLDEN, prefix + "_*.npz")))
+
+
+def load_flag_case(path):
+    z = np.load(path)
+    cube = np.zeros(tuple(int(v) for v in z["shape"]), dtype=np.float32)
+    cube[:, z["kept_bands"], :] = z["cube_kept"]
+    want = (z["saturated"] * po.SATURATED + z["specular"] * po.SPECULAR + z["dark"] * po.DARK +
+            z["cloud"] * po.CLOUD).astype(np.uint8)
+    return cube, z["wave"], want, z
+
+
+@pytest.mark.parametrize("path", _fixtures("flags"))
+def test_flags_restatement_matches_reference_functions(path):
+    cube, wave, want, z = load_flag_case(path)
+    assert float(z["sat_thresh"]) == 6.0 and float(z["spec_thresh"]) == 9.0 and float(z["dark_thresh"]) == 0.104
+    assert want.any() and len(np.unique(want)) >= 5
+    assert np.array_equal(po.pixel_flags(cube, wave), want)
+
+
+@pytest.mark.parametrize("path", _fixtures("profile"))
+def test_profile_restatement_matches_reference_statements(path):
+    z = np.load(path)
+    for robust, tag in ((False, "plain"), (True, "robust")):
+        r = po.column_profile(z["mf"], use_robust_stats=robust)
+        names = ("npix", "med", "mad", "p05", "p95") if robust else ("npix", "avg", "std", "min", "max")
+        for key, name in zip(("colnum", "colavg", "colstd", "colmin", "colmax"), names):
+            assert np.array_equal(r[name], z["%s_%s" % (tag, key)], equal_nan=True), (tag, key)
+
+
+@pytest.mark.parametrize("path", _fixtures("filtdet"))
+def test_prefilter_restatement_matches_reference_statements(path):
+    z = np.load(path)
+    det, cmin, dmask = po.detection_prefilter(z["mf"], k=int(z["k"]), mfmin=int(z["mfmin"]), mfmax=int(z["mfmax"]))
+    assert np.array_equal(det, z["detkde"]) and np.array_equal(cmin, z["ch4min"]) and np.array_equal(dmask, z["detmask"])
+    assert dmask.any() and not dmask.all()
+
+
+def test_cnn_input_restatement_matches_reference_transform():
+    from srcfinder_b200 import detect
+    z = np.load(os.path.join(GOLDEN, "cnnnorm_70x33.npz"))
+    assert sorted(str(n) for n in z["names"]) == sorted(detect.CNN_MODELS)
+    for name in z["names"]:
+        vmin, vmax, mean, std = z["par_" + str(name)]
+        assert tuple(detect.CNN_MODELS[str(name)]) == (vmin, vmax, mean, std)
+        assert np.array_equal(po.cnn_input(z["x"], vmin, vmax, mean, std), z["out_" + str(name)])
+
+
+def test_gaussian_weights_are_scipys():
+    from scipy.ndimage import correlate1d, gaussian_filter1d
+    from srcfinder_b200 import detect
+    w = detect.gaussian_weights(50)
+    assert len(w) == 101 and detect.KERNEL == 50 and (detect.MFMIN, detect.MFMAX) == (500, 1500)
+    x = np.random.default_rng(3).normal(size=400)
+    assert np.array_equal(correlate1d(x, w[::-1], mode="reflect"), gaussian_filter1d(x, 50, truncate=1))
