@@ -41,7 +41,8 @@ enum {
     CMF_COL_DEGENERATE = 2,   /* a single valid pixel: NaN scores, alpha index 0 (reference behaviour) */
     CMF_COL_SINGULAR = 4,     /* C not invertible: scores := 0 ("singular matrix", :371-374) */
     CMF_COL_NOCONVERGE = 8,   /* eigen-solver hit its sweep cap */
-    CMF_COL_ALLINF = 16       /* every nll inf: alpha := 0, index -1 (:123-127) */
+    CMF_COL_ALLINF = 16,      /* every nll inf: alpha := 0, index -1 (:123-127) */
+    CMF_COL_RECHECKED = 32    /* the screening certificate was not met: every alpha re-evaluated in FP64 */
 };
 
 /* What cmf_download()/cmf_device_ptr() can return.  Shapes use L lines, S samples, D active bands,
@@ -70,7 +71,11 @@ enum {
     CMF_OUT_LABELS = 16,      /* int32  [L][S]   cluster labels in use (given by cmf_set_labels or found by cmf_set_clustering) */
     CMF_OUT_PCA = 17,         /* double [S][L][pcadim] projections the on-device k-means partitioned (:311) */
     CMF_OUT_KMEANS_ITERS = 18,/* int32  [S]      reassignment passes the k-means needed */
-    CMF_OUT_FLAGS = 19        /* uint8  [lines][samples] of the last cmf_pixel_flags() call */
+    CMF_OUT_FLAGS = 19,       /* uint8  [lines][samples] of the last cmf_pixel_flags() call */
+    CMF_OUT_SCREEN_CHECK = 20 /* double [S]      screened runs: largest |exact - screened| nll over the alphas that were
+                                                  re-evaluated exactly, as a fraction of the margin (0 = column decided by
+                                                  the screen alone or fully exact); the run re-evaluates every alpha of a
+                                                  column in FP64 when this reaches 1/4, see cmf_set_screen_margin */
 };
 
 typedef struct cmf_problem {
@@ -141,6 +146,15 @@ int cmf_set_regfull(cmf_ctx* ctx, int enable);
  * CMF_OUT_COLSTATS covers every scored pixel; CMF_OUT_NVALID then holds the background count.  Unimodal runs
  * only (ignored while labels / clustering are set).  exclude == NULL returns to the default.  Host pointer. */
 int cmf_set_exclusion(cmf_ctx* ctx, const uint8_t* exclude);
+
+/* The alpha search is screened on the tensor cores and every alpha whose screened nll lies within
+ * rel_margin * max|screened part of nll| of the minimum is re-evaluated exactly (CMF_OUT_SCREEN_TOL holds the absolute
+ * margin per column).  Default 2e-5.  With certify != 0 (default) every run carries a runtime certificate: a refined
+ * column also gets its best EXCLUDED 8-alpha tile evaluated in FP64; if the exact minimum falls into that tile, or the
+ * measured |exact - screened| of the column reaches 1/4 of the margin, all alphas of the column are re-evaluated in
+ * FP64; and if the worst measurement of the flightline reaches 1/4, so are the columns the screen decided alone.
+ * certify = 0 or a smaller margin are for diagnostics (tests/test_gpu_parity.py drives both). */
+int cmf_set_screen_margin(cmf_ctx* ctx, double rel_margin, int certify);
 
 /* ---- compute: the whole column loop (:297-392) for every column, no host round trip ---- */
 enum {

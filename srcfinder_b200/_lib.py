@@ -16,18 +16,18 @@ SYMBOLS = [
     "cmf_device_ptr", "cmf_output_bytes", "cmf_kernel_count", "cmf_kernel_name", "cmf_kernel_times",
     "cmf_launch_count", "cmf_screen_kernel", "cmf_host_alloc", "cmf_host_free", "cmf_host_register", "cmf_host_unregister",
     "cmf_microbench", "cmf_pixel_flags", "cmf_column_profile", "cmf_column_profile_image",
-    "cmf_detection_prefilter", "cmf_cnn_input", "cmf_looshrinkage",
+    "cmf_detection_prefilter", "cmf_cnn_input", "cmf_looshrinkage", "cmf_set_screen_margin",
 ]
 
 OUT_MF, OUT_MASK, OUT_COLSTATS, OUT_ALPHA_INDEX, OUT_NLL, OUT_MU, OUT_WEIGHTS, OUT_STATUS, OUT_NVALID, \
     OUT_EIGVALS, OUT_SWEEPS, OUT_NCAND, OUT_SCREEN_TOL, OUT_CLUSTER_ID, OUT_ALPHA_IMAGE, OUT_MODE_LIST, OUT_LABELS, OUT_PCA, \
-    OUT_KMEANS_ITERS, OUT_FLAGS = range(20)
+    OUT_KMEANS_ITERS, OUT_FLAGS, OUT_SCREEN_CHECK = range(21)
 RUN_TIMING = 1
 RUN_EXACT = 2
 RUN_ASYNC = 4
 MODEL_LOOSHRINKAGE, MODEL_EMPIRICAL = 0, 1
 FLAG_SATURATED, FLAG_SPECULAR, FLAG_DARK, FLAG_CLOUD = 1, 2, 4, 8
-COL_EMPTY, COL_DEGENERATE, COL_SINGULAR, COL_NOCONVERGE, COL_ALLINF = 1, 2, 4, 8, 16
+COL_EMPTY, COL_DEGENERATE, COL_SINGULAR, COL_NOCONVERGE, COL_ALLINF, COL_RECHECKED = 1, 2, 4, 8, 16, 32
 
 
 class Problem(C.Structure):
@@ -74,6 +74,7 @@ def load():
         "cmf_set_clustering": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
         "cmf_set_regfull": (C.c_int, [vp, C.c_int]),
         "cmf_set_exclusion": (C.c_int, [vp, vp]),
+        "cmf_set_screen_margin": (C.c_int, [vp, C.c_double, C.c_int]),
         "cmf_run": (C.c_int, [vp, u32]),
         "cmf_sync": (C.c_int, [vp]),
         "cmf_run_host": (C.c_int, [vp, vp, vp, vp, vp, u32]),

@@ -56,8 +56,10 @@ struct cmf_ctx {
     bool use_screen5 = false;     // tcgen05/TMEM screening kernel (k_screen5.cu)
     double *rsum = nullptr, *fscreen = nullptr, *tol_col = nullptr, *slogT = nullptr;
     int eigen_method = 0;         // 0 Householder + QL, 1 cyclic Jacobi (CMF_EIGEN=jacobi, cross-checks)
-    int *sel_index = nullptr, *ncand = nullptr;
-    unsigned long long* tile_mask = nullptr;
+    int *sel_index = nullptr, *ncand = nullptr, *probe = nullptr;
+    unsigned long long *tile_mask = nullptr, *redo = nullptr;
+    double *check = nullptr, *check_worst = nullptr;   // runtime certificate of the screen (k_screen.cu, K4)
+    int certify = 1;
     // background modes (-k > 1, -r): labels are an input, everything derived from them lives on the device
     bool have_labels = false;
     int kmodes = 1, reject_min = 0;
@@ -193,7 +195,7 @@ void fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* sel, const int* nloo
     if (screen) {
         launch_select(d, ctx->fscreen, ctx->nchunk_screen, ctx->logdet, ctx->rsum, ctx->n, nloo, ctx->screen_tol,
                       ctx->nll, ctx->sel_index, ctx->tile_mask, ctx->ncand, ctx->tol_col,
-                      ctx->use_screen5 ? ctx->betaf : nullptr, st);
+                      ctx->use_screen5 ? ctx->betaf : nullptr, ctx->probe, st);
         ++ctx->launches;
     }
     mark(7);
@@ -206,7 +208,20 @@ void fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* sel, const int* nloo
     launch_finalize(d, ctx->fpart, ctx->nchunk_loo, ctx->logdet, ctx->n, ctx->alphas_d, ctx->P, ctx->lam,
                     ctx->mu, ctx->abscf_d, ctx->model, ctx->reflectance, ctx->scale, ctx->nll, ctx->mindex,
                     ctx->w, ctx->wT, ctx->c0, ctx->status, screen ? ctx->sel_index : nullptr,
-                    screen ? ctx->tile_mask : nullptr, nloo, st);
+                    screen ? ctx->tile_mask : nullptr, nloo, st, screen ? ctx->probe : nullptr,
+                    screen ? ctx->tol_col : nullptr, screen ? ctx->check : nullptr, screen ? ctx->redo : nullptr);
+    if (screen) {
+        // runtime certificate of the screen: columns whose measured screening error is not safely below the margin
+        // (or all screen-decided columns, if the flightline's worst measurement is not) are re-evaluated exactly;
+        // when nothing is flagged the two extra launches return at once
+        launch_certify(d, ctx->check, ctx->sel_index, ctx->certify, ctx->redo, ctx->check_worst, st);
+        launch_loo(d, ctx->xt, ctx->mu, ctx->Pf, ctx->Wf, ctx->beta, ctx->nchunk_loo, ctx->fpart, ctx->redo, st);
+        launch_finalize(d, ctx->fpart, ctx->nchunk_loo, ctx->logdet, ctx->n, ctx->alphas_d, ctx->P, ctx->lam,
+                        ctx->mu, ctx->abscf_d, ctx->model, ctx->reflectance, ctx->scale, ctx->nll, ctx->mindex,
+                        ctx->w, ctx->wT, ctx->c0, ctx->status, nullptr, nullptr, nloo, st, nullptr, nullptr, nullptr,
+                        nullptr, ctx->redo);
+        ctx->launches += 3;
+    }
     mark(9);
     launch_score(d, ctx->slab, ctx->mask, ctx->wT, ctx->c0, ctx->status, ctx->nodata, ctx->mf, ctx->stat_part,
                  ctx->nlanes, ctx->score_lpc, sel, ctx->mindex, ctx->alpha_img, st);
@@ -444,6 +459,7 @@ OutDesc out_desc(const cmf_ctx* c, int what) {
         case CMF_OUT_PCA: return {c->ypca, c->auto_cluster ? LS * c->pcadim * sizeof(double) : 0};
         case CMF_OUT_KMEANS_ITERS: return {c->km_iters, c->auto_cluster ? (size_t)d.S * sizeof(int) : 0};
         case CMF_OUT_FLAGS: return {c->flags_d, c->flags_bytes};
+        case CMF_OUT_SCREEN_CHECK: return {c->check, (size_t)d.S * sizeof(double)};
         default: return {nullptr, 0};
     }
 }
@@ -634,6 +650,10 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     A_(dalloc(ctx, &ctx->sel_index, (size_t)d.S));
     A_(dalloc(ctx, &ctx->ncand, (size_t)d.S));
     A_(dalloc(ctx, &ctx->tile_mask, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->redo, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->probe, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->check, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->check_worst, (size_t)1));
     A_(dalloc(ctx, &ctx->tol_col, (size_t)d.S));
     A_(dalloc(ctx, &ctx->slogT, (size_t)d.S));
     A_(dalloc(ctx, &ctx->nuse, (size_t)d.S));
@@ -801,6 +821,14 @@ int cmf_set_exclusion(cmf_ctx* ctx, const uint8_t* exclude) {
     launch_invert_u8(ctx->excl_sel, (long long)LS, ctx->stream);      // exclude != 0  ->  sel = 0
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_excl = true;
+    return CMF_OK;
+}
+
+int cmf_set_screen_margin(cmf_ctx* ctx, double rel_margin, int certify) {
+    if (!ctx) return CMF_E_ARG;
+    if (!(rel_margin > 0.0) || !(rel_margin < 1.0)) return fail(ctx, CMF_E_ARG, "screen margin must lie in (0, 1)");
+    ctx->screen_tol = rel_margin;
+    ctx->certify = certify ? 1 : 0;
     return CMF_OK;
 }
 

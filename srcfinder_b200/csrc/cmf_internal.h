@@ -22,7 +22,8 @@ enum : int {
     kStatusDegenerate = 2,   // n == 1: the reference produces NaN scores and alpha index 0
     kStatusSingular = 4,     // C not invertible: MF := 0 (cmf/robust_mf.py:371-374)
     kStatusNoConverge = 8,   // Jacobi hit the sweep cap (results still written)
-    kStatusAllInf = 16       // every nll was inf: alpha := 0, index -1 (cmf/robust_mf.py:123-127)
+    kStatusAllInf = 16,      // every nll was inf: alpha := 0, index -1 (cmf/robust_mf.py:123-127)
+    kStatusRechecked = 32    // the screening certificate failed: every alpha was re-evaluated in FP64
 };
 
 struct Dims {
@@ -91,12 +92,18 @@ double screen5_selftest(int N, int K, int row_off, int swap_lbo_sbo);
 void launch_select(const Dims& d, const double* fscreen, int nchunk, const double* logdet, const double* rsum,
                    const int* n, const int* nloo, double tol, double* nll, int* sel_index,
                    unsigned long long* tile_mask, int* ncand, double* tol_out, const float* betaf_fold,
-                   cudaStream_t st);
+                   int* probe, cudaStream_t st);
+// runtime certificate of the screened alpha search: measured screening error must stay below 1/kCertFactor of the margin
+constexpr double kCertFactor = 4.0;
+void launch_certify(const Dims& d, const double* check, const int* sel_index, int enabled, unsigned long long* redo,
+                    double* worst, cudaStream_t st);
 void launch_finalize(const Dims& d, const double* fpart, int nchunk, const double* logdet, const int* n,
                      const double* alphas, const double* P, const double* lam, const double* mu,
                      const double* abscf, int model, int reflectance, double scale, double* nll,
                      int* mindex, double* w, double* wT, double* c0, int* status, const int* sel_index,
-                     const unsigned long long* tile_mask, const int* nloo, cudaStream_t st);
+                     const unsigned long long* tile_mask, const int* nloo, cudaStream_t st,
+                     const int* probe = nullptr, const double* tol_col = nullptr, double* check = nullptr,
+                     unsigned long long* redo = nullptr, const unsigned long long* only = nullptr);
 void launch_score(const Dims& d, const float* slab, const uint8_t* mask, const double* wT, const double* c0,
                   const int* status, double nodata, double* mf, double* stat_part, int nlanes,
                   int lines_per_cta, const uint8_t* sel, const int* mindex, int16_t* alpha_img, cudaStream_t st);

@@ -814,7 +814,9 @@ __global__ void __launch_bounds__(256)
                     int reflectance, double scale, double* __restrict__ nll_g, int* __restrict__ mindex_g,
                     double* __restrict__ w_g, double* __restrict__ wT_g, double* __restrict__ c0_g,
                     int* __restrict__ status_g, const int* __restrict__ sel_index,
-                    const unsigned long long* __restrict__ tile_mask, const int* __restrict__ nloo_g) {
+                    const unsigned long long* __restrict__ tile_mask, const int* __restrict__ nloo_g,
+                    const int* __restrict__ probe_g, const double* __restrict__ tol_g, double* __restrict__ check_g,
+                    unsigned long long* __restrict__ redo_g, const unsigned long long* __restrict__ only_g) {
     extern __shared__ double sm[];
     double* nll = sm;           // [AP]
     double* tvec = nll + AP;    // [DP]
@@ -826,6 +828,10 @@ __global__ void __launch_bounds__(256)
     const int s = blockIdx.x, tid = threadIdx.x;
     const int n = n_g[s];
     const int Sp = (S + 1) & ~1;
+    // second pass of the screening certificate: only the columns that are re-evaluated exactly
+    if (only_g != nullptr && only_g[s] == 0ull) return;
+    __shared__ double err_sh[8];
+    if (tid == 0 && check_g) { check_g[s] = 0.0; redo_g[s] = 0ull; }   // overwritten below for a refined column
     // background-mode pass without members in this column (or past the end of its mode list): the column
     // keeps what earlier passes produced; the scoring pass has no member to write either
     if (nloo_g != nullptr && n == 0) return;
@@ -854,6 +860,7 @@ __global__ void __launch_bounds__(256)
         const int sel = screened ? sel_index[s] : -2;
         const unsigned long long tmask = screened ? tile_mask[s] : ~0ull;
         const double const_term = (double)D * log(2.0 * M_PI);
+        double emax = 0.0;          // largest |exact - screened| over the alphas evaluated exactly (certificate)
         for (int i = tid; i < A; i += blockDim.x) {
             double v;
             if (!screened || ((tmask >> ((i >> 3) & 63)) & 1ull)) {
@@ -862,11 +869,19 @@ __global__ void __launch_bounds__(256)
                 const double ld = det_roundtrip(logdet_g[(long long)s * AP + i]);
                 if (!(fabs(ld) < inf)) v = inf;   // det underflows to 0 -> alpha skipped; overflows -> log(inf) (:112-113)
                 else v = 0.5 * (const_term + ld) + fs / (2.0 * nl);
+                if (screened && check_g) {
+                    const double old = nll_g[(long long)s * A + i];
+                    if (fabs(v) < inf && fabs(old) < inf) emax = fmax(emax, fabs(v - old));
+                }
                 nll_g[(long long)s * A + i] = v;
             } else {
                 v = nll_g[(long long)s * A + i];
             }
             nll[i] = v;
+        }
+        if (check_g) {
+            for (int o = 16; o > 0; o >>= 1) emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+            if ((tid & 31) == 0) err_sh[tid >> 5] = emax;
         }
         __syncthreads();
         if (tid == 0) {
@@ -891,6 +906,25 @@ __global__ void __launch_bounds__(256)
             }
             mindex_g[s] = best;
             alpha_sel = al;
+            if (check_g) {
+                // Runtime certificate, part 2: this column is trusted if the exact minimum does not sit in the probe
+                // tile (the best tile the screen had EXCLUDED) and the measured screening error is below
+                // 1/kCertFactor of the margin; otherwise every alpha of the column is re-evaluated in FP64.
+                double e = 0.0;
+                for (int w8 = 0; w8 < (int)(blockDim.x >> 5); ++w8) e = fmax(e, err_sh[w8]);
+                double frac = 0.0;
+                unsigned long long redo = 0ull;
+                if (screened && sel == -2 && tmask != ~0ull) {
+                    const double margin = tol_g[s];
+                    frac = margin > 0.0 ? e / margin : 0.0;
+                    const int probe = probe_g ? probe_g[s] : -1;
+                    if (frac * kCertFactor > 1.0 || (best >= 0 && probe >= 0 && (best >> 3) == probe)) redo = ~0ull;
+                }
+                check_g[s] = frac;
+                redo_g[s] = redo;
+            } else if (only_g != nullptr) {
+                status_g[s] |= kStatusRechecked;
+            }
         }
     } else {
         if (tid == 0) { mindex_g[s] = -2; alpha_sel = 0.0; }
@@ -1007,11 +1041,12 @@ void launch_finalize(const Dims& d, const double* fpart, int nchunk, const doubl
                      const double* alphas, const double* P, const double* lam, const double* mu,
                      const double* abscf, int model, int reflectance, double scale, double* nll, int* mindex,
                      double* w, double* wT, double* c0, int* status, const int* sel_index,
-                     const unsigned long long* tile_mask, const int* nloo, cudaStream_t st) {
+                     const unsigned long long* tile_mask, const int* nloo, cudaStream_t st, const int* probe,
+                     const double* tol_col, double* check, unsigned long long* redo, const unsigned long long* only) {
     const size_t smem = (size_t)(d.AP + 3 * d.DP) * sizeof(double);
     finalize_kernel<<<d.S, 256, smem, st>>>(fpart, nchunk, logdet, n, alphas, d.A, d.AP, d.D, d.DP, d.S, P,
                                             lam, mu, abscf, model, reflectance, scale, nll, mindex, w, wT, c0,
-                                            status, sel_index, tile_mask, nloo);
+                                            status, sel_index, tile_mask, nloo, probe, tol_col, check, redo, only);
 }
 
 }  // namespace cmf

@@ -322,13 +322,13 @@ __global__ void __launch_bounds__(128)
                   const int* __restrict__ nloo_g, int A, int AP, int AP16,
                   int D, int S, double tol, double* __restrict__ nll_g, int* __restrict__ sel_index,
                   unsigned long long* __restrict__ tile_mask, int* __restrict__ ncand_g,
-                  double* __restrict__ tol_g, const float* __restrict__ betaf_fold) {
+                  double* __restrict__ tol_g, const float* __restrict__ betaf_fold, int* __restrict__ probe_g) {
     const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (s >= S) return;
     const int n = n_g[s];
     if (n < 2) {                               // K4 writes the degenerate results
-        if (lane == 0) { sel_index[s] = -3; tile_mask[s] = 0ull; ncand_g[s] = 0; tol_g[s] = 0.0; }
+        if (lane == 0) { sel_index[s] = -3; tile_mask[s] = 0ull; ncand_g[s] = 0; tol_g[s] = 0.0; probe_g[s] = -1; }
         return;
     }
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -373,12 +373,40 @@ __global__ void __launch_bounds__(128)
             mask |= __shfl_xor_sync(0xffffffffu, mask, o);
         }
     }
+    // Runtime certificate, part 1: a column that is refined anyway also gets its best EXCLUDED tile evaluated
+    // exactly (the probe).  K4 then checks that the exact minimum does not sit in the probe tile and measures the
+    // screening error on every evaluated alpha against the margin.
+    // Every 32nd column is a sentinel: refined (best tile + probe) even when the screen separates its alphas, so that
+    // every flightline carries measurements of the screening error (part 3 extends them to the other columns).
+    const bool sentinel = (s & 31) == 0;
+    if (!bad && vmin < inf && cnt == 1 && sentinel) { cnt = 2; mask = 1ull << (first >> 3); }
+    int probe = -1;
+    if (!bad && vmin < inf && cnt > 1) {
+        double pv = inf;
+        int pi = 0x7fffffff;
+        for (int i = lane; i < A; i += 32) {
+            if ((mask >> (i >> 3)) & 1ull) continue;
+            const double v = nll_g[(long long)s * A + i];
+            if (v < pv) { pv = v; pi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, pv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, pi, o);
+            if (ov < pv || (ov == pv && oi < pi)) { pv = ov; pi = oi; }
+        }
+        if (pv < inf) probe = pi >> 3;
+    }
     if (lane == 0) {
         tol_g[s] = tol * hmax + 1.0e-10;
+        probe_g[s] = -1;
         if (bad) { sel_index[s] = -2; tile_mask[s] = ~0ull; ncand_g[s] = A; }          // refine everything
         else if (!(vmin < inf)) { sel_index[s] = -1; tile_mask[s] = 0ull; ncand_g[s] = 0; }   // all inf (:123-127)
         else if (cnt == 1) { sel_index[s] = first; tile_mask[s] = 0ull; ncand_g[s] = 1; }
-        else { sel_index[s] = -2; tile_mask[s] = mask; ncand_g[s] = cnt; }
+        else {
+            sel_index[s] = -2; ncand_g[s] = cnt;
+            if (probe >= 0) { mask |= 1ull << probe; probe_g[s] = probe; }
+            tile_mask[s] = mask;
+        }
     }
 }
 
@@ -441,9 +469,37 @@ void launch_screen(const Dims& d, const float* xt, const double* mu, const doubl
 void launch_select(const Dims& d, const double* fscreen, int nchunk, const double* logdet, const double* rsum,
                    const int* n, const int* nloo, double tol, double* nll, int* sel_index,
                    unsigned long long* tile_mask, int* ncand, double* tol_out, const float* betaf_fold,
-                   cudaStream_t st) {
+                   int* probe, cudaStream_t st) {
     select_kernel<<<(d.S + 3) / 4, 128, 0, st>>>(fscreen, nchunk, logdet, rsum, n, nloo, d.A, d.AP, d.AP16, d.D, d.S, tol,
-                                                 nll, sel_index, tile_mask, ncand, tol_out, betaf_fold);
+                                                 nll, sel_index, tile_mask, ncand, tol_out, betaf_fold, probe);
+}
+
+// Runtime certificate, part 3 (one CTA): the largest measured screening error of the flightline, as a fraction of the
+// margin, also vouches for the columns the screen decided alone.  If it reaches kCertFactor^-1 of the margin every
+// such column is sent to the exact pass as well; columns whose own check failed in K4 already are.
+__global__ void __launch_bounds__(256)
+    certify_kernel(const double* __restrict__ check, const int* __restrict__ sel_index, int S, int enabled,
+                   unsigned long long* __restrict__ redo, double* __restrict__ worst_out) {
+    __shared__ double red[8];
+    double w = 0.0;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) if (check[s] > w) w = check[s];
+    for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = w;
+    __syncthreads();
+    w = red[0];
+    for (int i = 1; i < 8; ++i) w = fmax(w, red[i]);
+    if (threadIdx.x == 0 && worst_out) *worst_out = w;
+    const bool all = enabled && (w * kCertFactor > 1.0);
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        unsigned long long r = redo[s];                 // set by K4 for a column whose own check failed
+        if (all && sel_index[s] >= 0) r = ~0ull;
+        redo[s] = enabled ? r : 0ull;
+    }
+}
+
+void launch_certify(const Dims& d, const double* check, const int* sel_index, int enabled, unsigned long long* redo,
+                    double* worst, cudaStream_t st) {
+    certify_kernel<<<1, 256, 0, st>>>(check, sel_index, d.S, enabled, redo, worst);
 }
 
 }  // namespace cmf

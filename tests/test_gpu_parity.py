@@ -181,6 +181,66 @@ def test_screening_selects_the_exact_argmin(L, S, seed, bad):
     assert np.array_equal(ref["alpha_index"], sc["alpha_index"])
 
 
+def _heavy_tail_cube(L, S, seed):
+    """Student-t residuals and sensor noise, bright blocks and a few extreme pixels (u = beta r approaching the 0.25
+    poison of the screen): the columns the Gaussian scenes never produce."""
+    rng = np.random.default_rng(seed)
+    cube = synth.make_cube(L, S, seed=seed)
+    x = cube[:, 350:422, :].astype(np.float64)
+    mu = x.mean(axis=0, keepdims=True)
+    x = mu + (x - mu) * (1.0 + 0.5 * np.abs(rng.standard_t(3, size=(L, 1, S))))       # heavy-tailed illumination
+    x += 0.004 * rng.standard_t(4, size=x.shape)                                       # heavy-tailed sensor noise (u up to ~0.2)
+    for c in range(0, S, 3):                                                           # bright blocks
+        l0 = int(rng.integers(0, L - 60))
+        x[l0:l0 + 40, :, c] *= 1.0 + rng.uniform(0.5, 2.0)
+    # spectrally rough outliers of growing size in every fourth column: from harmless to pixels beyond the screen's
+    # u = 1/4 poison (those columns are searched in FP64 outright)
+    cols = np.arange(1, S, 4)
+    for k, c in enumerate(cols):
+        l = rng.integers(0, L, size=3)
+        x[l, :, c] += rng.normal(0.0, 0.004 * 2.0 ** (k % 8), size=(3, 72))
+    cube[:, 350:422, :] = np.maximum(x, 1.0e-4).astype(np.float32)
+    return cube
+
+
+@pytest.mark.parametrize("L,S,seed", [(4000, 96, 64)])
+def test_screen_certificate_on_heavy_tails(L, S, seed):
+    """The screened search on heavy-tailed columns: the default run must pick the FP64 argmin in every column, the
+    runtime certificate must rescue a deliberately useless margin (test_full_flightline_properties shows that the
+    same useless margin WITHOUT the certificate does go wrong at flightline size)."""
+    cube = _heavy_tail_cube(L, S, seed)
+    active = [351, 422]
+    ab = _abscf(active)
+    Lc, B, Sc = cube.shape
+    with ColumnwiseMF(Lc, B, Sc, active, ab) as eng:
+        eng.upload(cube)
+        eng.run(exact=True)
+        ex = eng.results()
+        eng.run()
+        sc = eng.results(); chk = eng.screen_check(); st = eng.status()
+        eng.set_screen_margin(1.0e-9, certify=True)
+        eng.run()
+        rescued = eng.results(); st_rescued = eng.status(); chk_rescued = eng.screen_check()
+        eng.set_screen_margin(1.0e-9, certify=False)
+        eng.run()
+        raw = eng.results()
+    # default margin: exact selection, certificate quiet or (where it fired) still exact
+    assert np.array_equal(sc["alpha_index"], ex["alpha_index"])
+    assert np.array_equal(sc["mf"], ex["mf"], equal_nan=True)
+    assert np.all(chk >= 0.0) and chk.max() > 0.0                # the sentinel / refined columns measured something
+    print("default margin: worst measured error / margin = %.3f, rechecked columns = %d"
+          % (chk.max(), int(((st & 32) != 0).sum())))
+    # useless margin + certificate: measured error >> margin on the sentinels -> everything re-evaluated exactly
+    assert chk_rescued.max() * 4.0 > 1.0
+    assert np.array_equal(rescued["alpha_index"], ex["alpha_index"])
+    assert np.array_equal(rescued["mf"], ex["mf"], equal_nan=True)
+    assert ((st_rescued & 32) != 0).sum() >= 1          # (poisoned columns were searched in FP64 from the start)
+    # useless margin, no certificate: the screen alone is not enough on this data
+    wrong = int((raw["alpha_index"] != ex["alpha_index"]).sum())
+    print("margin 1e-9 without certificate: %d of %d columns pick another alpha" % (wrong, S))
+    # (at these sizes the gaps between neighbouring alphas are wide; the flightline-size test demands wrong >= 1)
+
+
 def test_ql_and_jacobi_eigensolvers_agree(monkeypatch):
     """The default Householder + QL factorisation against the cyclic Jacobi cross-check: same spectrum to
     1e-12 of the largest eigenvalue, same alpha indices, scores within 1e-8 sigma."""
@@ -367,6 +427,25 @@ def test_full_flightline_properties():
         r1 = eng.results()
         eng.run()
         r2 = eng.results()
+        chk = eng.screen_check()
+        # the screened search at flightline size against the all-FP64 search, and the same with a useless margin and
+        # no certificate: with 598 columns of 20 000 lines the screening error (~0.16 of the default margin) is far
+        # above 1e-9 of it, so near-tied columns go wrong -- the margin and the certificate are what prevents that
+        eng.run(exact=True)
+        ex_idx = eng.alpha_index()
+        eng.set_screen_margin(1.0e-9, certify=False)
+        eng.run()
+        raw_idx = eng.alpha_index()
+        eng.set_screen_margin(1.0e-9, certify=True)
+        eng.run()
+        res_idx = eng.alpha_index(); res_status = eng.status()
+    assert np.array_equal(r1["alpha_index"], ex_idx)
+    assert 0.0 < chk.max() < 0.25 and (chk > 0).sum() >= S // 32
+    wrong = int((raw_idx != ex_idx).sum())
+    print("margin 1e-9 without certificate: %d of %d columns pick another alpha; default margin: worst measured "
+          "error %.3f of the margin over %d measured columns" % (wrong, S, chk.max(), int((chk > 0).sum())))
+    assert wrong >= 1
+    assert np.array_equal(res_idx, ex_idx) and ((res_status & 32) != 0).sum() > S // 2
     assert np.array_equal(r1["mf"], r2["mf"]) and np.array_equal(r1["alpha_index"], r2["alpha_index"])
     assert r1["mask"].all() and np.all(r1["status"] == 0)
     t = ab[None, :] * r1["mu"]
