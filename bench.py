@@ -294,8 +294,8 @@ def run_gpu(args):
     lib = _lib.load()
 
     # FP64 tensor peak for the roofline (rank 0, before the timed region)
-    dmma_peak = lib.cmf_microbench(local, 0, 3) if rank == 0 else 0.0
-    mma_peak = lib.cmf_microbench(local, 9, 3) if rank == 0 else 0.0
+    dmma_peak = _lib.load_tools().cmf_microbench(local, 0, 3) if rank == 0 else 0.0
+    mma_peak = _lib.load_tools().cmf_microbench(local, 9, 3) if rank == 0 else 0.0
 
     slab = synth.make_slab_torch(L, S, ACTIVE[0], ACTIVE[1], dev, seed=2 + rank)
     stream = torch.cuda.current_stream()

@@ -267,17 +267,6 @@ void cmf_host_free(void* p);
 int cmf_host_register(void* p, size_t bytes);
 int cmf_host_unregister(void* p);
 
-/* ---- micro-benchmarks used for the roofline denominators (profiles/): returns achieved rate ---- */
-/* kind: 0 DMMA.8x8x4 TFLOP/s (32 warps/SM), 8 same with 8 warps/SM and 24 accumulators, 1 DFMA TFLOP/s,
- *       2 HBM read GB/s (8-byte loads), 3 HBM read GB/s (16-byte), 4 HBM copy GB/s (read+write bytes),
- *       5 bulk-async-copy read GB/s, 6 f32->f64 conversions G/s, 7 FP64 log+divide pairs G/s,
- *       9 legacy mma.sync tf32 TFLOP/s, 10 legacy mma.sync bf16 TFLOP/s, 11 FP32 FFMA TFLOP/s,
- *       12-15 dependent-issue latency in cycles of DFMA / rsqrt+DADD / sqrt+DADD / divide+DADD (one thread),
- *       16-18 cycles per step of the QL rotation recurrence: alone / 20 chains per SM / 5 chains per SM,
- *       30-33 GB/s of the two halves of the repack pass alone: slab read through 4-byte LDGSTS / 8-byte LDGSTS /
- *             8-byte loads, and the 16-byte xt write side */
-double cmf_microbench(int device, int kind, int iters);
-
 #ifdef __cplusplus
 }
 #endif

@@ -6,8 +6,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# CMF_B200_LIB: development hook for instrumented builds of the same library (tools/ only)
+# CMF_B200_LIB: development hook for other builds of the same library (tools/ and the cross-check tests load
+# libcmf_b200_tools.so through it in a subprocess)
 LIB_PATH = os.environ.get("CMF_B200_LIB") or os.path.join(_HERE, "libcmf_b200.so")
+TOOLS_LIB_PATH = os.path.join(_HERE, "libcmf_b200_tools.so")
 
 # every symbol include/cmf_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
@@ -15,7 +17,7 @@ SYMBOLS = [
     "cmf_upload_bil", "cmf_upload_lines", "cmf_bind_device_slab", "cmf_set_labels", "cmf_set_clustering", "cmf_set_regfull", "cmf_set_exclusion", "cmf_run", "cmf_sync", "cmf_run_host", "cmf_download",
     "cmf_device_ptr", "cmf_output_bytes", "cmf_kernel_count", "cmf_kernel_name", "cmf_kernel_times",
     "cmf_launch_count", "cmf_screen_kernel", "cmf_host_alloc", "cmf_host_free", "cmf_host_register", "cmf_host_unregister",
-    "cmf_microbench", "cmf_pixel_flags", "cmf_column_profile", "cmf_column_profile_image",
+    "cmf_pixel_flags", "cmf_column_profile", "cmf_column_profile_image",
     "cmf_detection_prefilter", "cmf_cnn_input", "cmf_looshrinkage", "cmf_set_screen_margin",
 ]
 
@@ -90,7 +92,6 @@ def load():
         "cmf_host_free": (None, [vp]),
         "cmf_host_register": (C.c_int, [vp, sz]),
         "cmf_host_unregister": (C.c_int, [vp]),
-        "cmf_microbench": (C.c_double, [C.c_int, C.c_int, C.c_int]),
         "cmf_pixel_flags": (C.c_int, [vp, vp, C.c_int, i32, i32, i32, C.POINTER(FlagSpec), vp]),
         "cmf_column_profile": (C.c_int, [vp, C.c_int, C.c_double, vp]),
         "cmf_column_profile_image": (C.c_int, [vp, vp, i32, i32, C.c_double, C.c_int, C.c_double, vp]),
@@ -103,3 +104,18 @@ def load():
         fn.restype, fn.argtypes = res, args
     _lib = lib
     return lib
+
+
+_tools = None
+
+
+def load_tools():
+    """The tools build (include/cmf_b200_tools.h): only its micro-benchmark entry is declared here."""
+    global _tools
+    if _tools is None:
+        if not os.path.exists(TOOLS_LIB_PATH):
+            raise OSError("libcmf_b200_tools.so is not built: run `python -m srcfinder_b200.build`")
+        _tools = C.CDLL(TOOLS_LIB_PATH)
+        _tools.cmf_microbench.restype = C.c_double
+        _tools.cmf_microbench.argtypes = [C.c_int, C.c_int, C.c_int]
+    return _tools

@@ -140,7 +140,7 @@ cudaError_t dalloc(cmf_ctx* c, T** p, size_t count) {
         *p = reinterpret_cast<T*>(q);
         // testing hook: CMF_POISON=1 fills every work buffer with 0xFF (NaN / -1) so that any read of memory the
         // pipeline has not written shows up (fresh cudaMalloc pages are usually zero, recycled ones are not)
-        static const bool poison = getenv("CMF_POISON") != nullptr;
+        static const bool poison = cmf_hook("CMF_POISON") != nullptr;
         if (poison) e = cudaMemset(q, 0xFF, bytes);
     }
     return e;
@@ -530,7 +530,9 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     if (!p->abscf) return fail(ctx, CMF_E_ARG, "abscf is NULL");
     const int D = p->band_hi - p->band_lo + 1;
     const int NT = (D + 7) / 8;
-    const bool wide = NT > kMaxNT;
+    // CMF_FORCE_WIDE (tools build only): run a narrow window through the wide-window kernel set, an independent
+    // implementation of every step (cross-check, tests/test_gpu_wide.py)
+    const bool wide = NT > kMaxNT || cmf_hook("CMF_FORCE_WIDE") != nullptr;
     const bool loo = p->model == CMF_MODEL_LOOSHRINKAGE;
     if (!loo && p->model != CMF_MODEL_EMPIRICAL) return fail(ctx, CMF_E_ARG, "unknown model");
     if (loo && (p->num_alphas < 1 || p->num_alphas > 4096 || !p->alphas))
@@ -568,7 +570,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
         ctx->can_screen = false; ctx->use_screen5 = false;
         // the integer Gram accumulates 32-bit sums of products of balanced base-256 digits: fewer than 2^17 lines
         ctx->use_gram8 = d.L < (1 << 17);
-        if (const char* e = getenv("CMF_WIDE_GRAM")) if (strcmp(e, "fp64") == 0) ctx->use_gram8 = false;
+        if (const char* e = cmf_hook("CMF_WIDE_GRAM")) if (strcmp(e, "fp64") == 0) ctx->use_gram8 = false;
         const size_t zcol = (size_t)d.L * d.DP * sizeof(double);
         ctx->zbatch = (int)std::max<size_t>(1, std::min<size_t>((size_t)d.S, ((size_t)4 << 30) / zcol));
         ctx->nlanes = score_plan(d, ctx->sm_count, &ctx->score_lpc);
@@ -588,10 +590,9 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     ctx->nchunk_screen = ctx->nchunk_loo;
     // the screening pass needs its tables in shared memory and a 64-bit tile mask (A <= 512)
     ctx->can_screen = loo && d.NT2 <= 64 && screen_smem_bytes(d) <= 227 * 1024;
-    if (const char* e = getenv("CMF_SCREEN_TOL")) ctx->screen_tol = atof(e);      // tuning hook (tools/ only)
     ctx->use_screen5 = ctx->can_screen && screen5_supported(d);
-    if (const char* e = getenv("CMF_SCREEN_IMPL")) if (strcmp(e, "legacy") == 0) ctx->use_screen5 = false;
-    if (const char* e = getenv("CMF_EIGEN")) ctx->eigen_method = (strcmp(e, "jacobi") == 0) ? 1 : 0;
+    if (const char* e = cmf_hook("CMF_SCREEN_IMPL")) if (strcmp(e, "legacy") == 0) ctx->use_screen5 = false;
+    if (const char* e = cmf_hook("CMF_EIGEN")) ctx->eigen_method = (strcmp(e, "jacobi") == 0) ? 1 : 0;
     }
 
     const size_t LS = (size_t)d.L * d.S;

@@ -4,7 +4,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
 namespace cmf {
+
+// Tuning / cross-check hooks read from the environment exist only in the TOOLS build of the library
+// (srcfinder_b200/build.py: libcmf_b200_tools.so, -DCMF_TUNING_HOOKS); the shipped library ignores the environment.
+#ifdef CMF_TUNING_HOOKS
+inline const char* cmf_hook(const char* name) { return getenv(name); }
+#else
+inline const char* cmf_hook(const char*) { return nullptr; }
+#endif
 
 constexpr int kMaxNT = 12;          // active bands padded to 8*NT, NT <= 12 (D <= 96) for the shared-memory kernels
 constexpr int kGramTL = 16;         // lines per Gram tile (4 k-steps of DMMA.8x8x4)
@@ -88,7 +98,9 @@ size_t screen5_table_floats(const Dims& d);
 void launch_screen5(const Dims& d, const float* xt, const double* mu, const int* n, const int* nloo,
                     const double* alphas, const double* P, const double* lam, float* tab, float* betaf,
                     int nchunk, double* fscreen, cudaStream_t st);
+#ifdef CMF_TUNING_HOOKS
 double screen5_selftest(int N, int K, int row_off, int swap_lbo_sbo);
+#endif
 void launch_select(const Dims& d, const double* fscreen, int nchunk, const double* logdet, const double* rsum,
                    const int* n, const int* nloo, double tol, double* nll, int* sel_index,
                    unsigned long long* tile_mask, int* ncand, double* tol_out, const float* betaf_fold,

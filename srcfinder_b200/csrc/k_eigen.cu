@@ -35,6 +35,7 @@ __device__ __forceinline__ double pilot_term(const double* __restrict__ mu, cons
     return (double)n * dr * dc;
 }
 
+#ifdef CMF_TUNING_HOOKS     // cyclic Jacobi: cross-check of the QL solver, tools build only
 template <int NT>
 __global__ void __launch_bounds__(512)
     eigen_kernel(const double* __restrict__ gram_part, int nchunk, const int* __restrict__ n_g, int D,
@@ -186,6 +187,8 @@ __global__ void __launch_bounds__(512)
     }
     if (tid == 0) slogT_g[s] = sumlogT;
 }
+
+#endif  // CMF_TUNING_HOOKS
 
 // ---------------------------------------------------------------------------------------- K2 (QL)
 // Householder tridiagonalisation + implicit-shift QL with accumulated transformations (the EISPACK
@@ -993,10 +996,12 @@ static void launch_eigen_t(const Dims& d, const double* gram_part, int nchunk, c
         cudaFuncSetAttribute(eigen_ql_kernel<NT, kEigFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         eigen_ql_kernel<NT, kEigFull><<<d.S, kQlThreads, smem, st>>>(gram_part, nchunk, n, d.D, mu, ctr, P, lam, slogT,
                                                                     status, sweeps, gramT_part, nT);
+#ifdef CMF_TUNING_HOOKS
     } else if (method == 1) {
         const size_t smem = (size_t)(2 * DP * LD + 2 * DP + 2 * (DP / 2 + 1)) * sizeof(double);
         cudaFuncSetAttribute(eigen_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         eigen_kernel<NT><<<d.S, 512, smem, st>>>(gram_part, nchunk, n, d.D, mu, ctr, P, lam, slogT, status, sweeps);
+#endif
     } else {
         const size_t smem = (size_t)(DP * LD + 5 * DP + 8) * sizeof(double);
         cudaFuncSetAttribute(eigen_ql_kernel<NT, kEigDiag>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -423,7 +423,7 @@ static void screen_variant(int* g1t, int* nprod) {
     static int v[2] = {-1, -1};
     if (v[0] < 0) {
         v[0] = 1; v[1] = 3;   // measured: TF32 projection keeps the screening error at 0.07 of the margin
-        if (const char* e = getenv("CMF_SCREEN_VARIANT")) sscanf(e, "%d,%d", &v[0], &v[1]);
+        if (const char* e = cmf_hook("CMF_SCREEN_VARIANT")) sscanf(e, "%d,%d", &v[0], &v[1]);
     }
     *g1t = v[0]; *nprod = v[1];
 }
@@ -448,10 +448,15 @@ static void launch_screen_t(const Dims& d, const float* xt, const double* mu, co
                             cudaStream_t st) {
     int g1t, nprod;
     screen_variant(&g1t, &nprod);
+#ifdef CMF_TUNING_HOOKS
     if (g1t && nprod == 3) launch_screen_v<NT, true, 3>(d, xt, mu, Pf, Ps, Ws, betaf, n, nchunk, fscreen, st);
     else if (g1t) launch_screen_v<NT, true, 2>(d, xt, mu, Pf, Ps, Ws, betaf, n, nchunk, fscreen, st);
     else if (nprod == 3) launch_screen_v<NT, false, 3>(d, xt, mu, Pf, Ps, Ws, betaf, n, nchunk, fscreen, st);
     else launch_screen_v<NT, false, 2>(d, xt, mu, Pf, Ps, Ws, betaf, n, nchunk, fscreen, st);
+#else
+    (void)g1t; (void)nprod;
+    launch_screen_v<NT, true, 3>(d, xt, mu, Pf, Ps, Ws, betaf, n, nchunk, fscreen, st);   // the measured-best variant
+#endif
 }
 
 void launch_screen(const Dims& d, const float* xt, const double* mu, const double* Pf, const float* Ps,

@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(kT5Threads, 1)
     }
 }
 
+#ifdef CMF_TUNING_HOOKS
 // ------------------------------------------------------------------ self test (cmf_microbench kinds 20..23)
 // One 128 x N x K contraction with A written to TMEM by tcgen05.st and B in the canonical shared-memory
 // layout: checks the descriptor encoding, the TMEM A layout and the ld/st lane mapping against the host.
@@ -518,6 +519,8 @@ __global__ void __launch_bounds__(128, 1)
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+#endif  // CMF_TUNING_HOOKS
+
 }  // namespace
 
 // ------------------------------------------------------------------ launchers
@@ -559,6 +562,7 @@ void launch_screen5(const Dims& d, const float* xt, const double* mu, const int*
     }
 }
 
+#ifdef CMF_TUNING_HOOKS
 // max |D - A.B^T| of one tcgen05 TS-form contraction against the host; < 0 on a CUDA error
 double screen5_selftest(int N, int K, int row_off, int swap_lbo_sbo) {
     const int NB = N + row_off;
@@ -593,5 +597,7 @@ double screen5_selftest(int N, int K, int row_off, int swap_lbo_sbo) {
     cudaFree(dA); cudaFree(dB); cudaFree(dD);
     return err;
 }
+
+#endif  // CMF_TUNING_HOOKS
 
 }  // namespace cmf

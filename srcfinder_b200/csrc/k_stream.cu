@@ -622,14 +622,19 @@ __global__ void colstats_kernel(const double* __restrict__ stat_part, int nlanes
 // the older single-stage kernel (kept for A/B measurements through tools/).
 struct RepackVariant { int cg, lt, ns; };
 
+// the shipped library holds the measured-best shape and the small-tile fall-back; the sweep lives in the tools build
+#ifdef CMF_TUNING_HOOKS
 #define CMF_REPACK_VARIANTS(X) X(32, 8, 2) X(32, 4, 3) X(32, 4, 4) X(32, 2, 8) X(16, 4, 2)
+#else
+#define CMF_REPACK_VARIANTS(X) X(32, 4, 4) X(16, 4, 2)
+#endif
 
 static RepackVariant repack_variant_requested() {
     // tuning hook (tools/ only): CMF_REPACK_VARIANT=CG,LT,NS picks another instantiation
     static RepackVariant v = [] {
         const RepackVariant dflt{32, 4, 4};     // measured on B200 (profiles/r01g_ / r01i_tune_repack.json)
         RepackVariant r = dflt;
-        if (const char* e = getenv("CMF_REPACK_VARIANT")) sscanf(e, "%d,%d,%d", &r.cg, &r.lt, &r.ns);
+        if (const char* e = cmf_hook("CMF_REPACK_VARIANT")) sscanf(e, "%d,%d,%d", &r.cg, &r.lt, &r.ns);
         bool known = false;
 #define CMF_RV(CGv, LTv, NSv) known = known || (r.cg == CGv && r.lt == LTv && r.ns == NSv);
         CMF_REPACK_VARIANTS(CMF_RV)
@@ -666,7 +671,7 @@ static int repack_pipe_resident() {
 
 // 8-byte copies (repack_pair_kernel) whenever the rows allow it; CMF_REPACK_PAIR=0 keeps the 4-byte kernel (tools/)
 static bool repack_use_pair(const Dims& d, const RepackVariant& v) {
-    static const bool enabled = [] { const char* e = getenv("CMF_REPACK_PAIR"); return !(e && e[0] == '0'); }();
+    static const bool enabled = [] { const char* e = cmf_hook("CMF_REPACK_PAIR"); return !(e && e[0] == '0'); }();
     return enabled && d.vec2 && v.cg == 32;
 }
 
@@ -689,9 +694,11 @@ static int repack_pair_resident() {
 template <int NT>
 static int repack_pair_resident_t(const RepackVariant& v) {
     if (v.lt == 4 && v.ns == 4) return repack_pair_resident<NT, 4, 4>();
+#ifdef CMF_TUNING_HOOKS
     if (v.lt == 2 && v.ns == 8) return repack_pair_resident<NT, 2, 8>();
     if (v.lt == 4 && v.ns == 3) return repack_pair_resident<NT, 4, 3>();
     if (v.lt == 8 && v.ns == 2) return repack_pair_resident<NT, 8, 2>();
+#endif
     return 0;
 }
 
@@ -733,7 +740,7 @@ int repack_nsplit(const Dims& d) {
     if (resident < 1) resident = 1;
     const int groups = (d.S + v.cg - 1) / v.cg;
     int ns = (sms * resident) / groups;
-    if (const char* e = getenv("CMF_REPACK_NSPLIT")) ns = atoi(e);      // tuning hook (tools/ only)
+    if (const char* e = cmf_hook("CMF_REPACK_NSPLIT")) ns = atoi(e);      // tuning hook (tools/ only)
     const int maxsplit = (d.L + 4 * v.lt - 1) / (4 * v.lt);             // at least 4 tiles per CTA
     if (ns > maxsplit) ns = maxsplit;
     return ns < 1 ? 1 : ns;
@@ -773,7 +780,10 @@ static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t
                 line_base, line_limit, split_base, sel, write_mask);                                              \
             return;                                                                                               \
         }
-        CMF_RP(4, 4) CMF_RP(4, 3) CMF_RP(8, 2) CMF_RP(2, 8)
+        CMF_RP(4, 4)
+#ifdef CMF_TUNING_HOOKS
+        CMF_RP(4, 3) CMF_RP(8, 2) CMF_RP(2, 8)
+#endif
 #undef CMF_RP
     }
 #define CMF_RV(CGv, LTv, NSv)                                                                                \
@@ -815,7 +825,7 @@ static ScoreVariant score_variant() {
     // tuning hook (tools/ only): CMF_SCORE_VARIANT=NL,BC,MINB picks another instantiation
     static ScoreVariant v = [] {
         ScoreVariant r{2, 18, 2};   // measured best on B200: 0.59 ms per 20k-line flightline
-        if (const char* e = getenv("CMF_SCORE_VARIANT")) sscanf(e, "%d,%d,%d", &r.nl, &r.bc, &r.minb);
+        if (const char* e = cmf_hook("CMF_SCORE_VARIANT")) sscanf(e, "%d,%d,%d", &r.nl, &r.bc, &r.minb);
         return r;
     }();
     return v;
@@ -867,7 +877,10 @@ void launch_score(const Dims& d, const float* slab, const uint8_t* mask, const d
     if (v.nl == NL && v.bc == BC && v.minb == MB)                                                       \
         return launch_score_tiled<NL, BC, MB>(d, slab, mask, wT, c0, status, nodata, mf, stat_part, nlanes, \
                                               lines_per_cta, sel, mindex, alpha_img, st);
-        CMF_SV(2, 18, 2) CMF_SV(2, 12, 2) CMF_SV(4, 8, 2) CMF_SV(2, 8, 3)
+        CMF_SV(2, 18, 2)
+#ifdef CMF_TUNING_HOOKS
+        CMF_SV(2, 12, 2) CMF_SV(4, 8, 2) CMF_SV(2, 8, 3)
+#endif
 #undef CMF_SV
         return launch_score_tiled<2, 18, 2>(d, slab, mask, wT, c0, status, nodata, mf, stat_part, nlanes,
                                             lines_per_cta, sel, mindex, alpha_img, st);

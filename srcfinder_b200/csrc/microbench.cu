@@ -2,7 +2,7 @@
 // for the FP64 tensor path (MEASURED_PEAKS.json only carries HBM copy and bf16 GEMM figures).
 #include <stdio.h>
 
-#include "../../include/cmf_b200.h"
+#include "../../include/cmf_b200_tools.h"
 #include "cmf_common.cuh"
 #include "cmf_internal.h"
 

@@ -46,14 +46,43 @@ def test_kernel_table(lib):
     assert b"sm_100a" in lib.cmf_version()
 
 
-def test_native_code_is_blackwell_native():
-    """The shipped SASS uses FP64 tensor MMA and bulk async copies (UBLKCP), built for sm_100a."""
+def test_native_code_is_blackwell_native(lib):
+    """The shipped SASS is Blackwell-native: 5th-generation tensor-core MMAs with TMEM operands and accumulators
+    (tcgen05: UTCHMMA = TF32 screen, UTCIMMA = integer Gram; LDTM / STTM = tcgen05.ld / .st), bulk async copies on the
+    TMA engine (UBLKCP) tracked by mbarriers (SYNCS), FP64 tensor MMA (DMMA), built for sm_100a.  The per-kernel
+    opcode census is committed under profiles/ (tools/sass_census.py)."""
     from srcfinder_b200 import _lib
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    assert "DMMA" in sass
-    assert "UBLKCP" in sass
-    assert "SYNCS" in sass      # mbarrier
+    for op in ("UTCHMMA", "UTCIMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "SYNCS", "DMMA"):
+        assert op in sass, op
+    # per kernel: the screen and the integer Gram must be the tcgen05 kernels
+    fn = {}
+    cur = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            fn[cur] = set()
+        elif cur:
+            for op in ("UTCHMMA", "UTCIMMA", "LDTM", "STTM", "UBLKCP", "DMMA"):
+                if op in line:
+                    fn[cur].add(op)
+    screen = [k for k in fn if "loo_screen5_kernel" in k]
+    gram8 = [k for k in fn if "wide_gram8_kernel" in k]
+    assert screen and all({"UTCHMMA", "LDTM", "STTM", "UBLKCP"} <= fn[k] for k in screen)
+    assert gram8 and all({"UTCIMMA", "LDTM", "UBLKCP"} <= fn[k] for k in gram8)
+
+
+def test_product_library_ignores_the_environment(lib):
+    """Environment tuning hooks, the micro-benchmarks and the cross-check solver live in the tools build only."""
+    from srcfinder_b200 import _lib
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "cmf_microbench" not in out
+    und = subprocess.run(["nm", "-D", "--undefined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "getenv" not in und
+    tools = subprocess.run(["nm", "-D", "--defined-only", _lib.TOOLS_LIB_PATH], capture_output=True, text=True).stdout
+    assert "cmf_microbench" in tools
 
 
 def test_no_cpu_fallback(lib):

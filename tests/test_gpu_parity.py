@@ -241,27 +241,46 @@ def test_screen_certificate_on_heavy_tails(L, S, seed):
     # (at these sizes the gaps between neighbouring alphas are wide; the flightline-size test demands wrong >= 1)
 
 
-def test_ql_and_jacobi_eigensolvers_agree(monkeypatch):
-    """The default Householder + QL factorisation against the cyclic Jacobi cross-check: same spectrum to
-    1e-12 of the largest eigenvalue, same alpha indices, scores within 1e-8 sigma."""
-    cube = synth.make_cube(700, 12, seed=71, bad_pixels=True)
-    active = [351, 422]
-    ab = _abscf(active)
-    L, B, S = cube.shape
-    out = {}
-    for method in ("ql", "jacobi"):
-        monkeypatch.setenv("CMF_EIGEN", method)
-        with ColumnwiseMF(L, B, S, active, ab) as eng:
-            eng.upload(cube)
-            eng.run()
-            out[method] = (eng.results(), np.sort(eng.eigvals(), axis=1), eng.status())
-    monkeypatch.delenv("CMF_EIGEN")
-    (rq, lq, sq), (rj, lj, sj) = out["ql"], out["jacobi"]
-    assert np.all(sq == 0) and np.all(sj == 0)
-    assert np.max(np.abs(lq - lj)) < 1e-12 * lj.max()
-    assert np.array_equal(rq["alpha_index"], rj["alpha_index"])
-    err = np.nanmax(np.abs(rq["mf"] - rj["mf"]), axis=0) / rq["colstd"]
-    assert np.max(err) < 1e-8
+def _run_in_subprocess(code, env_extra, tools_lib):
+    """Run ``code`` (it must np.savez its results to sys.argv[1]) in a fresh interpreter; ``tools_lib`` loads
+    libcmf_b200_tools.so (the build with the environment hooks) instead of the product library."""
+    import os, subprocess, sys, tempfile
+    from srcfinder_b200 import _lib
+    env = dict(os.environ)
+    for k in ("CMF_POISON", "CMF_EIGEN", "CMF_FORCE_WIDE", "CMF_B200_LIB"):
+        env.pop(k, None)
+    env.update(env_extra)
+    if tools_lib:
+        env["CMF_B200_LIB"] = _lib.TOOLS_LIB_PATH
+    path = os.path.join(tempfile.mkdtemp(), "r.npz")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0, %r)\n" % root + code, path], check=True, env=env)
+    return np.load(path)
+
+
+def test_independent_solvers_agree():
+    """The shipped path (Householder + QL in shared memory, DMMA Gram, screened search) against two independent
+    implementations in the tools build of the library: the cyclic Jacobi solver (CMF_EIGEN=jacobi) and the whole
+    wide-window kernel set forced onto the 72-band window (CMF_FORCE_WIDE: integer tcgen05 Gram, global-memory
+    tridiagonalisation, separate QL recurrence, blocked FP64 search).  Same spectrum, same alpha indices, same scores."""
+    code = ("import numpy as np\n"
+            "from srcfinder_b200 import ColumnwiseMF, synth\n"
+            "cube = synth.make_cube(700, 12, seed=71, bad_pixels=True)\n"
+            "ab = synth.load_ch4_library()[350:422, 2]\n"
+            "L, B, S = cube.shape\n"
+            "with ColumnwiseMF(L, B, S, [351, 422], ab) as eng:\n"
+            "    eng.upload(cube); eng.run(); r = eng.results()\n"
+            "    np.savez(sys.argv[1], mf=r['mf'], ai=r['alpha_index'], cs=r['colstd'], st=r['status'],\n"
+            "             eig=np.sort(eng.eigvals(), axis=1), w=r['weights'])\n")
+    base = _run_in_subprocess(code, {}, tools_lib=False)
+    assert np.all(base["st"] == 0)
+    for env in ({"CMF_EIGEN": "jacobi"}, {"CMF_FORCE_WIDE": "1"}):
+        other = _run_in_subprocess(code, env, tools_lib=True)
+        assert np.all(other["st"] == 0), env
+        assert np.max(np.abs(base["eig"] - other["eig"])) < 1e-11 * other["eig"].max(), env
+        assert np.array_equal(base["ai"], other["ai"]), env
+        err = np.nanmax(np.abs(base["mf"] - other["mf"]), axis=0) / base["cs"]
+        assert np.max(err) < 1e-7, (env, err.max())
 
 
 def test_empirical_and_co2_window():
@@ -367,27 +386,19 @@ def test_streamed_upload_from_a_memmap(tmp_path):
 
 
 def test_no_read_of_unwritten_work_memory():
-    """CMF_POISON=1 fills every work buffer with 0xFF at allocation (NaN / -1): results must not change, i.e. no
-    kernel relies on cudaMalloc handing out zeroed pages (recycled pages are not)."""
-    import subprocess, sys, os
-    code = ("import numpy as np, sys; sys.path.insert(0, %r)\n"
+    """CMF_POISON=1 (tools build) fills every work buffer with 0xFF at allocation (NaN / -1): results must not change,
+    i.e. no kernel relies on cudaMalloc handing out zeroed pages (recycled pages are not).  Narrow and wide windows."""
+    code = ("import numpy as np\n"
             "from srcfinder_b200 import cmf_cube, synth\n"
             "cube = synth.make_cube(640, 9, seed=77, bad_pixels=True)\n"
             "ab = synth.load_ch4_library()[350:422, 2]\n"
             "r = cmf_cube(cube, ab, [351, 422]); k = cmf_cube(cube, ab, [351, 422], kmodes=3, reject_min=85, regfull=True)\n"
-            "np.savez(sys.argv[1], mf=r['mf'], ai=r['alpha_index'], cs=r['colstd'], kmf=k['mf'], kai=k['alpha_index'])\n"
-            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    import tempfile
-    outs = []
-    for poison in (False, True):
-        env = dict(os.environ)
-        env.pop("CMF_POISON", None)
-        if poison:
-            env["CMF_POISON"] = "1"
-        path = os.path.join(tempfile.mkdtemp(), "r.npz")
-        subprocess.run([sys.executable, "-c", code, path], check=True, env=env)
-        outs.append(np.load(path))
-    for key in ("mf", "ai", "cs", "kmf", "kai"):
+            "abw = synth.load_ch4_library()[4:420, 2]\n"
+            "w = cmf_cube(cube[:, :, :3], abw, [5, 420], reflectance=True)\n"
+            "np.savez(sys.argv[1], mf=r['mf'], ai=r['alpha_index'], cs=r['colstd'], kmf=k['mf'], kai=k['alpha_index'],\n"
+            "         wmf=w['mf'], wai=w['alpha_index'])\n")
+    outs = [_run_in_subprocess(code, {"CMF_POISON": "1"} if poison else {}, tools_lib=True) for poison in (False, True)]
+    for key in ("mf", "ai", "cs", "kmf", "kai", "wmf", "wai"):
         assert np.array_equal(outs[0][key], outs[1][key], equal_nan=True), key
 
 

@@ -19,12 +19,12 @@ if os.environ.get("PROBE_TC5", "1") == "1":
     # kind 21 (LBO/SBO swapped on purpose) faults and poisons the context: development use only
     for kind, name in {20: "tc5_selftest_n80", 22: "tc5_selftest_n96_rowoff112",
                        23: "tc5_selftest_n112", 24: "tc5_selftest_n72", 25: "tc5_selftest_n256_k8"}.items():
-        out[name] = lib.cmf_microbench(0, kind, 1)
+        out[name] = _lib.load_tools().cmf_microbench(0, kind, 1)
         print(name, out[name], flush=True)
 if os.environ.get("PROBE_MICRO", "1") != "1":
     names = {}
 for kind, name in names.items():
-    out[name] = lib.cmf_microbench(0, kind, 5)
+    out[name] = _lib.load_tools().cmf_microbench(0, kind, 5)
     print(name, out[name], flush=True)
 
 L = int(os.environ.get("PROBE_L", "20000"))

@@ -11,7 +11,7 @@ CASES = {20: "n80_k72", 21: "n80_k72_swapped_lbo_sbo", 22: "n96_k72_rowoff112", 
 if len(sys.argv) > 1:
     sys.path.insert(0, ROOT)
     from srcfinder_b200 import _lib
-    print("RESULT", _lib.load().cmf_microbench(0, int(sys.argv[1]), 1))
+    print("RESULT", _lib.load_tools().cmf_microbench(0, int(sys.argv[1]), 1))
     sys.exit(0)
 out = {}
 for kind, name in CASES.items():
