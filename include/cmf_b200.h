@@ -113,6 +113,11 @@ int cmf_upload_bil(cmf_ctx* ctx, const float* host_cube);
  * cmf_sync() before overwriting a block it has handed in.  The input is complete once every line has been given. */
 int cmf_upload_lines(cmf_ctx* ctx, const float* host_block, int32_t line0, int32_t nlines, int32_t band_first,
                      int32_t block_bands);
+/* Wait until the copy of the most recent cmf_upload_lines() call that read from `host_block` has finished (an event
+ * recorded behind that copy), without waiting for copies from other staging blocks that were enqueued later: this is
+ * what lets a reader refill block A while block B is still on the PCIe link.  Returns at once for an unknown block. */
+int cmf_upload_wait(cmf_ctx* ctx, const float* host_block);
+
 /* Input already on the device: pointer to element (line 0, band band_lo, sample 0); consecutive lines are
  * line_pitch floats apart, consecutive bands band_pitch floats apart (a full BIL cube: B*S and S). */
 int cmf_bind_device_slab(cmf_ctx* ctx, const float* dev_slab, int64_t line_pitch, int32_t band_pitch);

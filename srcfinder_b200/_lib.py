@@ -14,7 +14,7 @@ TOOLS_LIB_PATH = os.path.join(_HERE, "libcmf_b200_tools.so")
 # every symbol include/cmf_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "cmf_create", "cmf_destroy", "cmf_last_error", "cmf_version", "cmf_set_stream", "cmf_set_problem",
-    "cmf_upload_bil", "cmf_upload_lines", "cmf_bind_device_slab", "cmf_set_labels", "cmf_set_clustering", "cmf_set_regfull", "cmf_set_exclusion", "cmf_run", "cmf_sync", "cmf_run_host", "cmf_download",
+    "cmf_upload_bil", "cmf_upload_lines", "cmf_upload_wait", "cmf_bind_device_slab", "cmf_set_labels", "cmf_set_clustering", "cmf_set_regfull", "cmf_set_exclusion", "cmf_run", "cmf_sync", "cmf_run_host", "cmf_download",
     "cmf_device_ptr", "cmf_output_bytes", "cmf_kernel_count", "cmf_kernel_name", "cmf_kernel_times",
     "cmf_launch_count", "cmf_screen_kernel", "cmf_host_alloc", "cmf_host_free", "cmf_host_register", "cmf_host_unregister",
     "cmf_pixel_flags", "cmf_column_profile", "cmf_column_profile_image",
@@ -71,6 +71,7 @@ def load():
         "cmf_set_problem": (C.c_int, [vp, C.POINTER(Problem)]),
         "cmf_upload_bil": (C.c_int, [vp, vp]),
         "cmf_upload_lines": (C.c_int, [vp, vp, i32, i32, i32, i32]),
+        "cmf_upload_wait": (C.c_int, [vp, vp]),
         "cmf_bind_device_slab": (C.c_int, [vp, vp, i64, i32]),
         "cmf_set_labels": (C.c_int, [vp, vp, C.c_int, C.c_int]),
         "cmf_set_clustering": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -116,7 +116,9 @@ class ColumnwiseMF(object):
                 l1 = min(self.L, l0 + nb)
                 k = i % 2
                 if i >= 2:
-                    self.sync()                      # the copy that last used this buffer has finished
+                    # only the copy that last read THIS staging block has to be done (an event per block); the copy
+                    # of the other block, enqueued after it, stays in flight while this block is refilled from disk
+                    self._check(self._lib.cmf_upload_wait(self._ctx, C.c_void_p(ptrs[k])))
                 np.copyto(views[k][:l1 - l0], cube_lbs[l0:l1, lo - 1:hi, :], casting="same_kind")
                 self._check(self._lib.cmf_upload_lines(self._ctx, C.c_void_p(ptrs[k]), l0, l1 - l0, lo, self.D))
             self.sync()

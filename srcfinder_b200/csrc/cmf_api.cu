@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/cmf_b200.h"
@@ -65,7 +66,7 @@ struct cmf_ctx {
     int kmodes = 1, reject_min = 0;
     int32_t* labels_d = nullptr;
     int8_t* entries = nullptr;
-    uint32_t* rejmask = nullptr;
+    uint32_t *rejmask = nullptr, *flagmask = nullptr;
     int *nentries = nullptr, *nuse = nullptr;
     uint8_t *sel = nullptr, *inlier = nullptr;
     int16_t *cluster_img = nullptr, *alpha_img = nullptr;
@@ -87,6 +88,7 @@ struct cmf_ctx {
     std::vector<std::vector<cudaEvent_t>> ev_sets;  // one set of K_COUNT+1 events per timed run
     int timed_runs = 0;                             // timed runs recorded since the last cmf_kernel_times()
     std::vector<cudaEvent_t> blk_ev;
+    std::vector<std::pair<const void*, cudaEvent_t>> stage_ev;   // one event per staging block of cmf_upload_lines
     bool timed = false;
     bool screened = false;                          // the last run used the screening path
     int launches = 0;
@@ -376,12 +378,12 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
                               ctx->km_iters, st);
             ctx->launches += 4;
         }
-        launch_modes(d, ctx->labels_d, ctx->mask, ctx->reject_min, ctx->entries, ctx->rejmask, ctx->nentries, st);
+        launch_modes(d, ctx->labels_d, ctx->mask, ctx->reject_min, ctx->entries, ctx->rejmask, ctx->nentries, ctx->flagmask, st);
         launch_fill_f64(ctx->mf, (long long)LS, ctx->nodata, st);
         CK(cudaMemsetAsync(ctx->alpha_img, 0, LS * sizeof(int16_t), st));
         ctx->launches += 3;
         for (int t = 0; t < ctx->kmodes; ++t) {
-            launch_members(d, ctx->labels_d, ctx->mask, t, ctx->entries, ctx->rejmask, ctx->sel,
+            launch_members(d, ctx->labels_d, ctx->mask, t, ctx->entries, ctx->rejmask, ctx->flagmask, ctx->sel,
                            t == 0 ? ctx->cluster_img : nullptr, ctx->inlier, st);
             launch_repack(d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, 0, d.L,
                           ctx->sel, 0, st);
@@ -503,6 +505,7 @@ void cmf_destroy(cmf_ctx* ctx) {
     for (int i = 0; i <= K_COUNT; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (auto& set : ctx->ev_sets) for (cudaEvent_t e : set) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->blk_ev) cudaEventDestroy(e);
+    for (auto& pe : ctx->stage_ev) cudaEventDestroy(pe.second);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -660,6 +663,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     A_(dalloc(ctx, &ctx->nuse, (size_t)d.S));
     A_(dalloc(ctx, &ctx->nentries, (size_t)d.S));
     A_(dalloc(ctx, &ctx->rejmask, (size_t)d.S));
+    A_(dalloc(ctx, &ctx->flagmask, (size_t)d.S));
     A_(dalloc(ctx, &ctx->entries, (size_t)d.S * kMaxLabels));
     if (ctx->can_screen) {
         A_(dalloc(ctx, &ctx->Ws, (size_t)d.S * 2 * d.NT16 * d.NT * 32 * 4));
@@ -717,6 +721,23 @@ int cmf_upload_lines(cmf_ctx* ctx, const float* host_block, int32_t line0, int32
                          (size_t)block_bands * d.S * sizeof(float), width, (size_t)nlines, cudaMemcpyHostToDevice,
                          ctx->stream));
     ctx->have_input = true;     // the caller is responsible for handing in every line before cmf_run()
+    // an event behind this copy, keyed by the staging block, for cmf_upload_wait()
+    cudaEvent_t ev = nullptr;
+    for (auto& pe : ctx->stage_ev) if (pe.first == host_block) ev = pe.second;
+    if (!ev) {
+        if (ctx->stage_ev.size() >= 16) { ev = ctx->stage_ev.front().second; ctx->stage_ev.erase(ctx->stage_ev.begin()); }
+        else CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->stage_ev.emplace_back(host_block, ev);
+    }
+    CK(cudaEventRecord(ev, ctx->stream));
+    return CMF_OK;
+}
+
+int cmf_upload_wait(cmf_ctx* ctx, const float* host_block) {
+    if (!ctx) return CMF_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    for (auto& pe : ctx->stage_ev)
+        if (pe.first == host_block) CK(cudaEventSynchronize(pe.second));
     return CMF_OK;
 }
 

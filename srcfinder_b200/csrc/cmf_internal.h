@@ -120,9 +120,9 @@ void launch_score(const Dims& d, const float* slab, const uint8_t* mask, const d
                   const int* status, double nodata, double* mf, double* stat_part, int nlanes,
                   int lines_per_cta, const uint8_t* sel, const int* mindex, int16_t* alpha_img, cudaStream_t st);
 void launch_modes(const Dims& d, const int32_t* labels, const uint8_t* mask, int reject_min, int8_t* entries,
-                  uint32_t* rejmask, int* nentries, cudaStream_t st);
+                  uint32_t* rejmask, int* nentries, uint32_t* flagmask, cudaStream_t st);
 void launch_members(const Dims& d, const int32_t* labels, const uint8_t* mask, int t, const int8_t* entries,
-                    const uint32_t* rejmask, uint8_t* sel, int16_t* cluster_img, uint8_t* inlier,
+                    const uint32_t* rejmask, const uint32_t* flagmask, uint8_t* sel, int16_t* cluster_img, uint8_t* inlier,
                     cudaStream_t st);
 void launch_fill_f64(double* p, long long n, double v, cudaStream_t st);
 // PCA projection (P, lam = eigenvectors / eigenvalues of the column covariance, launch_eigen target 1) + k-means

@@ -20,7 +20,7 @@ namespace cmf {
 __global__ void __launch_bounds__(256)
     modes_kernel(const int32_t* __restrict__ labels, const uint8_t* __restrict__ mask, int L, int S,
                  int reject_min, int8_t* __restrict__ entries, uint32_t* __restrict__ rejmask,
-                 int* __restrict__ nentries) {
+                 int* __restrict__ nentries, uint32_t* __restrict__ flagmask) {
     __shared__ int cnt[kMaxLabels];
     const int s = blockIdx.x, tid = threadIdx.x;
     if (tid < kMaxLabels) cnt[tid] = 0;
@@ -48,6 +48,9 @@ __global__ void __launch_bounds__(256)
             if (flag) { rej |= 1u << l; ++nneg; }
             list[ne++] = (int8_t)(flag ? -l : l);
         }
+        // _bgmeta band 0 is written inside the counting loop (:326-327), i.e. with the negated ids even when the
+        // rejection is undone afterwards: keep the as-flagged set for the cluster image
+        flagmask[s] = rej;
         if (ne > 0 && nneg == ne) {            // all clusters rejected: proceed without rejection (:330-332)
             rej = 0u;
             for (int t = 0; t < ne; ++t) list[t] = (int8_t)(-list[t]);
@@ -62,7 +65,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     members_kernel(const int32_t* __restrict__ labels, const uint8_t* __restrict__ mask, long long LS, int S,
                    int t, const int8_t* __restrict__ entries, const uint32_t* __restrict__ rejmask,
-                   uint8_t* __restrict__ sel, int16_t* __restrict__ cluster_img, uint8_t* __restrict__ inlier) {
+                   const uint32_t* __restrict__ flagmask, uint8_t* __restrict__ sel, int16_t* __restrict__ cluster_img,
+                   uint8_t* __restrict__ inlier) {
     const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= LS) return;
     const int s = (int)(o % S);
@@ -76,7 +80,8 @@ __global__ void __launch_bounds__(256)
     if (known && e != kModeNone) member = (e >= 0) ? (lab == e && !rejected) : !rejected;
     sel[o] = member ? 1 : 0;
     if (cluster_img != nullptr) {
-        cluster_img[o] = known ? (int16_t)(rejected ? -lab : lab) : (int16_t)0;
+        const bool flagged = known && ((flagmask[s] >> lab) & 1u);
+        cluster_img[o] = known ? (int16_t)(flagged ? -lab : lab) : (int16_t)0;
         inlier[o] = (known && !rejected) ? 1 : 0;
     }
 }
@@ -125,15 +130,15 @@ __global__ void __launch_bounds__(256)
 }
 
 void launch_modes(const Dims& d, const int32_t* labels, const uint8_t* mask, int reject_min, int8_t* entries,
-                  uint32_t* rejmask, int* nentries, cudaStream_t st) {
-    modes_kernel<<<d.S, 256, 0, st>>>(labels, mask, d.L, d.S, reject_min, entries, rejmask, nentries);
+                  uint32_t* rejmask, int* nentries, uint32_t* flagmask, cudaStream_t st) {
+    modes_kernel<<<d.S, 256, 0, st>>>(labels, mask, d.L, d.S, reject_min, entries, rejmask, nentries, flagmask);
 }
 
 void launch_members(const Dims& d, const int32_t* labels, const uint8_t* mask, int t, const int8_t* entries,
-                    const uint32_t* rejmask, uint8_t* sel, int16_t* cluster_img, uint8_t* inlier,
+                    const uint32_t* rejmask, const uint32_t* flagmask, uint8_t* sel, int16_t* cluster_img, uint8_t* inlier,
                     cudaStream_t st) {
     const long long LS = (long long)d.L * d.S;
-    members_kernel<<<(unsigned)((LS + 255) / 256), 256, 0, st>>>(labels, mask, LS, d.S, t, entries, rejmask, sel,
+    members_kernel<<<(unsigned)((LS + 255) / 256), 256, 0, st>>>(labels, mask, LS, d.S, t, entries, rejmask, flagmask, sel,
                                                                  cluster_img, inlier);
 }
 

@@ -38,6 +38,15 @@ namespace cmf {
 namespace {
 
 constexpr int kT5Threads = 512;
+// register budgets after setmaxnreg (4 control warps, 4 convert/square warps, 8 epilogue warps; the sum
+// 4 a + 4 b + 8 c may not exceed 2048): the epilogue keeps 112 per-alpha accumulators per thread
+#ifndef CMF_S5_REGS_CTL
+#define CMF_S5_REGS_CTL 40
+#define CMF_S5_REGS_CVT 104
+#define CMF_S5_REGS_EPI 184
+#endif
+#define CMF_STR2(x) #x
+#define CMF_STR(x) CMF_STR2(x)
 constexpr int kT5Stages = 3;       // 64-row half tiles in flight
 constexpr int kT5HalfRows = 64;
 
@@ -216,7 +225,7 @@ __global__ void __launch_bounds__(kT5Threads, 1)
 
     const int wg = warp >> 2;
     if (wg == 0) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " CMF_STR(CMF_S5_REGS_CTL) ";");
         if (warp == 0 && lane == 0) {
             // ---------------- producer: tables once, then 64-row half tiles through the ring
             mbar_expect_tx(&bars[B_TAB], p.tab_bytes);
@@ -282,7 +291,7 @@ __global__ void __launch_bounds__(kT5Threads, 1)
         }
         __syncwarp();
     } else if (wg == 1) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " CMF_STR(CMF_S5_REGS_CVT) ";");
         // ---------------- convert (x -> xh|xl) and square (y -> zh|zl): thread = pixel = TMEM lane
         const int q = warp & 3, row = 32 * q + lane, myhalf = q >> 1, rin = row & (kT5HalfRows - 1);
         const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16);
@@ -358,7 +367,7 @@ __global__ void __launch_bounds__(kT5Threads, 1)
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " CMF_STR(CMF_S5_REGS_EPI) ";");
         // ---------------- epilogue: thread = pixel, one half of the alphas, per-alpha sums in registers
         const int q = warp & 3, half = (warp - 8) >> 2;
         const int ntile = half ? nt_b : nt_a;

@@ -55,20 +55,26 @@ def gather_column_tiles(tile, samples, dst=0, group=None):
     return out
 
 
-def gather_flightlines(tile, nflight, mine, dst=0, group=None):
+def gather_flightlines(tile, nflight, mine, dst=0, group=None, device=None):
     """Batch mode: every rank holds the score images of its own flightlines (list of (L, S) tensors, one
-    per index in `mine`); rank `dst` receives all `nflight` images in order."""
+    per index in `mine`, possibly empty when there are fewer flightlines than ranks); rank `dst` receives all
+    `nflight` images in order."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     per = max(len(flightline_shard(nflight, world, r)) for r in range(world))
-    L, S = tile[0].shape if tile else (0, 0)
-    shape = torch.tensor([L, S], dtype=torch.int64, device=tile[0].device if tile else None)
-    stack = tile[0].new_zeros((per, L, S)) if tile else None
+    dev = tile[0].device if tile else (torch.device(device) if device is not None else torch.device("cpu"))
+    # image shape and dtype from a rank that owns a flightline (rank 0 always does when nflight >= 1)
+    info = torch.tensor([tile[0].shape[0], tile[0].shape[1], 1 if tile[0].dtype == torch.float64 else 0]
+                        if tile else [0, 0, 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(info, op=dist.ReduceOp.MAX, group=group)
+    L, S = int(info[0]), int(info[1])
+    dtype = torch.float64 if int(info[2]) else torch.float32
+    stack = torch.zeros((per, L, S), dtype=dtype, device=dev)
     for i, t in enumerate(tile):
         stack[i] = t
-    recv = [stack.new_empty((per, L, S)) for _ in range(world)] if rank == dst else None
+    recv = [torch.empty((per, L, S), dtype=dtype, device=dev) for _ in range(world)] if rank == dst else None
     dist.gather(stack, recv, dst=dst, group=group)
     if rank != dst:
         return None

@@ -85,9 +85,11 @@ def open_memmap(data_path, meta=None, writable=False):
 def create_image(data_path, meta):
     """Write ``data_path + '.hdr'`` and allocate a zero-filled image; returns a writable memmap."""
     meta = dict(meta)
-    meta.setdefault("header offset", 0)
+    # a product never inherits the input's header offset or byte order (spectral's create_image writes native
+    # byte order at offset 0 whatever the metadata copied from the input file said, cmf/robust_mf.py:210-263)
+    meta["header offset"] = 0
+    meta["byte order"] = 0
     meta.setdefault("file type", "ENVI Standard")
-    meta.setdefault("byte order", 0)
     write_header(data_path + ".hdr", meta)
     nbytes = int(np.prod(image_shape(meta))) * image_dtype(meta).itemsize
     with open(data_path, "wb") as fh:

@@ -52,6 +52,15 @@ def _worker(rank, world, port, tmp):
     mine = cdist.flightline_shard(3, world, rank)
     tiles = [torch.from_numpy(orc.cmf_cube(synth.make_cube(120, 3, seed=90 + f), ab, active)["mf"]) for f in mine]
     batch = cdist.gather_flightlines(tiles, 3, mine, dst=0)
+    # (iii) fewer flightlines than ranks: rank 1 owns none and still takes part in the collective
+    lone = cdist.flightline_shard(1, world, rank)
+    lone_tiles = [tiles[0]] if (rank == 0 and lone) else []
+    single = cdist.gather_flightlines(lone_tiles, 1, lone, dst=0)
+    if rank == 0:
+        assert len(single) == 1 and torch.equal(single[0], tiles[0])
+        assert lone == [0]
+    else:
+        assert lone == [] and single is None
     if rank == 0:
         ref = orc.cmf_cube(cube, ab, active)["mf"]
         np.save(os.path.join(tmp, "ok.npy"), np.array([

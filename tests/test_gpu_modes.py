@@ -153,3 +153,32 @@ def test_c3_robust_flightline_with_rejection():
         assert np.array_equal(ok, r1["mf"][:, c0 + j] != -9999.0)
         err = np.max(np.abs(ref["mf"][ok, j] - r1["mf"][ok, c0 + j])) / np.std(ref["mf"][ok, j])
         assert err < 1e-6
+
+
+def test_all_clusters_rejected_keeps_flagged_ids_in_bgmeta():
+    """When every cluster of a column is below bgminsamp (possible only without a label 0: -0 == 0 never flips,
+    cmf/robust_mf.py:323-324) the reference warns, proceeds WITHOUT rejection (:330-332) -- but _bgmeta band 0 was
+    already written with the negated ids inside the counting loop (:326-327).  Scores as if nothing was rejected,
+    cluster image with negative ids."""
+    L, S = 400, 3
+    cube = synth.make_cube(L, S, seed=95)
+    active = [351, 422]
+    ab = synth.load_ch4_library()[active[0] - 1:active[1], 2]
+    labels = np.ones((L, S), dtype=np.int32)
+    labels[L // 2:, :] = 2
+    labels[:, 2] = np.where(np.arange(L) < 150, 0, 1)           # a column WITH label 0: ordinary rejection rules
+    big = 10 * L                                                 # every cluster is "too small"
+    got = cmf_cube(cube, ab, active, labels=labels, reject_min=big)
+    ref = orc.cmf_cube(cube, ab, active, labels=labels, reject_min=big)
+    free = cmf_cube(cube, ab, active, labels=labels, reject_min=0)
+    assert np.array_equal(got["mf"] == -9999.0, ref["mf"] == -9999.0)
+    for c in range(S):
+        ok = ref["mf"][:, c] != -9999.0
+        err = np.max(np.abs(got["mf"][ok, c] - ref["mf"][ok, c])) / np.std(ref["mf"][ok, c])
+        assert err <= 1e-6
+    # columns 0, 1: all rejected -> scored like the run without rejection, ids negative in the image
+    assert np.array_equal(got["mf"][:, :2], free["mf"][:, :2])
+    assert np.array_equal(got["cluster_id"][:, :2], -labels[:, :2])
+    # column 2: label 0 survives, label 1 is rejected (negative id, scores stay nodata)
+    assert np.array_equal(got["cluster_id"][:, 2], np.where(labels[:, 2] == 1, -1, 0))
+    assert np.all(got["mf"][labels[:, 2] == 1, 2] == -9999.0)
