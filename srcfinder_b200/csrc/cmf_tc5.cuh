@@ -91,6 +91,20 @@ __device__ __forceinline__ uint32_t tf32_round(float x) { return (__float_as_uin
 __device__ __forceinline__ uint32_t tf32_trunc(float x) { return __float_as_uint(x) & 0xffffe000u; }
 
 
+// One lane of a CONVERGED warp (elect.sync).  The MMA issuer warps run their loops with all 32 lanes and issue under
+// this predicate: with uniform control flow the descriptors stay in uniform registers, whereas a loop entered by
+// lane 0 alone makes the compiler wrap every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence
+// (measured: ~108 cycles per MMA issued against ~45 cycles of tensor work, profiles/r02_screen5_issue.md).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n.reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P1;\n}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] . B[smem]^T, kind::i8 (signed 8-bit operands, 32-bit integer accumulators), one thread issues
 __device__ __forceinline__ void mma_ss_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {

@@ -79,27 +79,27 @@ __global__ void __launch_bounds__(kG8Threads, 1)
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t sbase = smem_u32(smem_raw);
-            constexpr uint32_t lbo = 128 * 16, sbo = 128;
-            const uint32_t id = idesc_i8(128);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int slot = kb % kG8Stages, use = kb / kG8Stages;
-                mbar_wait_guard(&bars[slot], (uint32_t)(use & 1));
-                tc_fence_after();
-                const uint32_t st = sbase + slot * kG8Stage;
+        // MMA issuer: the whole warp runs the loop, one elected lane issues (see elect_one())
+        const uint32_t sbase = smem_u32(smem_raw);
+        constexpr uint32_t lbo = 128 * 16, sbo = 128;
+        const uint32_t id = idesc_i8(128);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int slot = kb % kG8Stages, use = kb / kG8Stages;
+            mbar_wait_guard(&bars[slot], (uint32_t)(use & 1));
+            tc_fence_after();
+            const uint32_t st = sbase + slot * kG8Stage;
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {                 // 32 lines = two 16-line chunks per MMA
-                    const uint64_t da = smem_desc(st + ks * 2 * lbo, lbo, sbo);
-                    for (int jj = 0; jj < nj; ++jj) {
-                        const uint64_t db = smem_desc(st + (1 + jj) * kG8Tile + ks * 2 * lbo, lbo, sbo);
-                        mma_ss_i8(tmem + 128 * jj, da, db, id, (kb > 0 || ks > 0) ? 1u : 0u);
-                    }
+            for (int ks = 0; ks < 2; ++ks) {                 // 32 lines = two 16-line chunks per MMA
+                const uint64_t da = smem_desc(st + ks * 2 * lbo, lbo, sbo);
+#pragma unroll
+                for (int jj = 0; jj < kG8MaxNJ; ++jj) {
+                    const uint64_t db = smem_desc(st + (1 + jj) * kG8Tile + ks * 2 * lbo, lbo, sbo);
+                    if (jj < nj && elect_one()) mma_ss_i8(tmem + 128 * jj, da, db, id, (kb > 0 || ks > 0) ? 1u : 0u);
                 }
-                tc_commit(&bars[kG8Stages + slot]);              // the stage is free once these MMAs have read it
             }
-            tc_commit(&bars[2 * kG8Stages]);
+            if (elect_one()) tc_commit(&bars[kG8Stages + slot]);     // the stage is free once these MMAs have read it
         }
+        if (elect_one()) tc_commit(&bars[2 * kG8Stages]);
         __syncwarp();
     } else {
         // ---------------- epilogue: TMEM lane = digit s * 32 + band i, column = 128 jj + digit t * 32 + band j

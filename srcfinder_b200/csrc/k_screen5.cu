@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(kT5Threads, 1)
                 bulk_g2s(ring + slot * kT5HalfRows * DP, col_base + (long long)h * kT5HalfRows * DP, bytes,
                          &bars[B_XFULL + slot]);
             }
-        } else if (warp == 1 && lane == 0) {
-            // ---------------- MMA issuer
+        } else if (warp == 1) {
+            // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues (see elect_one())
             const uint32_t sbase = smem_u32(smem_raw);
             const uint32_t lbo1 = N1 * 16, lbo2 = (uint32_t)NA * 16;
             const uint32_t id1 = idesc_tf32(N1), id2a = idesc_tf32(NA_a), id2b = idesc_tf32(NA_b > 0 ? NA_b : 16);
@@ -258,11 +258,13 @@ __global__ void __launch_bounds__(kT5Threads, 1)
                 for (int ks = 0; ks < NT; ++ks) {
                     const uint64_t dh = smem_desc(sbase + p.ph_off + 2 * ks * lbo1, lbo1, 128);
                     const uint64_t dl = smem_desc(sbase + p.pl_off + 2 * ks * lbo1, lbo1, 128);
-                    mma_ts_tf32(tmem + C_Y, tmem + C_XH + 8 * ks, dh, id1, ks > 0);
-                    mma_ts_tf32(tmem + C_Y, tmem + C_XL + 8 * ks, dh, id1, 1);
-                    mma_ts_tf32(tmem + C_Y, tmem + C_XH + 8 * ks, dl, id1, 1);
+                    if (elect_one()) {
+                        mma_ts_tf32(tmem + C_Y, tmem + C_XH + 8 * ks, dh, id1, ks > 0);
+                        mma_ts_tf32(tmem + C_Y, tmem + C_XL + 8 * ks, dh, id1, 1);
+                        mma_ts_tf32(tmem + C_Y, tmem + C_XH + 8 * ks, dl, id1, 1);
+                    }
                 }
-                tc_commit(&bars[B_G1]);
+                if (elect_one()) tc_commit(&bars[B_G1]);
                 mbar_wait_guard(&bars[B_ZREADY], ph);
                 if (t > 0) mbar_wait_guard(&bars[B_REMPTY], ph ^ 1u);
                 tc_fence_after();
@@ -270,22 +272,26 @@ __global__ void __launch_bounds__(kT5Threads, 1)
                 for (int ks = 0; ks < NT; ++ks) {
                     const uint64_t dh = smem_desc(sbase + p.wh_off + 2 * ks * lbo2, lbo2, 128);
                     const uint64_t dl = smem_desc(sbase + p.wl_off + 2 * ks * lbo2, lbo2, 128);
-                    mma_ts_tf32(tmem + C_R, tmem + C_Y + 8 * ks, dh, id2a, ks > 0);
-                    mma_ts_tf32(tmem + C_R, tmem + C_Y + 8 * ks, dl, id2a, 1);
-                    mma_ts_tf32(tmem + C_R, tmem + C_ZL + 8 * ks, dh, id2a, 1);
+                    if (elect_one()) {
+                        mma_ts_tf32(tmem + C_R, tmem + C_Y + 8 * ks, dh, id2a, ks > 0);
+                        mma_ts_tf32(tmem + C_R, tmem + C_Y + 8 * ks, dl, id2a, 1);
+                        mma_ts_tf32(tmem + C_R, tmem + C_ZL + 8 * ks, dh, id2a, 1);
+                    }
                 }
-                tc_commit(&bars[B_RFULL]);
+                if (elect_one()) tc_commit(&bars[B_RFULL]);
                 if (NA_b > 0) {
                     if (t > 0) { mbar_wait_guard(&bars[B_REMPTY + 1], ph ^ 1u); tc_fence_after(); }
 #pragma unroll 1
                     for (int ks = 0; ks < NT; ++ks) {
                         const uint64_t dh = smem_desc(sbase + p.wh_off + 2 * ks * lbo2 + NA_a * 16, lbo2, 128);
                         const uint64_t dl = smem_desc(sbase + p.wl_off + 2 * ks * lbo2 + NA_a * 16, lbo2, 128);
-                        mma_ts_tf32(tmem + C_R + NA_a, tmem + C_Y + 8 * ks, dh, id2b, ks > 0);
-                        mma_ts_tf32(tmem + C_R + NA_a, tmem + C_Y + 8 * ks, dl, id2b, 1);
-                        mma_ts_tf32(tmem + C_R + NA_a, tmem + C_ZL + 8 * ks, dh, id2b, 1);
+                        if (elect_one()) {
+                            mma_ts_tf32(tmem + C_R + NA_a, tmem + C_Y + 8 * ks, dh, id2b, ks > 0);
+                            mma_ts_tf32(tmem + C_R + NA_a, tmem + C_Y + 8 * ks, dl, id2b, 1);
+                            mma_ts_tf32(tmem + C_R + NA_a, tmem + C_ZL + 8 * ks, dh, id2b, 1);
+                        }
                     }
-                    tc_commit(&bars[B_RFULL + 1]);
+                    if (elect_one()) tc_commit(&bars[B_RFULL + 1]);
                 }
             }
         }
