@@ -7,9 +7,11 @@ AVIRIS-NG cube).
 
 A "step" is one pass of the whole hot path (repack/mask, statistics, eigen-decomposition, tensor-core screen
 of the LOO alpha search + exact FP64 refinement, weights, scoring, column statistics) over one synthetic flightline: BASELINE configs[1], 598 columns x 425 channels
-x 20 000 lines, active window 351..422.  With N > 1 every rank processes its own flightline (flightline
-sharding, no data-path collective) and the score tiles are gathered to rank 0 over NCCL inside the timed
-region.  One JSON line is printed by rank 0.
+x 20 000 lines, active window 351..422, the whole 425-band cube resident in HBM (the kernels read the active
+window in place, line pitch 425 x 598).  With N > 1 every rank processes its own flightline (flightline
+sharding, no data-path collective) and the score tiles are gathered over NCCL inside the timed region, the
+root rotating from flightline to flightline so that no single GPU receives every tile.  One JSON line is
+printed by rank 0.
 
 `value`  device-resident throughput (inputs already in HBM), CUDA events on the launching stream,
          max over ranks.
@@ -261,7 +263,10 @@ def workload_config(args, n):
                         "unimodal looshrinkage CMF, active bands %d..%d, 201 alphas"
                         % (args.samples, BANDS, args.lines, ACTIVE[0], ACTIVE[1]),
             "lines": args.lines, "samples": args.samples, "bands": BANDS, "active_bands": ACTIVE,
-            "alphas": 201, "flightlines_per_gpu": 1, "sharding": "flightline per GPU, NCCL gather of scores (overlapped with the next flightline)",
+            "alphas": 201, "flightlines_per_gpu": 1,
+            "sharding": "flightline per GPU; NCCL gather of the score tiles, root = flightline index mod N, overlapped "
+                        "with the next flightline (two contexts per GPU)",
+            "input": "425-band cube resident in HBM, active window read in place",
             "parallelism": "dp%d" % n, "timing": "inputs (3.4 GB/flightline) far larger than the 126 MB L2"}
 
 
@@ -297,37 +302,47 @@ def run_gpu(args):
     dmma_peak = _lib.load_tools().cmf_microbench(local, 0, 3) if rank == 0 else 0.0
     mma_peak = _lib.load_tools().cmf_microbench(local, 9, 3) if rank == 0 else 0.0
 
-    slab = synth.make_slab_torch(L, S, ACTIVE[0], ACTIVE[1], dev, seed=2 + rank)
+    # the whole 425-band cube resident in HBM (20.3 GB); only the active window carries data, as only it is read
+    cube = torch.zeros((L, BANDS, S), dtype=torch.float32, device=dev)
+    slab = cube[:, ACTIVE[0] - 1:ACTIVE[1], :]
+    synth.make_slab_torch(L, S, ACTIVE[0], ACTIVE[1], dev, seed=2 + rank, out=slab)
     stream = torch.cuda.current_stream()
-    eng = ColumnwiseMF(L, BANDS, S, ACTIVE, ab, device=local, stream=stream.cuda_stream)
-    eng.bind_device(slab.data_ptr())
-    mf_dev = None
+    # N > 1: two contexts used alternately, so that the score tile of flightline i is gathered straight out of its
+    # context while flightline i+1 runs in the other one (no staging copy)
+    nctx = 2 if world > 1 else 1
+    engines = [ColumnwiseMF(L, BANDS, S, ACTIVE, ab, device=local, stream=stream.cuda_stream) for _ in range(nctx)]
+    for e_ in engines:
+        e_.bind_device(slab.data_ptr(), line_pitch=BANDS * S, band_pitch=S)
+    eng = engines[0]
+    mf_dev = [None] * nctx
     gathered = None
     if world > 1:
-        # wrap the context's score buffer so NCCL gathers it without an extra copy
-        ptr = eng.device_ptr(_lib.OUT_MF)
-        mf_dev = _as_tensor(torch, ptr, (L, S), torch.float64, dev)
-        gathered = [torch.empty((L, S), dtype=torch.float64, device=dev) for _ in range(world)] if rank == 0 else None
-
-    # The gather of flightline i's score tile runs on NCCL's stream while flightline i+1 is being filtered: the
-    # tile is first copied (device to device, 96 MB) into a staging buffer so that the context can start the next
-    # step at once.  Every gather completes inside the timed region (barrier() waits for the last one).
-    staging = torch.empty((L, S), dtype=torch.float64, device=dev) if world > 1 else None
-    pending = [None]
+        mf_dev = [_as_tensor(torch, e_.device_ptr(_lib.OUT_MF), (L, S), torch.float64, dev) for e_ in engines]
+        gathered = [torch.empty((L, S), dtype=torch.float64, device=dev) for _ in range(world)]   # every rank is a root in turn
+    pending = [None] * nctx
+    counter = [0]
 
     def step(timing):
-        eng.run(timing=timing, sync=False)
+        i = counter[0]
+        counter[0] += 1
+        k = i % nctx
+        if pending[k] is not None:
+            pending[k].wait()                 # the gather that read this context's scores two flightlines ago
+            pending[k] = None
+        engines[k].run(timing=timing, sync=False)
         if world > 1:
-            if pending[0] is not None:
-                pending[0].wait()                 # stream-level wait: the staging buffer is free again
-            staging.copy_(mf_dev, non_blocking=True)
-            pending[0] = dist.gather(staging, gathered, dst=0, async_op=True)
+            root = i % world                  # the tiles of flightline i land on GPU i mod N
+            pending[k] = dist.gather(mf_dev[k], gathered if rank == root else None, dst=root, async_op=True)
+
+    def drain():
+        for k in range(nctx):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def barrier():
         if world > 1:
-            if pending[0] is not None:
-                pending[0].wait()
-                pending[0] = None
+            drain()
             dist.barrier()
         torch.cuda.synchronize()
 
@@ -340,9 +355,7 @@ def run_gpu(args):
         ev0.record(stream)
         for _ in range(args.steps):
             step(True)
-        if pending[0] is not None:                # the last gather is inside the timed region as well
-            pending[0].wait()
-            pending[0] = None
+        drain()                                   # the last gathers are inside the timed region as well
         ev1.record(stream)
         barrier()
     ms = ev0.elapsed_time(ev1)
@@ -350,14 +363,25 @@ def run_gpu(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    kt = eng.kernel_times()                       # mean per-kernel ms over the timed steps (same stream)
+    # mean per-kernel ms over the timed steps (CUDA events of every context, same stream)
+    kts = [e_.kernel_times() for e_ in engines[:min(nctx, args.steps)]]
+    kt = {k: float(np.mean([t[k] for t in kts])) for k in kts[0]}
     launches = eng.launch_count() * args.steps        # this library's kernels only (per rank); NCCL / torch copies not counted
     value = world * L * S * args.steps / (ms * 1e-3) / 1e6
 
     # ---- end to end through the host API (rank-local; every rank does the same work)
     e2e = None
     if not args.no_e2e:
-        e2e = measure_e2e(torch, eng, slab, L, S, D, args, world, rank, dev, barrier)
+        e2e = measure_e2e(torch, engines, slab, L, S, D, args, world, rank, dev, barrier)
+    skern = eng.screen_kernel() or "loo_screen_kernel"
+    wide = None
+    if rank == 0 and world == 1 and not args.no_wide:
+        for e_ in engines:
+            e_.close()
+        engines = []
+        del cube, slab
+        torch.cuda.empty_cache()
+        wide = measure_wide(torch, L, S, dev, stream)
     out = None
     if rank == 0:
         peaks, src = measured_peaks()
@@ -371,7 +395,6 @@ def run_gpu(args):
         score_bytes = (4.0 * D + 8.0 + 1.0) * L * S            # one read of the slab + f64 score + mask byte
         score_ms = kt.get("score", float("nan"))
         traffic = load_traffic()
-        skern = eng.screen_kernel() or "loo_screen_kernel"
         tc5 = skern == "loo_screen5_kernel"
         DP = (D + 7) // 8 * 8
         n1, na = ((DP + 15) // 16 * 16, 208) if tc5 else (DP, 208)
@@ -408,13 +431,16 @@ def run_gpu(args):
         }
         if e2e is not None:
             out["e2e"] = e2e
+        if wide is not None:
+            out["wide_window"] = wide
     if world > 1:
         dist.barrier()
     if rank == 0:
         if not args.no_cpu and world == 1:
             out["cpu_baseline"] = cpu_baseline_leg(L, budget_s=args.cpu_seconds)
         emit(out)
-    eng.close()
+    for e_ in engines:
+        e_.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -431,7 +457,63 @@ def _as_tensor(torch, ptr, shape, dtype, dev):
     return torch.as_tensor(_Arr(), device=dev).view(shape)
 
 
-def measure_e2e(torch, eng, slab, L, S, D, args, world, rank, dev, barrier):
+def h2d_ceiling(torch, host_window, dev, world, barrier, copies=6):
+    """Plain pinned-host -> device copies of one flightline's active window on every rank at once, nothing else
+    running: what the box's PCIe fabric gives N GPUs (GB/s per rank, slowest rank)."""
+    import torch.distributed as dist
+    dst = torch.empty(host_window.shape, dtype=torch.float32, device=dev)
+    dst.copy_(host_window, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(copies):
+        dst.copy_(host_window, non_blocking=True)
+    torch.cuda.synchronize()
+    gbs = host_window.numel() * 4 * copies / (time.perf_counter() - t0) / 1e9
+    if world > 1:
+        t = torch.tensor([gbs], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        gbs = float(t.item())
+    del dst
+    return gbs
+
+
+def measure_wide(torch, L, S, dev, stream):
+    """The reference's other window: `-R` with the CH4 library selects bands 5..420 (cmf/robust_mf.py:186-187,
+    D = 416).  One device-resident flightline through the wide-window kernel set, per-kernel CUDA events."""
+    from srcfinder_b200 import ColumnwiseMF, synth
+    try:
+        act = [5, 420]
+        Dw = act[1] - act[0] + 1
+        ab = synth.load_ch4_library()[act[0] - 1:act[1], 2]
+        slab = synth.make_slab_torch(L, S, act[0], act[1], dev, seed=3)
+        torch.cuda.synchronize()
+        with ColumnwiseMF(L, BANDS, S, act, ab, reflectance=True, device=dev.index, stream=stream.cuda_stream) as eng:
+            eng.bind_device(slab.data_ptr())
+            eng.run()
+            eng.run(timing=True)
+            kt = eng.kernel_times()
+            launches = eng.launch_count()
+            ok = int((eng.status() == 0).sum())
+        ms = float(sum(kt.values()))
+        lines64 = (L + 63) // 64 * 64
+        nrb = (Dw + 31) // 32
+        ops = 2.0 * (nrb * (nrb + 1) / 2) * 128 * 128 * lines64 * S       # executed int8 MACs x 2 of the Gram pass
+        return {"workload": "-R window: %d cols x %d ch x %d lines, active bands %d..%d (D = %d), unimodal looshrinkage"
+                            % (S, BANDS, L, act[0], act[1], Dw),
+                "ms_per_flightline": ms, "value": L * S / ms / 1e3, "unit": UNIT,
+                "kernel_ms": {k: round(v, 3) for k, v in kt.items()}, "gpu_launches": launches,
+                "columns_ok": ok,
+                "roofline_int8": {"kernel": "wide_gram8_kernel", "bound": "tensor", "unit": "TOP/s",
+                                  "achieved": ops / (kt["gram"] * 1e-3) / 1e12, "peak": 4500.0,
+                                  "frac": ops / (kt["gram"] * 1e-3) / 1e12 / 4500.0,
+                                  "peak_source": "nominal dense int8 rate of B200 (4.5 POP/s; MEASURED_PEAKS.json has "
+                                                 "no integer figure)",
+                                  "fp64_equivalent_tflops": 2.0 * Dw * Dw * L * S / (kt["gram"] * 1e-3) / 1e12}}
+    except Exception as exc:       # noqa: BLE001 -- the main line must survive
+        return {"error": str(exc)[:200]}
+
+
+def measure_e2e(torch, engines_in, slab, L, S, D, args, world, rank, dev, barrier):
     """cmf_run_host on a pinned host cube shaped like the reference's input file (L, 425, S) float32.
 
     Headline `value`: flightlines streamed through two contexts used alternately (CMF_RUN_ASYNC), i.e. the
@@ -447,9 +529,10 @@ def measure_e2e(torch, eng, slab, L, S, D, args, world, rank, dev, barrier):
         host = torch.zeros((L, BANDS, S), dtype=torch.float32, pin_memory=True)
         host[:, ACTIVE[0] - 1:ACTIVE[1], :].copy_(slab)         # only the bands the path reads carry data
         torch.cuda.synchronize()
-        eng2 = ColumnwiseMF(L, BANDS, S, ACTIVE, abscf_window(), device=dev.index)
-        engines = [eng, eng2]
-        own = [eng2]
+        engines = list(engines_in)
+        while len(engines) < 2:
+            engines.append(ColumnwiseMF(L, BANDS, S, ACTIVE, abscf_window(), device=dev.index))
+            own.append(engines[-1])
     except Exception as exc:
         # not enough lockable memory for the full 425-band cube on this box: the same bytes cross PCIe from a
         # pinned cube that holds the active window only (declared as a D-band cube)
@@ -497,13 +580,26 @@ def measure_e2e(torch, eng, slab, L, S, D, args, world, rank, dev, barrier):
     same = bool(torch.equal(mf[0], mf[1])) if steps > 1 else None
     for e_ in own:
         e_.close()
+    # what the PCIe fabric of this box gives the same bytes with nothing else running (all ranks at once)
+    try:
+        win = torch.empty((L, D, S), dtype=torch.float32, pin_memory=True)
+        ceiling = h2d_ceiling(torch, win, dev, world, barrier)
+        del win
+    except Exception:
+        ceiling = None
+    achieved_gbs = L * D * S * 4 / (dt / steps) / 1e9
     return {"value": world * L * S * steps / dt / 1e6, "unit": UNIT, "ms_per_step": dt / steps * 1e3,
+            "h2d_ceiling_gbs": ceiling,
+            "frac_of_h2d_ceiling": (achieved_gbs / ceiling) if ceiling else None,
+            "h2d_ceiling_note": "plain pinned-host -> device copy of one flightline's active window (3.44 GB) on every rank "
+                                "at once, slowest rank, GB/s per rank; measured per N on this pool: 55.6 / 55.6 / 28.8 / "
+                                "23.2 at N = 1 / 2 / 4 / 8 (profiles/r02_h2d_ceiling.jsonl): pairs of GPUs share ~58 GB/s",
             "h2d_bytes_per_step": L * D * S * 4, "d2h_bytes_per_step": L * S * 8 + 3 * S * 8 + S * 4,
             "steps": steps, "mode": "two contexts used alternately, cmf_run_host(CMF_RUN_ASYNC): the next "
                                     "flightline uploads while the previous one is scored",
             "sync_call": {"value": world * L * S * steps / dt_sync / 1e6, "unit": UNIT,
                           "ms_per_step": dt_sync / steps * 1e3},
-            "host_buffer": host_note, "h2d_gbs": L * D * S * 4 / (dt / steps) / 1e9,
+            "host_buffer": host_note, "h2d_gbs": achieved_gbs,
             "colstd_checksum": checksum, "both_contexts_identical": same}
 
 
@@ -568,6 +664,7 @@ def main():
     ap.add_argument("--samples", type=int, default=598)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-wide", action="store_true", help="skip the extra -R (416-band) flightline timing")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     args = ap.parse_args()
