@@ -529,10 +529,10 @@ def measure_e2e(torch, engines_in, slab, L, S, D, args, world, rank, dev, barrie
         host = torch.zeros((L, BANDS, S), dtype=torch.float32, pin_memory=True)
         host[:, ACTIVE[0] - 1:ACTIVE[1], :].copy_(slab)         # only the bands the path reads carry data
         torch.cuda.synchronize()
-        engines = list(engines_in)
-        while len(engines) < 2:
-            engines.append(ColumnwiseMF(L, BANDS, S, ACTIVE, abscf_window(), device=dev.index))
-            own.append(engines[-1])
+        # two contexts with their OWN streams (the device-resident contexts above share torch's stream): the upload of
+        # flightline i+1 must not queue behind the kernels of flightline i
+        engines = [ColumnwiseMF(L, BANDS, S, ACTIVE, abscf_window(), device=dev.index) for _ in range(2)]
+        own = list(engines)
     except Exception as exc:
         # not enough lockable memory for the full 425-band cube on this box: the same bytes cross PCIe from a
         # pinned cube that holds the active window only (declared as a D-band cube)
