@@ -263,9 +263,10 @@ def workload_config(args, n):
                         "unimodal looshrinkage CMF, active bands %d..%d, 201 alphas"
                         % (args.samples, BANDS, args.lines, ACTIVE[0], ACTIVE[1]),
             "lines": args.lines, "samples": args.samples, "bands": BANDS, "active_bands": ACTIVE,
-            "alphas": 201, "flightlines_per_gpu": 1,
-            "sharding": "flightline per GPU; NCCL gather of the score tiles, root = flightline index mod N, overlapped "
-                        "with the next flightline (two contexts per GPU)",
+            "alphas": 201, "flightlines_per_gpu": 1 if args.shard == "flightline" else "1/%d (column range)" % n,
+            "sharding": ("flightline per GPU; NCCL gather of the score tiles, root = flightline index mod N, overlapped "
+                         "with the next flightline (two contexts per GPU)") if args.shard == "flightline" else
+                        "one flightline per step, contiguous even-aligned column ranges per GPU, NCCL gather of the tiles",
             "input": "425-band cube resident in HBM, active window read in place",
             "parallelism": "dp%d" % n, "timing": "inputs (3.4 GB/flightline) far larger than the 126 MB L2"}
 
@@ -310,15 +311,28 @@ def run_gpu(args):
     # N > 1: two contexts used alternately, so that the score tile of flightline i is gathered straight out of its
     # context while flightline i+1 runs in the other one (no staging copy)
     nctx = 2 if world > 1 else 1
-    engines = [ColumnwiseMF(L, BANDS, S, ACTIVE, ab, device=local, stream=stream.cuda_stream) for _ in range(nctx)]
+    by_columns = args.shard == "columns" and world > 1
+    s0, s1 = (0, S)
+    if by_columns:
+        # ONE flightline per step for the whole job: every rank filters its own column range of the same cube in
+        # place (columns are independent problems, cmf/robust_mf.py:297) and the tiles are gathered
+        from srcfinder_b200.dist import column_shard_even
+        s0, s1 = column_shard_even(S, world, rank)
+        wmax = max(column_shard_even(S, world, r)[1] - column_shard_even(S, world, r)[0] for r in range(world))
+    Sg = s1 - s0
+    engines = [ColumnwiseMF(L, BANDS, Sg, ACTIVE, ab, device=local, stream=stream.cuda_stream) for _ in range(nctx)]
     for e_ in engines:
-        e_.bind_device(slab.data_ptr(), line_pitch=BANDS * S, band_pitch=S)
+        e_.bind_device(slab.data_ptr() + 4 * s0, line_pitch=BANDS * S, band_pitch=S)
     eng = engines[0]
     mf_dev = [None] * nctx
     gathered = None
+    pad = None
     if world > 1:
-        mf_dev = [_as_tensor(torch, e_.device_ptr(_lib.OUT_MF), (L, S), torch.float64, dev) for e_ in engines]
-        gathered = [torch.empty((L, S), dtype=torch.float64, device=dev) for _ in range(world)]   # every rank is a root in turn
+        mf_dev = [_as_tensor(torch, e_.device_ptr(_lib.OUT_MF), (L, Sg), torch.float64, dev) for e_ in engines]
+        gw = wmax if by_columns else S
+        gathered = [torch.empty((L, gw), dtype=torch.float64, device=dev) for _ in range(world)]   # every rank is a root in turn
+        if by_columns and Sg != wmax:
+            pad = [torch.zeros((L, wmax), dtype=torch.float64, device=dev) for _ in range(nctx)]
     pending = [None] * nctx
     counter = [0]
 
@@ -332,7 +346,11 @@ def run_gpu(args):
         engines[k].run(timing=timing, sync=False)
         if world > 1:
             root = i % world                  # the tiles of flightline i land on GPU i mod N
-            pending[k] = dist.gather(mf_dev[k], gathered if rank == root else None, dst=root, async_op=True)
+            send = mf_dev[k]
+            if pad is not None:                # shards narrower than the widest one are padded (12 MB copy)
+                pad[k][:, :Sg].copy_(mf_dev[k], non_blocking=True)
+                send = pad[k]
+            pending[k] = dist.gather(send, gathered if rank == root else None, dst=root, async_op=True)
 
     def drain():
         for k in range(nctx):
@@ -367,11 +385,12 @@ def run_gpu(args):
     kts = [e_.kernel_times() for e_ in engines[:min(nctx, args.steps)]]
     kt = {k: float(np.mean([t[k] for t in kts])) for k in kts[0]}
     launches = eng.launch_count() * args.steps        # this library's kernels only (per rank); NCCL / torch copies not counted
-    value = world * L * S * args.steps / (ms * 1e-3) / 1e6
+    jobs = 1 if by_columns else world             # flightlines finished per step by the whole job
+    value = jobs * L * S * args.steps / (ms * 1e-3) / 1e6
 
     # ---- end to end through the host API (rank-local; every rank does the same work)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not by_columns:
         e2e = measure_e2e(torch, engines, slab, L, S, D, args, world, rank, dev, barrier)
     skern = eng.screen_kernel() or "loo_screen_kernel"
     wide = None
@@ -388,23 +407,23 @@ def run_gpu(args):
         # dominant kernel: the tensor-core screening pass of the alpha search.  Algorithmic work per pixel
         # (SURVEY 8(d)): the projection 2 D^2 plus the alpha contraction 2 D A; the kernel executes three
         # TF32 products per FP64-equivalent product (hi/lo splits), which is not counted as useful work.
-        flops = (2.0 * D * D + 2.0 * D * 201) * L * S
+        flops = (2.0 * D * D + 2.0 * D * 201) * L * Sg
         screen_ms = kt.get("screen", float("nan"))
         achieved = flops / (screen_ms * 1e-3) / 1e12
         tf32_peak = 0.5 * float(peaks.get("bf16_tflops", 1590.0))
-        score_bytes = (4.0 * D + 8.0 + 1.0) * L * S            # one read of the slab + f64 score + mask byte
+        score_bytes = (4.0 * D + 8.0 + 1.0) * L * Sg            # one read of the slab + f64 score + mask byte
         score_ms = kt.get("score", float("nan"))
         traffic = load_traffic()
         tc5 = skern == "loo_screen5_kernel"
         DP = (D + 7) // 8 * 8
         n1, na = ((DP + 15) // 16 * 16, 208) if tc5 else (DP, 208)
-        executed = 3.0 * (2.0 * DP * n1 + 2.0 * DP * na) * L * S / (screen_ms * 1e-3) / 1e12
+        executed = 3.0 * (2.0 * DP * n1 + 2.0 * DP * na) * L * Sg / (screen_ms * 1e-3) / 1e12
         pipe = ("tcgen05.mma kind::tf32 (SASS UTCMMA), accumulators in TMEM" if tc5 else
                 "mma.sync (SASS HMMA), whose measured ceiling in this run is %.0f TFLOP/s" % mma_peak)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if by_columns else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world),
             "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
             "roofline": {"kernel": skern, "bound": "tensor", "achieved": achieved, "peak": tf32_peak,
@@ -417,7 +436,7 @@ def run_gpu(args):
                          "flops_per_launch": flops, "executed_tflops": executed,
                          "executed_frac": executed / tf32_peak, "mma_sync_tf32_peak": mma_peak,
                          "share_of_step": screen_ms / max(sum(kt.values()), 1e-9)},
-            "roofline_fp64": {"kernel": "gram_kernel", "bound": "tensor", "achieved": D * (D + 8.0) * L * S
+            "roofline_fp64": {"kernel": "gram_kernel", "bound": "tensor", "achieved": D * (D + 8.0) * L * Sg
                               / (kt.get("gram", float("nan")) * 1e-3) / 1e12, "peak": dmma_peak, "unit": "TFLOP/s",
                               "peak_source": "FP64 DMMA.8x8x4 rate measured in this run (cmf_microbench kind 0)",
                               "note": "lower-triangle 8x8 tiles only: D(D+8) flop per pixel"},
@@ -665,6 +684,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-wide", action="store_true", help="skip the extra -R (416-band) flightline timing")
+    ap.add_argument("--shard", default="flightline", choices=["flightline", "columns"],
+                    help="N > 1: one flightline per rank and step (weak scaling, the contract's default) or ONE "
+                         "flightline per step split into column ranges (strong scaling, SURVEY 8(e)(i))")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     args = ap.parse_args()

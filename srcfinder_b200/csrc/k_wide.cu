@@ -353,8 +353,9 @@ __global__ void __launch_bounds__(256)
 // Householder reduction (EISPACK tred2 scheme, the one k_eigen.cu runs in shared memory) of the D x D matrix of
 // one column, in global memory / L2: one CTA per column, the leading block is kept fully symmetric so that
 // every pass reads whole rows (coalesced), then the accumulation of the transformations leaves Q in the matrix.
-constexpr int kWtThreads = 1024;
+constexpr int kWtThreads = 1024;      // largest shape (shared-memory plan of wide_eigen_fits)
 
+template <int NTHR>
 __device__ __forceinline__ double wt_block_sum(double v, double* red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -363,14 +364,15 @@ __device__ __forceinline__ double wt_block_sum(double v, double* red) {
     __syncthreads();
     double t = 0.0;
 #pragma unroll
-    for (int w = 0; w < kWtThreads / 32; ++w) t += red[w];
+    for (int w = 0; w < NTHR / 32; ++w) t += red[w];
     return t;
 }
 
-__global__ void __launch_bounds__(kWtThreads, 1)
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR, 1024 / NTHR)
     wide_tred_kernel(double* __restrict__ work, const int* __restrict__ n_g, int D, int DP, double* __restrict__ d_g,
                      double* __restrict__ e_g) {
-    constexpr int NW = kWtThreads / 32;
+    constexpr int NW = NTHR / 32;
     extern __shared__ double sm[];
     double* u = sm;              // [DP] Householder vector (row i)
     double* ev = u + DP;         // [DP] e / p / q vector
@@ -393,13 +395,13 @@ __global__ void __launch_bounds__(kWtThreads, 1)
         if (l > 0) {
             double part = 0.0;
             for (int k = tid; k <= l; k += blockDim.x) { const double v = a[(long long)i * LD + k]; u[k] = v; part += fabs(v); }
-            const double scale = wt_block_sum(part, red);
+            const double scale = wt_block_sum<NTHR>(part, red);
             if (scale == 0.0) {
                 if (tid == 0) ev[i] = u[l];
             } else {
                 part = 0.0;
                 for (int k = tid; k <= l; k += blockDim.x) { const double v = u[k] / scale; u[k] = v; part += v * v; }
-                h = wt_block_sum(part, red);
+                h = wt_block_sum<NTHR>(part, red);
                 const double f = u[l];
                 const double g = (f >= 0.0) ? -sqrt(h) : sqrt(h);
                 h -= f * g;
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(kWtThreads, 1)
                 __syncthreads();
                 part = 0.0;
                 for (int j = tid; j <= l; j += blockDim.x) part += ev[j] * u[j];
-                const double ff = wt_block_sum(part, red);
+                const double ff = wt_block_sum<NTHR>(part, red);
                 const double hh = ff / (h + h);
                 __syncthreads();
                 for (int j = tid; j <= l; j += blockDim.x) ev[j] -= hh * u[j];
@@ -656,12 +658,27 @@ __global__ void __launch_bounds__(kWrThreads, 1)
         if (cnt > 0 && tid < rows) {
             const double2* cr = rbuf + buf * DP;
             double f = q[m * rows + tid];
-            for (int t = 0; t < cnt; ++t) {
-                const int i = m - 1 - t;                     // rotation t acts on columns (i, i + 1)
-                const double2 cs = cr[t];
+            // the chain through f is two dependent FP64 operations per rotation; everything else (the rotation, the
+            // element it meets, s * z for the stored column) is loaded / formed eight rotations ahead of it
+            int t = 0;
+            for (; t + 8 <= cnt; t += 8) {
+                double2 cs[8];
+                double z[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { cs[k] = cr[t + k]; z[k] = q[(m - 1 - t - k) * rows + tid]; }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = m - 1 - t - k;             // rotation t + k acts on columns (i, i + 1)
+                    q[(i + 1) * rows + tid] = fma(cs[k].x, f, cs[k].y * z[k]);
+                    f = fma(cs[k].x, z[k], -(cs[k].y * f));
+                }
+            }
+            for (; t < cnt; ++t) {
+                const int i = m - 1 - t;
+                const double2 c1 = cr[t];
                 const double zi = q[i * rows + tid];
-                q[(i + 1) * rows + tid] = cs.y * zi + cs.x * f;
-                f = cs.x * zi - cs.y * f;
+                q[(i + 1) * rows + tid] = fma(c1.x, f, c1.y * zi);
+                f = fma(c1.x, zi, -(c1.y * f));
             }
             q[(m - cnt) * rows + tid] = f;
         }
@@ -955,9 +972,17 @@ void launch_wide_eigen(const Dims& d, const double* gram, const int* n, const do
     const int iter_cap = wide_iter_cap(d);
     wide_cov_kernel<<<d.S, 256, (size_t)3 * d.DP * sizeof(double), st>>>(gram, n, d.D, d.DP, mu, ctr, qexp, mode, work,
                                                                          dinv, slogT, status);
-    const size_t tsm = (size_t)(4 + kWtThreads / 32) * d.DP * sizeof(double);
-    cudaFuncSetAttribute(wide_tred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-    wide_tred_kernel<<<d.S, kWtThreads, tsm, st>>>(work, n, d.D, d.DP, dvec, evec);
+    int nthr = 1024;
+    if (const char* e = cmf_hook("CMF_WIDE_TRED")) nthr = atoi(e);      // tuning hook (tools build)
+    if (nthr == 512) {
+        const size_t tsm = (size_t)(4 + 512 / 32) * d.DP * sizeof(double);
+        cudaFuncSetAttribute(wide_tred_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        wide_tred_kernel<512><<<d.S, 512, tsm, st>>>(work, n, d.D, d.DP, dvec, evec);
+    } else {
+        const size_t tsm = (size_t)(4 + 1024 / 32) * d.DP * sizeof(double);
+        cudaFuncSetAttribute(wide_tred_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        wide_tred_kernel<1024><<<d.S, 1024, tsm, st>>>(work, n, d.D, d.DP, dvec, evec);
+    }
     wide_ql_kernel<<<d.S, 32, (size_t)2 * d.DP * sizeof(double), st>>>(dvec, evec, n, d.D, d.DP, rot, (long long)rot_cap,
                                                                        iters, iter_cap, niter, lam, status);
     const int rows = wide_rot_rows(d.DP);

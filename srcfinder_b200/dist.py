@@ -17,6 +17,14 @@ def column_shard(samples, world, rank):
     return s0, s1
 
 
+def column_shard_even(samples, world, rank):
+    """Like :func:`column_shard`, but every boundary is an even column (when ``samples`` is even): the shards of a
+    device-resident BIL cube then keep 8-byte aligned rows, which the fast repack and scoring kernels need."""
+    pairs = (int(samples) + 1) // 2
+    p0, p1 = column_shard(pairs, world, rank)
+    return min(2 * p0, int(samples)), min(2 * p1, int(samples))
+
+
 def flightline_shard(nflight, world, rank):
     """Round-robin flightline indices of rank `rank` (batch mode, BASELINE configs[3])."""
     return list(range(rank, int(nflight), int(world)))

@@ -78,3 +78,13 @@ def test_two_rank_shard_and_gather(tmp_path):
     ok = np.load(os.path.join(str(tmp_path), "ok.npy"))
     assert ok[0] == 1.0, "column-sharded gather differs from the unsharded result"
     assert ok[1] == 1.0, "flightline-sharded gather differs"
+
+
+def test_even_column_shards_cover_the_image():
+    for S in (598, 1242, 7, 16):
+        for world in (1, 2, 3, 4, 8):
+            sh = [cdist.column_shard_even(S, world, r) for r in range(world)]
+            assert sh[0][0] == 0 and sh[-1][1] == S
+            assert all(sh[i][1] == sh[i + 1][0] for i in range(world - 1))
+            if S % 2 == 0:
+                assert all(a % 2 == 0 for a, _ in sh)        # 8-byte aligned rows for every shard of a BIL cube
