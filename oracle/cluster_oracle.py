@@ -27,7 +27,8 @@ def pca_projections(x_nd, pcadim):
 
 
 def kmeans_labels(y_np, k, max_iter=100):
-    """Lloyd iterations on the quantised projections; returns (labels (n,), reassignment passes)."""
+    """Lloyd iterations on the quantised projections until no pixel changes cluster, at most ``n / 1024`` pixels
+    change (that reassignment is kept) or ``max_iter`` passes; returns (labels (n,), reassignment passes)."""
     y = np.asarray(y_np, dtype=np.float64)
     n, pd = y.shape
     mx = float(np.max(np.abs(y))) if n else 0.0
@@ -58,8 +59,11 @@ def kmeans_labels(y_np, k, max_iter=100):
                 acc = acc + df * df
             dist[:, c] = acc
         new = np.argmin(dist, axis=1)
-        if np.array_equal(new, lab):
+        nchg = int((new != lab).sum())
+        if nchg == 0:
             break
         lab = new
         it += 1
+        if nchg * 1024 <= n:          # converged to within 2^-10 of the column: keep the reassignment and stop
+            break
     return lab.astype(np.int32), it

@@ -70,6 +70,7 @@ struct cmf_ctx {
     int *nentries = nullptr, *nuse = nullptr;
     uint8_t *sel = nullptr, *inlier = nullptr;
     int16_t *cluster_img = nullptr, *alpha_img = nullptr;
+    int32_t* rowidx = nullptr;    // row of every member pixel in the compacted xt of a background-mode pass
     // on-device partition (cmf_set_clustering) and the -f regulariser (cmf_set_regfull)
     bool auto_cluster = false, regfull = false;
     int pcadim = 6, km_max_iter = 100, y_pd = 0;
@@ -385,10 +386,17 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
         for (int t = 0; t < ctx->kmodes; ++t) {
             launch_members(d, ctx->labels_d, ctx->mask, t, ctx->entries, ctx->rejmask, ctx->flagmask, ctx->sel,
                            t == 0 ? ctx->cluster_img : nullptr, ctx->inlier, st);
-            launch_repack(d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, 0, d.L,
+            // the members of this mode, compacted to the first rows of every column of xt (in line order): the
+            // statistics and the search then cost what the mode holds, not what the flightline holds
+            launch_rank(d, ctx->sel, ctx->rowidx, st);
+            ctx->d.rowidx = ctx->rowidx;
+            launch_repack(ctx->d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, 0, d.L,
                           ctx->sel, 0, st);
-            ctx->launches += 2;
+            ctx->d.rowidx = nullptr;
+            ctx->d.nrows = ctx->n;                 // the member count of the mean kernel (first launch of the pass)
+            ctx->launches += 3;
             fit_and_score(ctx, exact, ctx->sel, ctx->nuse, no_mark);
+            ctx->d.nrows = nullptr;
         }
         launch_colstats_modes(d, ctx->mf, ctx->inlier, ctx->nuse, ctx->nodata, ctx->colstats, st);
         ++ctx->launches;
@@ -424,6 +432,7 @@ int ensure_mode_buffers(cmf_ctx* ctx) {
     A_(dalloc(ctx, &ctx->inlier, LS));
     A_(dalloc(ctx, &ctx->cluster_img, LS));
     A_(dalloc(ctx, &ctx->alpha_img, LS));
+    A_(dalloc(ctx, &ctx->rowidx, LS));
     if (e != cudaSuccess) return fail(ctx, CMF_E_NOMEM, std::string("label buffers: ") + cudaGetErrorString(e));
     return CMF_OK;
 }
@@ -545,7 +554,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     free_buffers(ctx);
     ctx->have_labels = false;
     ctx->labels_d = nullptr; ctx->sel = nullptr; ctx->inlier = nullptr; ctx->cluster_img = nullptr;
-    ctx->alpha_img = nullptr;
+    ctx->alpha_img = nullptr; ctx->rowidx = nullptr;
     ctx->auto_cluster = false; ctx->regfull = false; ctx->y_pd = 0;
     ctx->have_excl = false; ctx->excl_sel = nullptr;
     ctx->gram_full = nullptr; ctx->vtop = nullptr; ctx->ypca = nullptr; ctx->qpca = nullptr; ctx->pick = nullptr;
@@ -556,6 +565,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     d.NT2 = (d.A + 7) / 8; d.AP = d.NT2 * 8;
     d.NT16 = (d.A + 15) / 16; d.AP16 = d.NT16 * 16;
     d.line_pitch = (long long)D * d.S; d.band_pitch = d.S; d.vec2 = (d.S % 2 == 0);
+    d.rowidx = nullptr; d.nrows = nullptr;
     ctx->B = p->bands; ctx->band_lo = p->band_lo; ctx->band_hi = p->band_hi;
     ctx->reflectance = p->reflectance; ctx->model = p->model; ctx->nodata = p->nodata;
     ctx->scale = p->reflectance ? 1.0 : 1.0e5;   // ppmscaling, robust_mf.py:38,:383-386

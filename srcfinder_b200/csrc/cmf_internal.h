@@ -43,6 +43,11 @@ struct Dims {
     long long line_pitch;    // elements between consecutive lines of the active slab
     int band_pitch;          // elements between consecutive bands (== samples of the cube)
     int vec2;                // 8-byte loads allowed (S, pitches even and base aligned)
+    // background-mode passes (-k > 1): the member pixels of a column are COMPACTED to the first rows of its xt block
+    // (rowidx[l*S + s] = row of pixel (l, s), in line order) and the statistics / search kernels stop at the column's
+    // member count nrows[s]; NULL = every line is a row (unimodal path)
+    const int32_t* rowidx;
+    const int* nrows;
 };
 
 // per-pixel spectrometer flags (spectrometer_masks/masks_sds.py:133-233); band indices are 0-based positions
@@ -125,6 +130,8 @@ void launch_members(const Dims& d, const int32_t* labels, const uint8_t* mask, i
                     const uint32_t* rejmask, const uint32_t* flagmask, uint8_t* sel, int16_t* cluster_img, uint8_t* inlier,
                     cudaStream_t st);
 void launch_fill_f64(double* p, long long n, double v, cudaStream_t st);
+// rowidx[l*S + s] = number of selected pixels of column s above line l (exclusive scan down the lines)
+void launch_rank(const Dims& d, const uint8_t* sel, int32_t* rowidx, cudaStream_t st);
 // PCA projection (P, lam = eigenvectors / eigenvalues of the column covariance, launch_eigen target 1) + k-means
 void launch_pca_kmeans(const Dims& d, const float* xt, const uint8_t* mask, const double* mu, const int* n,
                        const double* P, const double* lam, int pcadim, int k, int max_iter, int* pick,

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kKmThreads, PDM <= 8 ? 3 : 2)
     const int Lpad = (L + 31) & ~31;                       // whole warps walk the column together
     // one sweep: (assign) the label of every valid pixel, then its quantised components into the sums of that label
     auto sweep = [&](bool assign) {
-        int any = 0;
+        int any = 0;                                       // pixels of this thread that changed cluster
         int since = 0;
         // thread-private 32-bit sums in shared memory, element (c, p) of thread t at priv[(c * stride + p) * T + t]
         auto flush = [&]() {
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kKmThreads, PDM <= 8 ? 3 : 2)
                             }
                         if (c == 0 || dsq < bd) { bd = dsq; best = c; }
                     }
-                    if (best != lab8[l]) { lab8[l] = (uint8_t)best; any = 1; }
+                    if (best != lab8[l]) { lab8[l] = (uint8_t)best; ++any; }
                     lab = best;
                 } else {
                     lab = hist[(int)((((long long)qi[0] - lo) * kKmInitBins) / span)];
@@ -317,12 +317,19 @@ __global__ void __launch_bounds__(kKmThreads, PDM <= 8 ? 3 : 2)
         for (int i = tid; i < kKmWarps * k * stride; i += blockDim.x) acc[i] = 0;
         __syncthreads();
         // ---- reassign and rebuild the sums in the same pass
-        if (sweep(true)) changed = 1;
+        {
+            const int mychg = sweep(true);
+            if (mychg) atomicAdd(&changed, mychg);         // integer count: order-free
+        }
         __syncthreads();
         const int ch = changed;
         __syncthreads();
         if (tid == 0) changed = 0;
         if (!ch) break;
+        // converged to within 2^-10 of the column: the reassignment is kept and the iteration stops (the last
+        // per-mille of boundary pixels otherwise flip for dozens of sweeps; the reference's MiniBatchKMeans stops
+        // on a tolerance as well)
+        if ((long long)ch * 1024 <= (long long)n) { ++iter; break; }
     }
     for (int l = tid; l < L; l += blockDim.x)
         labels[(long long)l * S + s] = (q[l] != kInvalid) ? (int32_t)lab8[l] : 0;

@@ -106,7 +106,7 @@ __device__ __forceinline__ void gram_warp(const float* __restrict__ col_base, co
 template <int NT>
 __global__ void __launch_bounds__(kGramWarps * 32, 1)
     gram_kernel(const float* __restrict__ xt, const double* __restrict__ mu_g, int L, int lines_per_chunk,
-                int chunk_lo, int nchunk, double* __restrict__ gram_part) {
+                int chunk_lo, int nchunk, double* __restrict__ gram_part, const int* __restrict__ nrows) {
     constexpr int DP = 8 * NT, TL = kGramTL, NS = kGramNS, NTRI = NT * (NT + 1) / 2;
     constexpr int NROLE = (NT > 9) ? 2 : 1;
     constexpr int RSPLIT = (NT > 9) ? 8 : NT;   // role 0: tile rows [0,RSPLIT), role 1: [RSPLIT,NT)
@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(kGramWarps * 32, 1)
     const int s = blockIdx.x, chunk = chunk_lo + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c_begin = chunk * lines_per_chunk;
-    const int c_end = min(L, c_begin + lines_per_chunk);
+    // compacted background-mode pass: only the first nrows[s] rows of the column hold pixels
+    const int c_end = max(c_begin, min(nrows ? min(L, nrows[s]) : L, c_begin + lines_per_chunk));
 
     for (int i = threadIdx.x; i < DP; i += blockDim.x) mu_s[i] = mu_g[(long long)s * DP + i];
     for (int i = threadIdx.x; i < NTRI * 64; i += blockDim.x) red[i] = 0.0;
@@ -162,7 +163,7 @@ static void launch_gram_t(const Dims& d, const float* xt, const double* mu, int 
     cudaFuncSetAttribute(gram_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (chunk_hi <= chunk_lo) return;
     dim3 grid(d.S, chunk_hi - chunk_lo);
-    gram_kernel<NT><<<grid, kGramWarps * 32, smem, st>>>(xt, mu, d.L, lpc, chunk_lo, nchunk, gram_part);
+    gram_kernel<NT><<<grid, kGramWarps * 32, smem, st>>>(xt, mu, d.L, lpc, chunk_lo, nchunk, gram_part, d.nrows);
 }
 
 // Chunks [chunk_lo, chunk_hi) of `nchunk` chunks of `lpc` lines each (lpc a multiple of the Gram tile);

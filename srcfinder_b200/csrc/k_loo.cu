@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(kLooWarps * 32, 1)
     loo_kernel(const float* __restrict__ xt, const double* __restrict__ mu_g,
                const double* __restrict__ Pf_g, const double* __restrict__ Wf_g,
                const double* __restrict__ beta_g, int L, int NT2, int lines_per_chunk,
-               double* __restrict__ fpart, const unsigned long long* __restrict__ tile_mask) {
+               double* __restrict__ fpart, const unsigned long long* __restrict__ tile_mask,
+               const int* __restrict__ nrows) {
     constexpr int DP = 8 * NT, KS = DP / 4, MT = kLooMT, TL = 8 * MT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int AP = NT2 * 8;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(kLooWarps * 32, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q4 = lane & 3;
     const int c_begin = chunk * lines_per_chunk;
-    const int c_end = min(L, c_begin + lines_per_chunk);
+    const int c_end = max(c_begin, min(nrows ? min(L, nrows[s]) : L, c_begin + lines_per_chunk));   // compacted mode pass
     const int ntiles = (c_end - c_begin + TL - 1) / TL;
     const float* col_base = xt + (long long)s * L * DP;
     float* mytile = ring + warp * TL * DP;
@@ -223,10 +224,10 @@ static void launch_loo_t(const Dims& d, const float* xt, const double* mu, const
     dim3 grid(d.S, nchunk);
     if (base + wtab <= 227 * 1024) {
         cudaFuncSetAttribute(loo_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + wtab));
-        loo_kernel<NT, true><<<grid, kLooWarps * 32, base + wtab, st>>>(xt, mu, Pf, Wf, beta, d.L, d.NT2, lpc, fpart, tile_mask);
+        loo_kernel<NT, true><<<grid, kLooWarps * 32, base + wtab, st>>>(xt, mu, Pf, Wf, beta, d.L, d.NT2, lpc, fpart, tile_mask, d.nrows);
     } else {
         cudaFuncSetAttribute(loo_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
-        loo_kernel<NT, false><<<grid, kLooWarps * 32, base, st>>>(xt, mu, Pf, Wf, beta, d.L, d.NT2, lpc, fpart, tile_mask);
+        loo_kernel<NT, false><<<grid, kLooWarps * 32, base, st>>>(xt, mu, Pf, Wf, beta, d.L, d.NT2, lpc, fpart, tile_mask, d.nrows);
     }
 }
 

@@ -151,4 +151,24 @@ void launch_colstats_modes(const Dims& d, const double* mf, const uint8_t* inlie
     colstats_modes_kernel<<<d.S, 256, 0, st>>>(mf, inlier, nuse, d.L, d.S, nodata, colstats);
 }
 
+
+// One warp per column: exclusive count of the selected pixels above every line (ballot + popc, 32 lines at a time).
+__global__ void __launch_bounds__(128)
+    rank_kernel(const uint8_t* __restrict__ sel, int L, int S, int32_t* __restrict__ rowidx) {
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= S) return;
+    int base = 0;
+    for (int l0 = 0; l0 < L; l0 += 32) {
+        const int l = l0 + lane;
+        const bool on = l < L && sel[(long long)l * S + s] != 0;
+        const unsigned b = __ballot_sync(0xffffffffu, on);
+        if (l < L) rowidx[(long long)l * S + s] = base + __popc(b & ((1u << lane) - 1u));
+        base += __popc(b);
+    }
+}
+
+void launch_rank(const Dims& d, const uint8_t* sel, int32_t* rowidx, cudaStream_t st) {
+    rank_kernel<<<(d.S + 3) / 4, 128, 0, st>>>(sel, d.L, d.S, rowidx);
+}
+
 }  // namespace cmf

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kScreenWarps * 32, 1)
                       const double* __restrict__ Pf_g, const float* __restrict__ Ps_g,
                       const float* __restrict__ Ws_g, const float* __restrict__ betaf_g,
                       const int* __restrict__ n_g, int L, int NT16, int lines_per_chunk,
-                      double* __restrict__ fscreen) {
+                      double* __restrict__ fscreen, const int* __restrict__ nrows) {
     constexpr int DP = 8 * NT, KS = DP / 4, MT = kScreenMT, TL = 8 * MT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int AP16 = NT16 * 16;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kScreenWarps * 32, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q4 = lane & 3;
     const int c_begin = chunk * lines_per_chunk;
-    const int c_end = min(L, c_begin + lines_per_chunk);
+    const int c_end = max(c_begin, min(nrows ? min(L, nrows[blockIdx.x]) : L, c_begin + lines_per_chunk));   // compacted mode pass
     const int ntiles = (c_end - c_begin + TL - 1) / TL;
     const float* col_base = xt + (long long)s * L * DP;
     float* mytile = ring + warp * TL * DP;
@@ -439,7 +439,7 @@ static void launch_screen_v(const Dims& d, const float* xt, const double* mu, co
     lpc = (lpc + TL - 1) / TL * TL;
     dim3 grid(d.S, nchunk);
     loo_screen_kernel<NT, G1T, NPROD><<<grid, kScreenWarps * 32, smem, st>>>(xt, mu, Pf, Ps, Ws, betaf, n, d.L,
-                                                                             d.NT16, lpc, fscreen);
+                                                                             d.NT16, lpc, fscreen, d.nrows);
 }
 
 template <int NT>

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kT5Threads, 1)
     loo_screen5_kernel(const float* __restrict__ xt, const double* __restrict__ mu_g,
                        const float* __restrict__ tab_g, const float* __restrict__ betaf_g,
                        const int* __restrict__ n_g, int L, int NT16, int lines_per_chunk,
-                       double* __restrict__ fscreen) {
+                       double* __restrict__ fscreen, const int* __restrict__ ncomp) {
     constexpr int DP = 8 * NT, N1 = (DP + 15) / 16 * 16;
     constexpr uint32_t C_XH = 0, C_XL = DP, C_Y = 2 * DP, C_ZL = 2 * DP + N1, C_R = 3 * DP + N1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kT5Threads, 1)
     double* out = fscreen + ((long long)s * gridDim.y + chunk) * NA;
     if (n_g[s] < 2) return;                                      // nothing to search (K4 handles n < 2)
     const int c_begin = chunk * lines_per_chunk;
-    const int c_end = min(L, c_begin + lines_per_chunk);
+    const int c_end = min(ncomp ? min(L, ncomp[s]) : L, c_begin + lines_per_chunk);   // compacted mode pass: ncomp[s] rows
     if (c_end <= c_begin) {                                      // empty tail chunk
         for (int i = tid; i < NA; i += blockDim.x) out[i] = 0.0;
         return;
@@ -562,7 +562,7 @@ static void launch_screen5_t(const Dims& d, const float* xt, const double* mu, c
     cudaFuncSetAttribute(loo_screen5_kernel<NT, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);
     dim3 grid(d.S, nchunk);
     loo_screen5_kernel<NT, 7><<<grid, kT5Threads, p.total, st>>>(xt, mu, tab, betaf, n, d.L, d.NT16,
-                                                                 screen5_lines_per_chunk(d, nchunk), fscreen);
+                                                                 screen5_lines_per_chunk(d, nchunk), fscreen, d.nrows);
 }
 
 void launch_screen5(const Dims& d, const float* xt, const double* mu, const int* n, const int* nloo,

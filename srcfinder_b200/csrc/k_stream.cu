@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(CG * 2 * NT, repack_pipe_minb(NT, CG, LT, NS))
     const float* __restrict__ slab, long long line_pitch, int band_pitch, int L, int S, int D,
     float* __restrict__ xt, uint8_t* __restrict__ mask, double* __restrict__ colsum_part,
     int* __restrict__ colcnt_part, int lines_per_split, int line_base, int line_limit, int split_base,
-    const uint8_t* __restrict__ sel, int write_mask) {
+    const uint8_t* __restrict__ sel, int write_mask, const int32_t* __restrict__ rowidx) {
     constexpr int DP = 8 * NT, Q = 2 * NT, NTH = CG * Q, CS = LT * DP + 4;
     extern __shared__ __align__(16) float tile[];   // [NS][CG][CS]: ring of NS tiles
     __shared__ uint8_t bad[2][LT * CG];
@@ -178,19 +178,23 @@ __global__ void __launch_bounds__(CG * 2 * NT, repack_pipe_minb(NT, CG, LT, NS))
         }
         if (sel != nullptr) __syncthreads();
         if (col_ok) {
-            float* dst = xt + ((long long)(s0 + c) * L + l0) * DP + 4 * q;
+            float* colbase = xt + (long long)(s0 + c) * L * DP + 4 * q;
+            float* dst = colbase + (long long)l0 * DP;
             const float qnan = __int_as_float(0x7fc00000);
 #pragma unroll
             for (int l = 0; l < LT; ++l) {
                 if (l < nl) {
                     float4 x = v[l];
-                    if (bd[l * CG + c]) {
+                    const bool drop = bd[l * CG + c] != 0;
+                    if (drop) {
                         x = make_float4(qnan, qnan, qnan, qnan);
                     } else {
                         acc0 += (double)x.x; acc1 += (double)x.y; acc2 += (double)x.z; acc3 += (double)x.w;
                         ++cnt;
                     }
-                    *reinterpret_cast<float4*>(dst + l * DP) = x;
+                    if (rowidx == nullptr) *reinterpret_cast<float4*>(dst + l * DP) = x;
+                    else if (!drop)      // compacted: the member pixels of the column, in line order
+                        *reinterpret_cast<float4*>(colbase + (long long)rowidx[(long long)(l0 + l) * S + s0 + c] * DP) = x;
                 }
             }
         }
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(32 * NT, repack_pipe_minb(NT, 32, LT, NS)) rep
     const float* __restrict__ slab, long long line_pitch, int band_pitch, int L, int S, int D,
     float* __restrict__ xt, uint8_t* __restrict__ mask, double* __restrict__ colsum_part,
     int* __restrict__ colcnt_part, int lines_per_split, int line_base, int line_limit, int split_base,
-    const uint8_t* __restrict__ sel, int write_mask) {
+    const uint8_t* __restrict__ sel, int write_mask, const int32_t* __restrict__ rowidx) {
     constexpr int DP = 8 * NT, Q = 2 * NT, NP = 16, CG = 32, NTH = NP * Q, CS2 = LT * DP + 2;   // float2 units
     extern __shared__ __align__(16) float2 tile2[];   // [NS][NP][CS2]
     __shared__ uint8_t bad[2][LT * CG];
@@ -320,30 +324,41 @@ __global__ void __launch_bounds__(32 * NT, repack_pipe_minb(NT, 32, LT, NS)) rep
         }
         if (sel != nullptr) __syncthreads();
         if (col_ok) {
-            float* dst0 = xt + ((long long)(s0 + 2 * cp) * L + l0) * DP + 4 * q;
-            float* dst1 = dst0 + (long long)L * DP;
+            float* col0 = xt + (long long)(s0 + 2 * cp) * L * DP + 4 * q;
+            float* col1 = col0 + (long long)L * DP;
+            float* dst0 = col0 + (long long)l0 * DP;
+            float* dst1 = col1 + (long long)l0 * DP;
             const float qnan = __int_as_float(0x7fc00000);
             const float4 nan4 = make_float4(qnan, qnan, qnan, qnan);
 #pragma unroll
             for (int l = 0; l < LT; ++l) {
                 if (l < nl) {
                     float4 x0 = v0[l], x1 = v1[l];
-                    if (bd[l * CG + 2 * cp]) {
+                    const bool drop0 = bd[l * CG + 2 * cp] != 0, drop1 = bd[l * CG + 2 * cp + 1] != 0;
+                    if (drop0) {
                         x0 = nan4;
                     } else {
                         acc[0][0] += (double)x0.x; acc[0][1] += (double)x0.y; acc[0][2] += (double)x0.z;
                         acc[0][3] += (double)x0.w;
                         ++cnt0;
                     }
-                    if (bd[l * CG + 2 * cp + 1]) {
+                    if (drop1) {
                         x1 = nan4;
                     } else {
                         acc[1][0] += (double)x1.x; acc[1][1] += (double)x1.y; acc[1][2] += (double)x1.z;
                         acc[1][3] += (double)x1.w;
                         ++cnt1;
                     }
-                    *reinterpret_cast<float4*>(dst0 + l * DP) = x0;
-                    *reinterpret_cast<float4*>(dst1 + l * DP) = x1;
+                    if (rowidx == nullptr) {
+                        *reinterpret_cast<float4*>(dst0 + l * DP) = x0;
+                        *reinterpret_cast<float4*>(dst1 + l * DP) = x1;
+                    } else {
+                        // compacted: the member pixels of each column, in line order (rows past the member count are
+                        // never read: the consumers stop at nrows[s])
+                        const int2 r = *reinterpret_cast<const int2*>(rowidx + (long long)(l0 + l) * S + s0 + 2 * cp);
+                        if (!drop0) *reinterpret_cast<float4*>(col0 + (long long)r.x * DP) = x0;
+                        if (!drop1) *reinterpret_cast<float4*>(col1 + (long long)r.y * DP) = x1;
+                    }
                 }
             }
         }
@@ -758,7 +773,7 @@ static void launch_repack_pipe(const Dims& d, const float* slab, float* xt, uint
     repack_pipe_kernel<NT, CG, LT, NS><<<grid, CG * 2 * NT, smem, st>>>(slab, d.line_pitch, d.band_pitch, d.L, d.S,
                                                                         d.D, xt, mask, colsum_part, colcnt_part, lps,
                                                                         line_base, line_limit, split_base, sel,
-                                                                        write_mask);
+                                                                        write_mask, d.rowidx);
 }
 
 template <int NT>
@@ -777,7 +792,7 @@ static void launch_repack_t(const Dims& d, const float* slab, float* xt, uint8_t
                                  (int)smem);                                                                      \
             repack_pair_kernel<NT, LTv, NSv><<<grid, 32 * NT, smem, st>>>(                                        \
                 slab, d.line_pitch, d.band_pitch, d.L, d.S, d.D, xt, mask, colsum_part, colcnt_part, lps,         \
-                line_base, line_limit, split_base, sel, write_mask);                                              \
+                line_base, line_limit, split_base, sel, write_mask, d.rowidx);                                    \
             return;                                                                                               \
         }
         CMF_RP(4, 4)
