@@ -136,7 +136,7 @@ int cmf_set_labels(cmf_ctx* ctx, const int32_t* labels, int kmodes, int reject_m
  * (rule in csrc/k_cluster.cu, restated in oracle/cluster_oracle.py): components by descending eigenvalue, signed
  * so that v . mu >= 0; projections quantised to 2^-24 of the column's range and cluster sums kept in 64-bit
  * integers; initial partition = kmodes equal-count slices of component 1; Lloyd iterations until no pixel or at
- * most 1/1024 of the column's pixels change cluster, at most max_iter (<= 0: 100) of them.  kmodes <= 1 returns to the unimodal path.  CMF_OUT_LABELS returns the labels found. */
+ * most 1/256 of the column's pixels change cluster, at most max_iter (<= 0: 100) of them.  kmodes <= 1 returns to the unimodal path.  CMF_OUT_LABELS returns the labels found. */
 int cmf_set_clustering(cmf_ctx* ctx, int kmodes, int pcadim, int reject_min, int max_iter);
 
 /* -f (:161, :358): in a labelled / clustered looshrinkage run the shrinkage target of every mode fit is the

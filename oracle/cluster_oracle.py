@@ -27,7 +27,7 @@ def pca_projections(x_nd, pcadim):
 
 
 def kmeans_labels(y_np, k, max_iter=100):
-    """Lloyd iterations on the quantised projections until no pixel changes cluster, at most ``n / 1024`` pixels
+    """Lloyd iterations on the quantised projections until no pixel changes cluster, at most ``n / 256`` pixels
     change (that reassignment is kept) or ``max_iter`` passes; returns (labels (n,), reassignment passes)."""
     y = np.asarray(y_np, dtype=np.float64)
     n, pd = y.shape
@@ -64,6 +64,6 @@ def kmeans_labels(y_np, k, max_iter=100):
             break
         lab = new
         it += 1
-        if nchg * 1024 <= n:          # converged to within 2^-10 of the column: keep the reassignment and stop
+        if nchg * 256 <= n:           # converged to within 2^-8 of the column: keep the reassignment and stop
             break
     return lab.astype(np.int32), it

@@ -326,10 +326,10 @@ __global__ void __launch_bounds__(kKmThreads, PDM <= 8 ? 3 : 2)
         __syncthreads();
         if (tid == 0) changed = 0;
         if (!ch) break;
-        // converged to within 2^-10 of the column: the reassignment is kept and the iteration stops (the last
+        // converged to within 2^-8 of the column: the reassignment is kept and the iteration stops (the last
         // per-mille of boundary pixels otherwise flip for dozens of sweeps; the reference's MiniBatchKMeans stops
         // on a tolerance as well)
-        if ((long long)ch * 1024 <= (long long)n) { ++iter; break; }
+        if ((long long)ch * 256 <= (long long)n) { ++iter; break; }
     }
     for (int l = tid; l < L; l += blockDim.x)
         labels[(long long)l * S + s] = (q[l] != kInvalid) ? (int32_t)lab8[l] : 0;
