@@ -233,16 +233,18 @@ void fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* sel, const int* nloo
     ctx->screened = screen;
 }
 
-// The same for a wide active window (unimodal): every step is blocked, the per-column matrices live in global memory.
+// The same for a wide active window: every step is blocked, the per-column matrices live in global memory.
 // exact = true takes the FP64 tensor (DMMA) Gram pass instead of the integer tcgen05 pass (cross-check).
+// sel / nloo / write_mask as in fit_and_score (a background-mode pass fits the selected pixels, n of the search = nloo).
 template <class Mark>
-void wide_fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* excl, Mark mark) {
+void wide_fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* sel, const int* nloo, int write_mask, bool modes_pass,
+                        Mark mark) {
     const Dims& d = ctx->d;
     cudaStream_t st = ctx->stream;
     const bool g8 = ctx->use_gram8 && !exact;
-    launch_wide_stats(d, ctx->slab, ctx->mask, excl, 1, ctx->wsplit, ctx->wlps, ctx->colsum_part, ctx->colcnt_part,
-                      ctx->lo_part, ctx->hi_part, ctx->mu, ctx->n, ctx->ctr, ctx->qexp, st);
-    launch_wide_pack(d, ctx->slab, ctx->mask, excl, ctx->ctr, ctx->qexp, ctx->xt, g8 ? ctx->img : nullptr, st);
+    launch_wide_stats(d, ctx->slab, ctx->mask, sel, write_mask, ctx->wsplit, ctx->wlps, ctx->colsum_part,
+                      ctx->colcnt_part, ctx->lo_part, ctx->hi_part, ctx->mu, ctx->n, ctx->ctr, ctx->qexp, st);
+    launch_wide_pack(d, ctx->slab, ctx->mask, sel, ctx->ctr, ctx->qexp, ctx->xt, g8 ? ctx->img : nullptr, st);
     mark(1);
     mark(2);
     if (g8) launch_wide_gram8(d, ctx->img, ctx->wgram, st);
@@ -255,7 +257,7 @@ void wide_fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* excl, Mark mark
     ctx->launches += 10;
     const bool loo = ctx->model == CMF_MODEL_LOOSHRINKAGE;
     if (loo) {
-        launch_wide_tables(d, ctx->APW, ctx->n, nullptr, ctx->alphas_d, ctx->model, ctx->lam, ctx->slogT, ctx->logdet,
+        launch_wide_tables(d, ctx->APW, ctx->n, nloo, ctx->alphas_d, ctx->model, ctx->lam, ctx->slogT, ctx->logdet,
                            ctx->beta, ctx->rsum, ctx->Wtab, st);
         ++ctx->launches;
     }
@@ -273,10 +275,10 @@ void wide_fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* excl, Mark mark
     mark(8);
     launch_finalize(d, ctx->fpart, ctx->nchunk_loo, ctx->logdet, ctx->n, ctx->alphas_d, ctx->P, ctx->lam, ctx->mu,
                     ctx->abscf_d, ctx->model, ctx->reflectance, ctx->scale, ctx->nll, ctx->mindex, ctx->w, ctx->wT,
-                    ctx->c0, ctx->status, nullptr, nullptr, nullptr, st);
+                    ctx->c0, ctx->status, nullptr, nullptr, nloo, st);
     mark(9);
     launch_score(d, ctx->slab, ctx->mask, ctx->wT, ctx->c0, ctx->status, ctx->nodata, ctx->mf, ctx->stat_part,
-                 ctx->nlanes, ctx->score_lpc, nullptr, ctx->mindex, ctx->alpha_img, st);
+                 ctx->nlanes, ctx->score_lpc, modes_pass ? sel : nullptr, ctx->mindex, ctx->alpha_img, st);
     mark(10);
     ctx->launches += 2;
     ctx->screened = false;
@@ -308,9 +310,9 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
     // ---- pass over every valid pixel: validity mask, column-major copy, column sums
     const bool chased = blocks_ready != nullptr && !modes;
     const uint8_t* excl = (!modes && ctx->have_excl) ? ctx->excl_sel : nullptr;
-    if (ctx->wide) {
-        if (blocks_ready) for (cudaEvent_t e : *blocks_ready) cudaStreamWaitEvent(st, e, 0);
-        wide_fit_and_score(ctx, exact, excl, mark);
+    if (ctx->wide && blocks_ready) for (cudaEvent_t e : *blocks_ready) cudaStreamWaitEvent(st, e, 0);
+    if (ctx->wide && !modes) {
+        wide_fit_and_score(ctx, exact, excl, nullptr, 1, false, mark);
         if (excl) {
             launch_count_mask(d, ctx->mask, ctx->nuse, st);
             launch_colstats_modes(d, ctx->mf, ctx->mask, ctx->nuse, ctx->nodata, ctx->colstats, st);
@@ -363,6 +365,37 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
         }
         mark(11);
     } else {
+        if (ctx->wide) {
+            // ---- background modes on a wide window: the same plan with the blocked kernels (no compaction)
+            const size_t LSw = (size_t)d.L * d.S;
+            const bool g8 = ctx->use_gram8 && !exact;
+            launch_wide_stats(d, ctx->slab, ctx->mask, nullptr, 1, ctx->wsplit, ctx->wlps, ctx->colsum_part,
+                              ctx->colcnt_part, ctx->lo_part, ctx->hi_part, ctx->mu, ctx->nuse, ctx->ctr, ctx->qexp, st);   // nuse (:302)
+            ctx->launches += 3;
+            if (ctx->auto_cluster) {
+                // PCA basis of the whole column (:310-311): plain eigenvectors of its covariance
+                launch_wide_pack(d, ctx->slab, ctx->mask, nullptr, ctx->ctr, ctx->qexp, ctx->xt, g8 ? ctx->img : nullptr, st);
+                if (g8) launch_wide_gram8(d, ctx->img, ctx->wgram, st);
+                else launch_wide_gram64(d, ctx->xt, ctx->ctr, ctx->wgram, st);
+                launch_wide_eigen(d, ctx->wgram, ctx->nuse, ctx->mu, ctx->ctr, g8 ? ctx->qexp : nullptr, 1, ctx->wwork,
+                                  ctx->wdinv, ctx->wdvec, ctx->wevec, ctx->rot, ctx->iters, ctx->sweeps, ctx->P, ctx->lam,
+                                  ctx->slogT, ctx->status, st);
+                launch_pca_kmeans(d, ctx->xt, ctx->mask, ctx->mu, ctx->nuse, ctx->P, ctx->lam, ctx->pcadim, ctx->kmodes,
+                                  ctx->km_max_iter, ctx->pick, ctx->vtop, ctx->ypca, ctx->qpca, ctx->lab8, ctx->labels_d,
+                                  ctx->km_iters, st);
+                ctx->launches += 9;
+            }
+            launch_modes(d, ctx->labels_d, ctx->mask, ctx->reject_min, ctx->entries, ctx->rejmask, ctx->nentries, ctx->flagmask, st);
+            launch_fill_f64(ctx->mf, (long long)LSw, ctx->nodata, st);
+            CK(cudaMemsetAsync(ctx->alpha_img, 0, LSw * sizeof(int16_t), st));
+            ctx->launches += 3;
+            for (int t = 0; t < ctx->kmodes; ++t) {
+                launch_members(d, ctx->labels_d, ctx->mask, t, ctx->entries, ctx->rejmask, ctx->flagmask, ctx->sel,
+                               t == 0 ? ctx->cluster_img : nullptr, ctx->inlier, st);
+                ++ctx->launches;
+                wide_fit_and_score(ctx, exact, ctx->sel, ctx->nuse, 0, true, no_mark);
+            }
+        } else {
         // ---- background modes (cmf/robust_mf.py:306-344): one fit-and-score pass per mode-list entry
         const size_t LS = (size_t)d.L * d.S;
         launch_mean(d, ctx->colsum_part, ctx->colcnt_part, ctx->nsplit, ctx->mu, ctx->nuse, st);   // nuse (:302)
@@ -397,6 +430,7 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
             ctx->launches += 3;
             fit_and_score(ctx, exact, ctx->sel, ctx->nuse, no_mark);
             ctx->d.nrows = nullptr;
+        }
         }
         launch_colstats_modes(d, ctx->mf, ctx->inlier, ctx->nuse, ctx->nodata, ctx->colstats, st);
         ++ctx->launches;
@@ -771,7 +805,6 @@ int cmf_set_labels(cmf_ctx* ctx, const int32_t* labels, int kmodes, int reject_m
     if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_set_labels before cmf_set_problem");
     CK(cudaSetDevice(ctx->device));
     if (labels == nullptr) { ctx->have_labels = false; ctx->auto_cluster = false; return CMF_OK; }
-    if (ctx->wide) return fail(ctx, CMF_E_ARG, "background modes are not supported for active windows wider than 96 bands");
     if (kmodes < 1 || kmodes > kMaxLabels) return fail(ctx, CMF_E_ARG, "kmodes must be 1..32");
     const Dims& d = ctx->d;
     const size_t LS = (size_t)d.L * d.S;
@@ -794,15 +827,16 @@ int cmf_set_clustering(cmf_ctx* ctx, int kmodes, int pcadim, int reject_min, int
     if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_set_clustering before cmf_set_problem");
     CK(cudaSetDevice(ctx->device));
     if (kmodes <= 1) { ctx->auto_cluster = false; ctx->have_labels = false; return CMF_OK; }
-    if (ctx->wide) return fail(ctx, CMF_E_ARG, "background modes are not supported for active windows wider than 96 bands");
     if (kmodes > kMaxLabels) return fail(ctx, CMF_E_ARG, "kmodes must be 1..32");
     const Dims& d = ctx->d;
     if (pcadim < 1 || pcadim > kMaxPcaDim || pcadim > d.D)
         return fail(ctx, CMF_E_ARG, "pcadim must be 1..min(16, active bands)");
     int rc = ensure_mode_buffers(ctx);
     if (rc) return rc;
-    rc = ensure_full_gram(ctx);
-    if (rc) return rc;
+    if (!ctx->wide) {
+        rc = ensure_full_gram(ctx);
+        if (rc) return rc;
+    }
     const size_t LS = (size_t)d.L * d.S;
     if (ctx->y_pd < pcadim) {      // (re)allocate the projection buffer; smaller requests reuse it
         cudaError_t e = cudaSuccess;
@@ -831,7 +865,9 @@ int cmf_set_regfull(cmf_ctx* ctx, int enable) {
     if (!ctx) return CMF_E_ARG;
     if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_set_regfull before cmf_set_problem");
     CK(cudaSetDevice(ctx->device));
-    if (enable && !ctx->wide) {
+    if (enable && ctx->wide)
+        return fail(ctx, CMF_E_ARG, "-f (full-column regulariser) is not supported for active windows wider than 96 bands");
+    if (enable) {
         int rc = ensure_full_gram(ctx);
         if (rc) return rc;
     }

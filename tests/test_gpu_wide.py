@@ -76,6 +76,43 @@ def test_wide_window_empirical_and_degenerate():
     assert loo["alpha_index"][1] == -2
 
 
+def test_wide_window_background_modes():
+    """-k / -r on the 416-band window (the reference allows it with -R): given labels against the oracle, and the
+    partition found on the device reproduces the labelled run; -f on a wide window fails loudly."""
+    from srcfinder_b200 import CmfError
+    active = [5, 420]
+    L, S = 1500, 2
+    cube = synth.make_cube(L, S, seed=46, bad_pixels=True)
+    ab = _abscf(active)
+    bright = np.nan_to_num(cube[:, 380, :], nan=0.0, posinf=0.0)
+    labels = (bright > np.median(bright, axis=0, keepdims=True)).astype(np.int32)
+    labels[100:140, 1] = 1 - labels[100:140, 1]
+    rmin = orc.min_cluster_samples(active)
+    ref = orc.cmf_cube(cube, ab, active, reflectance=True, labels=labels, reject_min=rmin)
+    got = cmf_cube(cube, ab, active, reflectance=True, labels=labels, reject_min=rmin)
+    assert np.array_equal(got["mask"], ref["mask"])
+    assert np.array_equal(got["mf"] == -9999.0, ref["mf"] == -9999.0)
+    assert np.array_equal(got["alpha_index"], ref["alpha_index"])
+    for c in range(S):
+        ok = ref["mf"][:, c] != -9999.0
+        err = np.max(np.abs(got["mf"][ok, c] - ref["mf"][ok, c])) / np.std(ref["mf"][ok, c])
+        assert err <= WIDE_SIGMA, "column %d: %.3g sigma" % (c, err)
+        assert got["colnum"][c] == ref["colnum"][c]
+        assert got["colstd"][c] == pytest.approx(ref["colstd"][c], rel=1e-6)
+    # the partition found on the device: the run equals a labelled run with those labels
+    Lc, B, Sc = cube.shape
+    with ColumnwiseMF(Lc, B, Sc, active, ab, reflectance=True) as eng:
+        eng.upload(cube)
+        eng.set_clustering(2, pcadim=6, reject_min=rmin)
+        eng.run()
+        auto = eng.results(); found = eng.labels()
+        with pytest.raises(CmfError):
+            eng.set_regfull(True)
+    again = cmf_cube(cube, ab, active, reflectance=True, labels=found, reject_min=rmin)
+    assert np.array_equal(auto["mf"], again["mf"], equal_nan=True)
+    assert set(np.unique(found[auto["mask"]])) == {0, 1}
+
+
 def test_wide_window_determinism_and_run_host():
     """Same bits from repeated runs and from the one-call host API."""
     active = [5, 420]
