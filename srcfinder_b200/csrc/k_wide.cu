@@ -754,60 +754,93 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------- W5 / W6
-// C[m][n] = sum_k A[m][k] B[k][n] for a 64 x 64 block with A row-major in global memory (pitch lda, rows are
-// pixels) and B row-major (pitch ldb): 16-deep stages, A transposed on its way into shared memory.
+// C[m][n] = sum_k A[m][k] B[k][n] for a 128 x 64 block with A row-major in global memory (pitch lda, rows are pixels)
+// and B row-major (pitch ldb).  8 warps (4 in m x 2 in n), each a 32 x 32 block of 4 x 4 DMMA tiles; 16-deep stages:
+// A is kept as it arrives, [m][k] with a pitch of 20 doubles (== 4 mod 16: the fragment reads of a half-warp and the
+// stores of a half-warp both fall on 16 different 8-byte banks), B as [k][n] with pitch kWP.  The next stage is
+// fetched into registers while the current one is multiplied.
+constexpr int kRP = 20;
+constexpr int kRowsThreads = 256;
+
+__device__ __forceinline__ void dmma_stage_rows(const double* __restrict__ As, const double* __restrict__ Bs,
+                                                double (&acc)[4][4][2], int wm, int wn, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        double a[4], b[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            a[t] = As[(wm * 32 + t * 8 + g) * kRP + 4 * kk + q];
+            b[t] = Bs[(4 * kk + q) * kWP + wn * 32 + t * 8 + g];
+        }
+#pragma unroll
+        for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+            for (int tj = 0; tj < 4; ++tj) mma884(acc[ti][tj][0], acc[ti][tj][1], a[ti], b[tj]);
+    }
+}
+
 template <typename TA, bool CENTRE>
 __device__ __forceinline__ void gemm_rows_block(const TA* __restrict__ A, long long lda, int m_valid, int K,
-                                                const double* __restrict__ ctr, const double* __restrict__ B,
+                                                const double* __restrict__ ctr_s, const double* __restrict__ B,
                                                 long long ldb, int n_valid, double* As, double* Bs,
                                                 double (&acc)[4][4][2], int tid) {
     const int lane = tid & 31, warp = tid >> 5, wm = warp >> 1, wn = warp & 1;
-    // A stage: element e = tid + 128 r: row m = e / 16, k = e % 16;  B stage: k = e / 64, n = e % 64
+    // A stage: element e = tid + 256 r: k = e % 16, row m = e / 16;  B stage: n = e % 64, k = e / 64
     const int ak = tid & 15, am = tid >> 4, bn = tid & 63, bk = tid >> 6;
-    double ra[8], rb[8];
+    TA ra[8];
+    double rb[4];
     auto fetch = [&](int k0) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const int m = am + 8 * r, k = k0 + ak;
-            double v = 0.0;
-            if (m < m_valid && k < K) {
-                const TA x = A[(long long)m * lda + k];
-                v = CENTRE ? centred(x, ctr[k]) : (double)x;
-            }
-            ra[r] = v;
-            const int kb = k0 + bk + 2 * r;
+            const int m = am + 16 * r, k = k0 + ak;
+            ra[r] = (m < m_valid && k < K) ? A[(long long)m * lda + k] : (TA)0;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int kb = k0 + bk + 4 * r;
             rb[r] = (kb < K && bn < n_valid) ? B[(long long)kb * ldb + bn] : 0.0;
         }
     };
     fetch(0);
     for (int k0 = 0; k0 < K; k0 += 16) {
         __syncthreads();
+        {
+            const int k = k0 + ak;
+            const double c = (CENTRE && k < K) ? ctr_s[k] : 0.0;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            As[ak * kWP + am + 8 * r] = ra[r];
-            Bs[(bk + 2 * r) * kWP + bn] = rb[r];
+            for (int r = 0; r < 8; ++r) {
+                const TA x = ra[r];
+                As[(am + 16 * r) * kRP + ak] = (k < K && am + 16 * r < m_valid) ? (CENTRE ? centred(x, c) : (double)x) : 0.0;
+            }
         }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) Bs[(bk + 4 * r) * kWP + bn] = rb[r];
         __syncthreads();
         if (k0 + 16 < K) fetch(k0 + 16);
-        dmma_stage(As, Bs, acc, wm, wn, lane);
+        dmma_stage_rows(As, Bs, acc, wm, wn, lane);
     }
 }
 
 // Z[px][j] = (sum_b (x[px][b] - mu_b) P[b][j])^2 for the columns s0 .. s0 + gridDim.z - 1 (Z is a per-batch buffer)
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kRowsThreads, 2)
     wide_proj_kernel(const T* __restrict__ xt, const double* __restrict__ mu_g, const double* __restrict__ P_g,
                      const int* __restrict__ n_g, int L, int D, int DP, int s0, double* __restrict__ Z) {
-    __shared__ double As[16 * kWP], Bs[16 * kWP];
+    extern __shared__ double rows_sm[];
+    double* As = rows_sm;                    // [128][kRP]
+    double* Bs = As + 128 * kRP;             // [16][kWP]
+    double* mu_s = Bs + 16 * kWP;            // [DP]
     const int s = s0 + blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (n_g[s] < 2) return;
-    const int j0 = blockIdx.x * 64, p0 = blockIdx.y * 64;
+    const int j0 = blockIdx.x * 64, p0 = blockIdx.y * 128;
+    for (int i = tid; i < DP; i += blockDim.x) mu_s[i] = mu_g[(long long)s * DP + i];
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    gemm_rows_block<T, true>(xt + ((long long)s * L + p0) * DP, DP, min(64, L - p0), D, mu_g + (long long)s * DP,
+    gemm_rows_block<T, true>(xt + ((long long)s * L + p0) * DP, DP, min(128, L - p0), D, mu_s,
                              P_g + (long long)s * DP * DP + j0, DP, min(64, DP - j0), As, Bs, acc, tid);
     const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3;
     double* Zc = Z + (long long)blockIdx.z * L * DP;
@@ -852,12 +885,14 @@ __device__ __forceinline__ double wide_loo_term(double r, double beta) {
 }
 
 // fpart[s][chunk][alpha] = sum over the chunk's pixels of log q + r/q with r = sum_j Z[px][j] W[j][alpha]
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kRowsThreads, 2)
     wide_loo_kernel(const double* __restrict__ Z, const double* __restrict__ W_g, const double* __restrict__ beta_g,
                     const int* __restrict__ n_g, int L, int D, int DP, int AP, int APW, int s0, int lines_per_chunk,
                     int nchunk, double* __restrict__ fpart) {
-    __shared__ double As[16 * kWP], Bs[16 * kWP];
-    __shared__ double xch[2][64];
+    extern __shared__ double rows_sm[];
+    double* As = rows_sm;                    // [128][kRP]
+    double* Bs = As + 128 * kRP;             // [16][kWP]
+    double* xch = Bs + 16 * kWP;             // [4][64]
     const int s = s0 + blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int a0 = blockIdx.x * 64, chunk = blockIdx.y;
     const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3;
@@ -874,13 +909,13 @@ __global__ void __launch_bounds__(128)
             fsum[tj][e] = 0.0;
         }
     const double* Zc = Z + (long long)blockIdx.z * L * DP;
-    for (int p0 = c_begin; p0 < c_end; p0 += 64) {
+    for (int p0 = c_begin; p0 < c_end; p0 += 128) {
         double acc[4][4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        gemm_rows_block<double, false>(Zc + (long long)p0 * DP, DP, min(64, c_end - p0), D, nullptr,
+        gemm_rows_block<double, false>(Zc + (long long)p0 * DP, DP, min(128, c_end - p0), D, nullptr,
                                        W_g + (long long)s * DP * APW + a0, APW, min(64, APW - a0), As, Bs, acc, tid);
         // rows past the chunk end were loaded as zero: r = 0 and the term vanishes
 #pragma unroll
@@ -893,7 +928,7 @@ __global__ void __launch_bounds__(128)
                 fsum[tj][e] += f;
             }
     }
-    // sum over the 8 pixel rows of a fragment (lanes with equal q), then over the two warps in m, fixed order
+    // sum over the 8 pixel rows of a fragment (lanes with equal q), then over the four warps in m, fixed order
 #pragma unroll
     for (int tj = 0; tj < 4; ++tj)
 #pragma unroll
@@ -907,10 +942,10 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int tj = 0; tj < 4; ++tj)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) xch[wm][wn * 32 + tj * 8 + 2 * q + e] = fsum[tj][e];
+            for (int e = 0; e < 2; ++e) xch[wm * 64 + wn * 32 + tj * 8 + 2 * q + e] = fsum[tj][e];
     }
     __syncthreads();
-    if (tid < 64 && a0 + tid < AP) out[a0 + tid] = xch[0][tid] + xch[1][tid];
+    if (tid < 64 && a0 + tid < AP) out[a0 + tid] = ((xch[tid] + xch[64 + tid]) + xch[128 + tid]) + xch[192 + tid];
 }
 
 // ---------------------------------------------------------------------------------------- launchers
@@ -1004,22 +1039,26 @@ void launch_wide_tables(const Dims& d, int APW, const int* n, const int* nloo, c
 void launch_wide_loo(const Dims& d, int APW, const float* xt, const double* mu, const double* P, const double* W,
                      const double* beta, const int* n, int s0, int ns, int nchunk, double* Z, double* fpart,
                      cudaStream_t st) {
-    dim3 g1((d.DP + 63) / 64, (d.L + 63) / 64, ns);
-    wide_proj_kernel<float><<<g1, 128, 0, st>>>(xt, mu, P, n, d.L, d.D, d.DP, s0, Z);
+    const size_t sm1 = (size_t)(128 * kRP + 16 * kWP + d.DP) * sizeof(double);
+    const size_t sm2 = (size_t)(128 * kRP + 16 * kWP + 256) * sizeof(double);
+    dim3 g1((d.DP + 63) / 64, (d.L + 127) / 128, ns);
+    wide_proj_kernel<float><<<g1, kRowsThreads, sm1, st>>>(xt, mu, P, n, d.L, d.D, d.DP, s0, Z);
     int lpc = (d.L + nchunk - 1) / nchunk;
-    lpc = (lpc + 63) / 64 * 64;
+    lpc = (lpc + 127) / 128 * 128;
     dim3 g2(APW / 64, nchunk, ns);
-    wide_loo_kernel<<<g2, 128, 0, st>>>(Z, W, beta, n, d.L, d.D, d.DP, d.AP, APW, s0, lpc, nchunk, fpart);
+    wide_loo_kernel<<<g2, kRowsThreads, sm2, st>>>(Z, W, beta, n, d.L, d.D, d.DP, d.AP, APW, s0, lpc, nchunk, fpart);
 }
 
 void launch_wide_loo_f64(int L, int D, int DP, int AP, int APW, const double* x, const double* zero_mu,
                          const double* P, const double* W, const double* beta, const int* n, double* Z,
                          double* fpart, cudaStream_t st) {
-    dim3 g1((DP + 63) / 64, (L + 63) / 64, 1);
-    wide_proj_kernel<double><<<g1, 128, 0, st>>>(x, zero_mu, P, n, L, D, DP, 0, Z);
-    const int lpc = (L + 63) / 64 * 64;
+    const size_t sm1 = (size_t)(128 * kRP + 16 * kWP + DP) * sizeof(double);
+    const size_t sm2 = (size_t)(128 * kRP + 16 * kWP + 256) * sizeof(double);
+    dim3 g1((DP + 63) / 64, (L + 127) / 128, 1);
+    wide_proj_kernel<double><<<g1, kRowsThreads, sm1, st>>>(x, zero_mu, P, n, L, D, DP, 0, Z);
+    const int lpc = (L + 127) / 128 * 128;
     dim3 g2(APW / 64, 1, 1);
-    wide_loo_kernel<<<g2, 128, 0, st>>>(Z, W, beta, n, L, D, DP, AP, APW, 0, lpc, 1, fpart);
+    wide_loo_kernel<<<g2, kRowsThreads, sm2, st>>>(Z, W, beta, n, L, D, DP, AP, APW, 0, lpc, 1, fpart);
 }
 
 
