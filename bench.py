@@ -364,7 +364,11 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    # warm-up: at least 3 steps, and with N > 1 at least two steps per gather root, so that NCCL has set up the
+    # peer connections of EVERY root before the timed region (they are made lazily on first use: measured 700 ms
+    # per step at N = 8 when roots were first used inside the timed region)
+    nwarm = max(args.warmup, 3, 2 * world if world > 1 else 0)
+    for _ in range(nwarm):
         step(False)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -422,7 +426,7 @@ def run_gpu(args):
                 "mma.sync (SASS HMMA), whose measured ceiling in this run is %.0f TFLOP/s" % mma_peak)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": nwarm, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if by_columns else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, world),
             "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
