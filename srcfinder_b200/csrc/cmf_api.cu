@@ -636,7 +636,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     ctx->nlanes = score_plan(d, ctx->sm_count, &ctx->score_lpc);
     ctx->nchunk_screen = ctx->nchunk_loo;
     // the screening pass needs its tables in shared memory and a 64-bit tile mask (A <= 512)
-    ctx->can_screen = loo && d.NT2 <= 64 && screen_smem_bytes(d) <= 227 * 1024;
+    ctx->can_screen = loo && d.NT2 <= 64 && (screen5_supported(d) || screen_smem_bytes(d) <= 227 * 1024);
     ctx->use_screen5 = ctx->can_screen && screen5_supported(d);
     if (const char* e = cmf_hook("CMF_SCREEN_IMPL")) if (strcmp(e, "legacy") == 0) ctx->use_screen5 = false;
     if (const char* e = cmf_hook("CMF_EIGEN")) ctx->eigen_method = (strcmp(e, "jacobi") == 0) ? 1 : 0;

@@ -23,6 +23,7 @@
 //     [2DP, 2DP+N1)       Y, then zh       D of GEMM1, A of GEMM2
 //     [2DP+N1, 3DP+N1)    zl               A of GEMM2
 //     [3DP+N1, .. + NA)   R                D of GEMM2
+#include <algorithm>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -116,15 +117,17 @@ enum { B_TAB = 0, B_XFULL = 1, B_XEMPTY = 4, B_XREADY = 7, B_G1 = 8, B_ZREADY = 
 // W rows are alphas i (K = eigen-direction j); hi = tf32(v), lo = tf32(v - hi).
 __global__ void __launch_bounds__(256)
     screen5_tables_kernel(const int* __restrict__ n_g, const int* __restrict__ nloo_g,
-                          const double* __restrict__ alphas, int A, int D, int NT, int NT16,
+                          const double* __restrict__ alphas, int A, int D, int NT, int NT16c, int nparts, int AP16,
                           const double* __restrict__ P_g, const double* __restrict__ lam_g,
                           float* __restrict__ tab_g, float* __restrict__ betaf_g) {
-    const T5Plan p = t5_plan(NT, NT16);
-    const int s = blockIdx.x, tid = threadIdx.x;
+    // one table set per (column, alpha part): a part is the NT16c alpha tiles one CTA of the screen handles
+    const T5Plan p = t5_plan(NT, NT16c);
+    const int s = blockIdx.x, part = blockIdx.y, tid = threadIdx.x;
+    const int a_off = part * p.NA;
     const int n = n_g[s];
     if (n < 2) return;
     const int DP = p.DP;
-    float* tab = tab_g + (size_t)s * (p.tab_bytes / 4);
+    float* tab = tab_g + ((size_t)s * nparts + part) * (p.tab_bytes / 4);
     const double* P = P_g + (long long)s * DP * DP;
     const double* lam = lam_g + (long long)s * DP;
     for (int idx = tid; idx < p.KC * p.N1 * 4; idx += blockDim.x) {
@@ -136,10 +139,11 @@ __global__ void __launch_bounds__(256)
         tab[p.pl_off / 4 + idx] = to_tf32((float)(v - (double)hi));
     }
     const double dn = (double)(nloo_g ? nloo_g[s] : n);
-    for (int i = tid; i < p.NA; i += blockDim.x)
-        betaf_g[(long long)s * p.NA + i] = (i < A) ? (float)((1.0 - alphas[i]) / (dn - 1.0)) : 0.f;
+    if (part == 0)
+        for (int i = tid; i < AP16; i += blockDim.x)
+            betaf_g[(long long)s * AP16 + i] = (i < A) ? (float)((1.0 - alphas[i]) / (dn - 1.0)) : 0.f;
     for (int idx = tid; idx < p.KC * p.NA * 4; idx += blockDim.x) {
-        const int e = idx & 3, i = (idx >> 2) % p.NA, c = (idx >> 2) / p.NA;
+        const int e = idx & 3, i = a_off + (idx >> 2) % p.NA, c = (idx >> 2) / p.NA;
         const int j = 4 * c + e;
         double w = 0.0;
         if (j < D && i < A) {
@@ -158,8 +162,10 @@ template <int NT, int NH16>
 __global__ void __launch_bounds__(kT5Threads, 1)
     loo_screen5_kernel(const float* __restrict__ xt, const double* __restrict__ mu_g,
                        const float* __restrict__ tab_g, const float* __restrict__ betaf_g,
-                       const int* __restrict__ n_g, int L, int NT16, int lines_per_chunk,
+                       const int* __restrict__ n_g, int L, int NT16, int AP16, int lines_per_chunk,
                        double* __restrict__ fscreen, const int* __restrict__ ncomp) {
+    // NT16 = alpha tiles of THIS CTA (blockIdx.z selects the alpha part; windows of more than 72 bands split the
+    // alphas over two CTAs so that tables and accumulators fit shared memory and TMEM), AP16 = padded alphas in all
     constexpr int DP = 8 * NT, N1 = (DP + 15) / 16 * 16;
     constexpr uint32_t C_XH = 0, C_XL = DP, C_Y = 2 * DP, C_ZL = 2 * DP + N1, C_R = 3 * DP + N1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -170,12 +176,14 @@ __global__ void __launch_bounds__(kT5Threads, 1)
 
     const int s = blockIdx.x, chunk = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    double* out = fscreen + ((long long)s * gridDim.y + chunk) * NA;
+    const int a_off = blockIdx.z * NA;                           // first alpha of this CTA's part
+    const int na_out = min(NA, AP16 - a_off);                    // alphas of the part that exist
+    double* out = fscreen + ((long long)s * gridDim.y + chunk) * AP16 + a_off;
     if (n_g[s] < 2) return;                                      // nothing to search (K4 handles n < 2)
     const int c_begin = chunk * lines_per_chunk;
     const int c_end = min(ncomp ? min(L, ncomp[s]) : L, c_begin + lines_per_chunk);   // compacted mode pass: ncomp[s] rows
     if (c_end <= c_begin) {                                      // empty tail chunk
-        for (int i = tid; i < NA; i += blockDim.x) out[i] = 0.0;
+        for (int i = tid; i < na_out; i += blockDim.x) out[i] = 0.0;
         return;
     }
     const int nrows = c_end - c_begin;
@@ -211,7 +219,7 @@ __global__ void __launch_bounds__(kT5Threads, 1)
         mu2[i] = make_float2(mh, (float)(m - (double)mh));
     }
     for (int i = tid; i < NA; i += blockDim.x) {
-        const float b = betaf_g[(long long)s * NA + i];
+        const float b = (i < na_out) ? betaf_g[(long long)s * AP16 + a_off + i] : 0.f;
         const float binv = 1.0f / b;
         beta_s[i] = b;
         // beta == 0 (alpha == 1, padding): u == 0 and every term vanishes; keep the constants finite
@@ -229,7 +237,8 @@ __global__ void __launch_bounds__(kT5Threads, 1)
         if (warp == 0 && lane == 0) {
             // ---------------- producer: tables once, then 64-row half tiles through the ring
             mbar_expect_tx(&bars[B_TAB], p.tab_bytes);
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(tab_g) + (size_t)s * p.tab_bytes;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(tab_g) +
+                                       ((size_t)s * gridDim.z + blockIdx.z) * p.tab_bytes;
             for (uint32_t off = 0; off < p.tab_bytes; off += 32768u) {
                 const uint32_t bytes = min(32768u, p.tab_bytes - off);
                 bulk_g2s(smem_raw + off, src + off, bytes, &bars[B_TAB]);
@@ -460,7 +469,7 @@ __global__ void __launch_bounds__(kT5Threads, 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
     const double* red = reinterpret_cast<const double*>(ring);
-    for (int i = tid; i < NA; i += blockDim.x) {
+    for (int i = tid; i < na_out; i += blockDim.x) {
         const int half = (i >= NA_a) ? 1 : 0, j = i - (half ? NA_a : 0);
         double a = 0.0;
 #pragma unroll
@@ -539,40 +548,63 @@ __global__ void __launch_bounds__(128, 1)
 }  // namespace
 
 // ------------------------------------------------------------------ launchers
-bool screen5_supported(const Dims& d) {
-    if (d.NT < 1 || d.NT > 9 || d.NT16 < 1 || d.NT16 > 14) return false;
-    const T5Plan p = t5_plan(d.NT, d.NT16);
-    if (3 * p.DP + p.N1 + p.NA > 512) return false;
-    // reduction scratch (8 warps x 112 doubles) reuses the ring
-    if ((size_t)kT5Stages * kT5HalfRows * p.DP * 4 < (size_t)8 * 7 * 16 * sizeof(double)) return false;
-    return p.total <= 227u * 1024u;
+// alpha parts (CTAs per column and chunk along the alphas) the screen needs for this window: 1 up to 72 bands, 2 up to
+// 88 bands (tables 146 KB + ring 68 KB of shared memory, 472 TMEM columns); 0 = does not fit
+static int screen5_parts(const Dims& d) {
+    if (d.NT < 1 || d.NT16 < 1 || d.NT16 > 14) return 0;
+    for (int parts = 1; parts <= 2; ++parts) {
+        if (parts == 1 && d.NT > 9) continue;
+        if (parts == 2 && (d.NT < 10 || d.NT > 11)) continue;
+        const int nt16c = (d.NT16 + parts - 1) / parts;
+        const int nh16 = parts == 1 ? 7 : 4;
+        if (nt16c > 2 * nh16) continue;
+        const T5Plan p = t5_plan(d.NT, nt16c);
+        if (3 * p.DP + p.N1 + p.NA > 512) continue;
+        // reduction scratch (8 warps x nh16 x 16 doubles) reuses the ring
+        if ((size_t)kT5Stages * kT5HalfRows * p.DP * 4 < (size_t)8 * nh16 * 16 * sizeof(double)) continue;
+        if (p.total <= 227u * 1024u) return parts;
+    }
+    return 0;
 }
 
-size_t screen5_table_floats(const Dims& d) { return t5_plan(d.NT, d.NT16).tab_bytes / 4; }
+bool screen5_supported(const Dims& d) { return screen5_parts(d) > 0; }
+
+size_t screen5_table_floats(const Dims& d) {
+    const int parts = std::max(1, screen5_parts(d));
+    return (size_t)parts * (t5_plan(d.NT, (d.NT16 + parts - 1) / parts).tab_bytes / 4);
+}
 
 int screen5_lines_per_chunk(const Dims& d, int nchunk) {
     int lpc = (d.L + nchunk - 1) / nchunk;
     return (lpc + 127) / 128 * 128;
 }
 
-template <int NT>
-static void launch_screen5_t(const Dims& d, const float* xt, const double* mu, const float* tab, const float* betaf,
-                             const int* n, int nchunk, double* fscreen, cudaStream_t st) {
-    const T5Plan p = t5_plan(d.NT, d.NT16);
-    cudaFuncSetAttribute(loo_screen5_kernel<NT, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);
-    dim3 grid(d.S, nchunk);
-    loo_screen5_kernel<NT, 7><<<grid, kT5Threads, p.total, st>>>(xt, mu, tab, betaf, n, d.L, d.NT16,
-                                                                 screen5_lines_per_chunk(d, nchunk), fscreen, d.nrows);
+template <int NT, int NH16>
+static void launch_screen5_t(const Dims& d, int parts, const float* xt, const double* mu, const float* tab,
+                             const float* betaf, const int* n, int nchunk, double* fscreen, cudaStream_t st) {
+    const int nt16c = (d.NT16 + parts - 1) / parts;
+    const T5Plan p = t5_plan(d.NT, nt16c);
+    cudaFuncSetAttribute(loo_screen5_kernel<NT, NH16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.total);
+    dim3 grid(d.S, nchunk, parts);
+    loo_screen5_kernel<NT, NH16><<<grid, kT5Threads, p.total, st>>>(xt, mu, tab, betaf, n, d.L, nt16c, d.AP16,
+                                                                    screen5_lines_per_chunk(d, nchunk), fscreen,
+                                                                    d.nrows);
 }
 
 void launch_screen5(const Dims& d, const float* xt, const double* mu, const int* n, const int* nloo,
                     const double* alphas, const double* P, const double* lam, float* tab, float* betaf,
                     int nchunk, double* fscreen, cudaStream_t st) {
-    screen5_tables_kernel<<<d.S, 256, 0, st>>>(n, nloo, alphas, d.A, d.D, d.NT, d.NT16, P, lam, tab, betaf);
+    const int parts = screen5_parts(d);
+    if (parts < 1) return;
+    const int nt16c = (d.NT16 + parts - 1) / parts;
+    screen5_tables_kernel<<<dim3(d.S, parts), 256, 0, st>>>(n, nloo, alphas, d.A, d.D, d.NT, nt16c, parts, d.AP16, P, lam,
+                                                            tab, betaf);
     switch (d.NT) {
-#define CMF_CASE(k) case k: launch_screen5_t<k>(d, xt, mu, tab, betaf, n, nchunk, fscreen, st); break;
+#define CMF_CASE(k) case k: launch_screen5_t<k, 7>(d, parts, xt, mu, tab, betaf, n, nchunk, fscreen, st); break;
         CMF_CASE(1) CMF_CASE(2) CMF_CASE(3) CMF_CASE(4) CMF_CASE(5) CMF_CASE(6) CMF_CASE(7) CMF_CASE(8) CMF_CASE(9)
 #undef CMF_CASE
+        case 10: launch_screen5_t<10, 4>(d, parts, xt, mu, tab, betaf, n, nchunk, fscreen, st); break;
+        case 11: launch_screen5_t<11, 4>(d, parts, xt, mu, tab, betaf, n, nchunk, fscreen, st); break;
         default: break;
     }
 }
