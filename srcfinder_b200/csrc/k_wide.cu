@@ -509,6 +509,272 @@ __global__ void __launch_bounds__(NTHR, 1024 / NTHR)
     }
 }
 
+// ---------------------------------------------------------------------------------------- W3: blocked tridiagonalisation
+// The same reduction in the blocked (LAPACK dsytrd / dlatrd / dorgtr) form, lower variant, panels of 8 columns.
+// wide_tred_kernel above touches the whole trailing matrix three times per column (matvec, rank-2 update read and
+// write) and ncu shows it bound by DRAM (800 MB of traffic per 416 x 416 matrix: 148 matrices do not fit the L2).
+// Here the trailing matrix is only READ once per column (w = A v with the corrections -V (W^T v) - W (V^T v) of the
+// panel's earlier reflectors) and updated once per panel (A -= V W^T + W V^T); Q is formed panel by panel with the
+// compact WY form (I - V T V^T), two passes per 16 reflectors instead of per reflector: ~240 MB per matrix.
+// A = Q T Q^T, Q = H_0 H_1 ... H_(n-2), H_c = I - tau_c v_c v_c^T, v_c zero above row c+1; v_c is kept in ROW c of
+// the (full, symmetric) matrix.  The panels V, W live in shared memory t-major ([16][DP]) so that every access is
+// either a broadcast or conflict-free.  Output: d, e in the EISPACK convention of wide_ql_kernel, Q in `work`.
+constexpr int kTbNB = 8;       // 1024 threads leave 64 registers each: 2 x 8 panel values per thread in the update
+constexpr int kTbThreads = 1024;
+
+__device__ __forceinline__ double tb_block_sum(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kTbThreads / 32; ++w) t += red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(kTbThreads, 1)
+    wide_tredb_kernel(double* __restrict__ work, const int* __restrict__ n_g, int D, int DP, double* __restrict__ d_g,
+                      double* __restrict__ e_g) {
+    constexpr int NB = kTbNB, NW = kTbThreads / 32;
+    extern __shared__ double sm[];
+    double* Vt = sm;                    // [NB][DP]   (t-major)
+    double* Wt = Vt + NB * DP;          // [NB][DP]
+    double* vv = Wt + NB * DP;          // [DP] current reflector
+    double* ww = vv + DP;               // [DP] column / w vector
+    double* dv = ww + DP;               // [DP]
+    double* ev = dv + DP;               // [DP]
+    double* tauv = ev + DP;             // [DP]
+    double* tmp = tauv + DP;            // [2 NB]
+    double* Gm = tmp + 2 * NB;          // [NB][NB]
+    double* Tm = Gm + NB * NB;          // [NB][NB]
+    double* pbuf = Tm + NB * NB;        // [2][NB][512] partial sums of phase 2
+    __shared__ double red[NW];
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (n_g[s] < 2) {
+        for (int i = tid; i < DP; i += blockDim.x) { d_g[(long long)s * DP + i] = 0.0; e_g[(long long)s * DP + i] = 0.0; }
+        return;
+    }
+    double* A = work + (long long)s * DP * DP;
+    const int LD = DP, n = D;
+    for (int i = tid; i < DP; i += blockDim.x) { dv[i] = 0.0; ev[i] = 0.0; tauv[i] = 0.0; }
+    // ---------------------------------------------------------------- phase 1: A -> tridiagonal, reflectors in rows
+    for (int i0 = 0; i0 < n - 1; i0 += NB) {
+        const int pb = min(NB, n - 1 - i0);
+        for (int i = tid; i < 2 * NB * DP; i += blockDim.x) Vt[i] = 0.0;      // Vt and Wt are contiguous
+        __syncthreads();
+        for (int i = 0; i < pb; ++i) {
+            const int c = i0 + i;
+            // (1) column c of the matrix as updated by the panel's earlier reflectors (row c read: symmetric)
+            for (int r = c + tid; r < n; r += blockDim.x) {
+                double a = A[(long long)c * LD + r];
+                for (int t = 0; t < i; ++t)
+                    a -= __dadd_rn(__dmul_rn(Vt[t * DP + r], Wt[t * DP + c]), __dmul_rn(Wt[t * DP + r], Vt[t * DP + c]));
+                ww[r] = a;
+            }
+            __syncthreads();
+            // (2) reflector annihilating rows c+2.. of the column
+            double part = 0.0;
+            for (int r = c + 2 + tid; r < n; r += blockDim.x) part += ww[r] * ww[r];
+            const double xn2 = tb_block_sum(part, red);
+            const double alpha = ww[c + 1];
+            double beta = alpha, tau_c = 0.0, scal = 0.0;
+            if (xn2 > 0.0) {
+                beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+                tau_c = (beta - alpha) / beta;
+                scal = 1.0 / (alpha - beta);
+            }
+            if (tid == 0) { dv[c] = ww[c]; ev[c + 1] = beta; tauv[c] = tau_c; }
+            for (int r = c + 1 + tid; r < n; r += blockDim.x) {
+                const double v = (r == c + 1) ? 1.0 : ww[r] * scal;
+                vv[r] = v;
+                Vt[i * DP + r] = v;
+            }
+            __syncthreads();
+            // (3) w = A[c+1:, c+1:] v on the matrix as it was when the panel started: one warp per row
+            for (int r = c + 1 + warp; r < n; r += NW) {
+                const double* row = A + (long long)r * LD;
+                double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+                int k = c + 1 + lane;
+                for (; k + 96 < n; k += 128) {
+                    const double x0 = row[k], x1 = row[k + 32], x2 = row[k + 64], x3 = row[k + 96];
+                    g0 += x0 * vv[k]; g1 += x1 * vv[k + 32]; g2 += x2 * vv[k + 64]; g3 += x3 * vv[k + 96];
+                }
+                for (; k < n; k += 32) g0 += row[k] * vv[k];
+                double gj = (g0 + g1) + (g2 + g3);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) gj += __shfl_xor_sync(0xffffffffu, gj, o);
+                if (lane == 0) ww[r] = gj;
+            }
+            // (4) tmp[2t] = W_t . v, tmp[2t+1] = V_t . v over rows c+1.. : one warp per product (2 i <= 32)
+            if (warp < 2 * i) {
+                const double* src = ((warp & 1) ? Vt : Wt) + (warp >> 1) * DP;
+                double g = 0.0;
+                for (int r = c + 1 + lane; r < n; r += 32) g += src[r] * vv[r];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+                if (lane == 0) tmp[warp] = g;
+            }
+            __syncthreads();
+            // (5) w <- tau (w - V (W^T v) - W (V^T v)); w <- w - (tau/2) (w . v) v
+            part = 0.0;
+            for (int r = c + 1 + tid; r < n; r += blockDim.x) {
+                double w = ww[r];
+                for (int t = 0; t < i; ++t)
+                    w -= __dadd_rn(__dmul_rn(Vt[t * DP + r], tmp[2 * t]), __dmul_rn(Wt[t * DP + r], tmp[2 * t + 1]));
+                w *= tau_c;
+                ww[r] = w;
+                part += w * vv[r];
+            }
+            const double wv = tb_block_sum(part, red);
+            const double alpha2 = -0.5 * tau_c * wv;
+            for (int r = c + 1 + tid; r < n; r += blockDim.x) Wt[i * DP + r] = ww[r] + alpha2 * vv[r];
+            __syncthreads();
+        }
+        // the panel's reflectors go into rows c of the matrix (dead from now on), v_c[c+1] = 1 stored explicitly
+        for (int i = warp; i < pb; i += NW) {
+            const int c = i0 + i;
+            for (int r = c + 1 + lane; r < n; r += 32) A[(long long)c * LD + r] = Vt[i * DP + r];
+        }
+        // trailing update A[r0:, r0:] -= V W^T + W V^T (every element, so the matrix stays exactly symmetric)
+        const int r0 = i0 + pb;
+        for (int r = r0 + warp; r < n; r += NW) {
+            double vr[NB], wr[NB];
+#pragma unroll
+            for (int t = 0; t < NB; ++t) { vr[t] = Vt[t * DP + r]; wr[t] = Wt[t * DP + r]; }
+            double* row = A + (long long)r * LD;
+            for (int k = r0 + lane; k < n; k += 32) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int t = 0; t < NB; ++t)
+                    sacc += __dadd_rn(__dmul_rn(vr[t], Wt[t * DP + k]), __dmul_rn(wr[t], Vt[t * DP + k]));
+                row[k] -= sacc;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) dv[n - 1] = A[(long long)(n - 1) * LD + (n - 1)];
+    __syncthreads();
+    for (int i = tid; i < DP; i += blockDim.x) {
+        d_g[(long long)s * DP + i] = (i < n) ? dv[i] : 0.0;
+        e_g[(long long)s * DP + i] = (i < n) ? ev[i] : 0.0;
+    }
+    // ---------------------------------------------------------------- phase 2: Q = H_0 ... H_(n-2), panels in reverse
+    int prev_lo = n;                                   // Q occupies [prev_lo:, prev_lo:] so far
+    for (int i0 = ((n - 2) / NB) * NB; i0 >= 0; i0 -= NB) {
+        const int pb = min(NB, n - 1 - i0);
+        const int lo = i0 + 1;
+        // the panel's reflectors, from rows c of the matrix
+        for (int i = tid; i < NB * DP; i += blockDim.x) Vt[i] = 0.0;
+        __syncthreads();
+        for (int i = warp; i < pb; i += NW) {
+            const int c = i0 + i;
+            for (int r = c + 1 + lane; r < n; r += 32) Vt[i * DP + r] = A[(long long)c * LD + r];
+        }
+        __syncthreads();
+        // extend Q to [lo:, lo:] with the identity: rows lo..prev_lo-1 entirely, columns lo..prev_lo-1 of the rows below
+        for (int r = lo + warp; r < n; r += NW) {
+            double* row = A + (long long)r * LD;
+            const int kend = (r < prev_lo) ? n : prev_lo;
+            for (int k = lo + lane; k < kend; k += 32) row[k] = (k == r) ? 1.0 : 0.0;
+        }
+        // Gram of the reflectors G[t][u] = v_t . v_u (u < t), one warp per pair
+        for (int pidx = warp; pidx < pb * pb; pidx += NW) {
+            const int t = pidx / pb, u = pidx % pb;
+            if (u >= t) continue;
+            double g = 0.0;
+            for (int r = lo + lane; r < n; r += 32) g += Vt[t * DP + r] * Vt[u * DP + r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+            if (lane == 0) { Gm[t * NB + u] = g; Gm[u * NB + t] = g; }
+        }
+        __syncthreads();
+        // T of the compact WY form (forward, columnwise): T[i][i] = tau_i, T[0:i, i] = -tau_i T[0:i, 0:i] (V^T v_i)
+        if (tid == 0) {
+            for (int i = 0; i < pb; ++i) {
+                const double ti = tauv[i0 + i];
+                for (int u = 0; u < i; ++u) {
+                    double a = 0.0;
+                    for (int k = u; k < i; ++k) a += Tm[u * NB + k] * Gm[k * NB + i];
+                    Tm[u * NB + i] = -ti * a;
+                }
+                Tm[i * NB + i] = ti;
+            }
+        }
+        __syncthreads();
+        // Q_sub <- Q_sub - V (T (V^T Q_sub)): thread <-> (column j, row parity), coalesced across j; the two partial
+        // sums of V^T Q are added in a fixed order
+        {
+            const int part = tid >> 9, jj = tid & 511;
+            for (int jb = lo; jb < n; jb += 512) {
+                const int j = jb + jj;
+                double acc[NB];
+#pragma unroll
+                for (int t = 0; t < NB; ++t) acc[t] = 0.0;
+                if (j < n) {
+                    int r = lo + part;
+                    for (; r + 6 < n; r += 8) {
+                        const double q0 = A[(long long)r * LD + j], q1 = A[(long long)(r + 2) * LD + j],
+                                     q2 = A[(long long)(r + 4) * LD + j], q3 = A[(long long)(r + 6) * LD + j];
+#pragma unroll
+                        for (int t = 0; t < NB; ++t)
+                            acc[t] += (Vt[t * DP + r] * q0 + Vt[t * DP + r + 2] * q1) +
+                                      (Vt[t * DP + r + 4] * q2 + Vt[t * DP + r + 6] * q3);
+                    }
+                    for (; r < n; r += 2) {
+                        const double qv = A[(long long)r * LD + j];
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) acc[t] += Vt[t * DP + r] * qv;
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < NB; ++t) pbuf[(part * NB + t) * 512 + jj] = acc[t];
+                __syncthreads();
+                if (j < n) {
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) acc[t] = pbuf[t * 512 + jj] + pbuf[(NB + t) * 512 + jj];
+                    // x = T acc, in place (x[t] needs acc[u >= t] only, T is upper triangular)
+#pragma unroll
+                    for (int t = 0; t < NB; ++t) {
+                        double a = 0.0;
+#pragma unroll
+                        for (int u = 0; u < NB; ++u)
+                            if (u >= t && u < pb && t < pb) a += Tm[t * NB + u] * acc[u];
+                        acc[t] = a;
+                    }
+                    int r = lo + part;
+                    for (; r + 6 < n; r += 8) {
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) {
+                            a0 += Vt[t * DP + r] * acc[t]; a1 += Vt[t * DP + r + 2] * acc[t];
+                            a2 += Vt[t * DP + r + 4] * acc[t]; a3 += Vt[t * DP + r + 6] * acc[t];
+                        }
+                        A[(long long)r * LD + j] -= a0; A[(long long)(r + 2) * LD + j] -= a1;
+                        A[(long long)(r + 4) * LD + j] -= a2; A[(long long)(r + 6) * LD + j] -= a3;
+                    }
+                    for (; r < n; r += 2) {
+                        double a = 0.0;
+#pragma unroll
+                        for (int t = 0; t < NB; ++t) a += Vt[t * DP + r] * acc[t];
+                        A[(long long)r * LD + j] -= a;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        prev_lo = lo;
+        __syncthreads();
+    }
+    // row and column 0 of Q
+    for (int k = tid; k < n; k += blockDim.x) {
+        A[k] = (k == 0) ? 1.0 : 0.0;
+        A[(long long)k * LD] = (k == 0) ? 1.0 : 0.0;
+    }
+    if (n == 1 && tid == 0) A[0] = 1.0;
+}
+
 // ---------------------------------------------------------------------------------------- W3: QL recurrences
 // Implicit-shift QL (tql2) on the tridiagonal (d, e) of every column, WITHOUT the eigenvectors: the plane-rotation
 // recurrence is a serial FP64 chain that only needs (d, e), so one warp per column runs it (lane 0; all lanes
@@ -1007,9 +1273,13 @@ void launch_wide_eigen(const Dims& d, const double* gram, const int* n, const do
     const int iter_cap = wide_iter_cap(d);
     wide_cov_kernel<<<d.S, 256, (size_t)3 * d.DP * sizeof(double), st>>>(gram, n, d.D, d.DP, mu, ctr, qexp, mode, work,
                                                                          dinv, slogT, status);
-    int nthr = 1024;
-    if (const char* e = cmf_hook("CMF_WIDE_TRED")) nthr = atoi(e);      // tuning hook (tools build)
-    if (nthr == 512) {
+    int nthr = 0;                                                       // 0: the blocked kernel
+    if (const char* e = cmf_hook("CMF_WIDE_TRED")) nthr = atoi(e);      // tuning hook (tools build): 1024 / 512 = unblocked
+    if (nthr == 0) {
+        const size_t tsm = (size_t)((2 * kTbNB + 5) * d.DP + 2 * kTbNB + 2 * kTbNB * kTbNB + 2 * kTbNB * 512) * sizeof(double);
+        cudaFuncSetAttribute(wide_tredb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        wide_tredb_kernel<<<d.S, kTbThreads, tsm, st>>>(work, n, d.D, d.DP, dvec, evec);
+    } else if (nthr == 512) {
         const size_t tsm = (size_t)(4 + 512 / 32) * d.DP * sizeof(double);
         cudaFuncSetAttribute(wide_tred_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
         wide_tred_kernel<512><<<d.S, 512, tsm, st>>>(work, n, d.D, d.DP, dvec, evec);
