@@ -936,7 +936,7 @@ __global__ void __launch_bounds__(kWrThreads, 1)
                 for (int k = 0; k < 8; ++k) {
                     const int i = m - 1 - t - k;             // rotation t + k acts on columns (i, i + 1)
                     q[(i + 1) * rows + tid] = fma(cs[k].x, f, cs[k].y * z[k]);
-                    f = fma(cs[k].x, z[k], -(cs[k].y * f));
+                    f = fma(-cs[k].y, f, cs[k].x * z[k]);       // one FMA on the chain: c * z does not wait for f
                 }
             }
             for (; t < cnt; ++t) {
@@ -944,7 +944,7 @@ __global__ void __launch_bounds__(kWrThreads, 1)
                 const double2 c1 = cr[t];
                 const double zi = q[i * rows + tid];
                 q[(i + 1) * rows + tid] = fma(c1.x, f, c1.y * zi);
-                f = fma(c1.x, zi, -(c1.y * f));
+                f = fma(-c1.y, f, c1.x * zi);
             }
             q[(m - cnt) * rows + tid] = f;
         }
