@@ -72,8 +72,8 @@ enum {
     CMF_OUT_PCA = 17,         /* double [S][L][pcadim] projections the on-device k-means partitioned (:311) */
     CMF_OUT_KMEANS_ITERS = 18,/* int32  [S]      reassignment passes the k-means needed */
     CMF_OUT_FLAGS = 19,       /* uint8  [lines][samples] of the last cmf_pixel_flags() call */
-    CMF_OUT_SCREEN_CHECK = 20 /* double [S]      screened runs: largest |exact - screened| nll over the alphas that were
-                                                  re-evaluated exactly, as a fraction of the margin (0 = column decided by
+    CMF_OUT_SCREEN_CHECK = 20 /* double [S]      screened runs: spread (max - min) of exact - screened nll over the alphas
+                                                  that were re-evaluated exactly, as a fraction of the margin (0 = decided by
                                                   the screen alone or fully exact); the run re-evaluates every alpha of a
                                                   column in FP64 when this reaches 1/4, see cmf_set_screen_margin */
 };
@@ -154,10 +154,12 @@ int cmf_set_exclusion(cmf_ctx* ctx, const uint8_t* exclude);
 
 /* The alpha search is screened on the tensor cores and every alpha whose screened nll lies within
  * rel_margin * max|screened part of nll| of the minimum is re-evaluated exactly (CMF_OUT_SCREEN_TOL holds the absolute
- * margin per column).  Default 2e-5.  With certify != 0 (default) every run carries a runtime certificate: a refined
+ * margin per column).  Default 1e-5.  With certify != 0 (default) every run carries a runtime certificate: a refined
  * column also gets its best EXCLUDED 8-alpha tile evaluated in FP64; if the exact minimum falls into that tile, or the
- * measured |exact - screened| of the column reaches 1/4 of the margin, all alphas of the column are re-evaluated in
- * FP64; and if the worst measurement of the flightline reaches 1/4, so are the columns the screen decided alone.
+ * measured spread (max - min over the evaluated alphas) of exact - screened nll reaches 1/4 of the margin -- only the
+ * variation of the screening error between alphas can misorder them, a common bias cancels -- all alphas of the column
+ * are re-evaluated in FP64; and if the worst measurement of the flightline reaches 1/4, so are the columns the screen
+ * decided alone.
  * certify = 0 or a smaller margin are for diagnostics (tests/test_gpu_parity.py drives both). */
 int cmf_set_screen_margin(cmf_ctx* ctx, double rel_margin, int certify);
 

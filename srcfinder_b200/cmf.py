@@ -168,7 +168,7 @@ class ColumnwiseMF(object):
             raise CmfError("exclusion mask must be (lines, samples) = %r, got %r" % ((self.L, self.S), ex.shape))
         self._check(self._lib.cmf_set_exclusion(self._ctx, C.c_void_p(ex.ctypes.data)))
 
-    def set_screen_margin(self, rel_margin=2.0e-5, certify=True):
+    def set_screen_margin(self, rel_margin=1.0e-5, certify=True):
         """Margin of the tensor-core screen of the alpha search and its runtime certificate (diagnostics)."""
         self._check(self._lib.cmf_set_screen_margin(self._ctx, float(rel_margin), 1 if certify else 0))
 

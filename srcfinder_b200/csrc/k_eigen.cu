@@ -833,7 +833,7 @@ __global__ void __launch_bounds__(256)
     const int Sp = (S + 1) & ~1;
     // second pass of the screening certificate: only the columns that are re-evaluated exactly
     if (only_g != nullptr && only_g[s] == 0ull) return;
-    __shared__ double err_sh[8];
+    __shared__ double err_sh[16];
     if (tid == 0 && check_g) { check_g[s] = 0.0; redo_g[s] = 0ull; }   // overwritten below for a refined column
     // background-mode pass without members in this column (or past the end of its mode list): the column
     // keeps what earlier passes produced; the scoring pass has no member to write either
@@ -863,7 +863,11 @@ __global__ void __launch_bounds__(256)
         const int sel = screened ? sel_index[s] : -2;
         const unsigned long long tmask = screened ? tile_mask[s] : ~0ull;
         const double const_term = (double)D * log(2.0 * M_PI);
-        double emax = 0.0;          // largest |exact - screened| over the alphas evaluated exactly (certificate)
+        // certificate: spread of (exact - screened) over the alphas evaluated exactly.  Only DIFFERENCES between
+        // alphas decide the argmin, so a bias of the screen that is common to the alphas of a column cancels; what can
+        // misorder two alphas is how much the screening error varies between them: max - min of (exact - screened).
+        const double big = __longlong_as_double(0x7ff0000000000000LL);
+        double dmax = -big, dmin = big;
         for (int i = tid; i < A; i += blockDim.x) {
             double v;
             if (!screened || ((tmask >> ((i >> 3) & 63)) & 1ull)) {
@@ -874,7 +878,7 @@ __global__ void __launch_bounds__(256)
                 else v = 0.5 * (const_term + ld) + fs / (2.0 * nl);
                 if (screened && check_g) {
                     const double old = nll_g[(long long)s * A + i];
-                    if (fabs(v) < inf && fabs(old) < inf) emax = fmax(emax, fabs(v - old));
+                    if (fabs(v) < inf && fabs(old) < inf) { dmax = fmax(dmax, v - old); dmin = fmin(dmin, v - old); }
                 }
                 nll_g[(long long)s * A + i] = v;
             } else {
@@ -883,8 +887,11 @@ __global__ void __launch_bounds__(256)
             nll[i] = v;
         }
         if (check_g) {
-            for (int o = 16; o > 0; o >>= 1) emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
-            if ((tid & 31) == 0) err_sh[tid >> 5] = emax;
+            for (int o = 16; o > 0; o >>= 1) {
+                dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+                dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+            }
+            if ((tid & 31) == 0) { err_sh[tid >> 5] = dmax; err_sh[8 + (tid >> 5)] = dmin; }
         }
         __syncthreads();
         if (tid == 0) {
@@ -913,8 +920,9 @@ __global__ void __launch_bounds__(256)
                 // Runtime certificate, part 2: this column is trusted if the exact minimum does not sit in the probe
                 // tile (the best tile the screen had EXCLUDED) and the measured screening error is below
                 // 1/kCertFactor of the margin; otherwise every alpha of the column is re-evaluated in FP64.
-                double e = 0.0;
-                for (int w8 = 0; w8 < (int)(blockDim.x >> 5); ++w8) e = fmax(e, err_sh[w8]);
+                double hi = -inf, lo = inf;
+                for (int w8 = 0; w8 < (int)(blockDim.x >> 5); ++w8) { hi = fmax(hi, err_sh[w8]); lo = fmin(lo, err_sh[8 + w8]); }
+                const double e = (hi >= lo) ? hi - lo : 0.0;        // spread of the screening error over the evaluated alphas
                 double frac = 0.0;
                 unsigned long long redo = 0ull;
                 if (screened && sel == -2 && tmask != ~0ull) {

@@ -172,10 +172,17 @@ def test_screening_selects_the_exact_argmin(L, S, seed, bad):
     assert np.array_equal(ex["mf"], sc["mf"], equal_nan=True)
     fin = np.isfinite(ex_nll) & np.isfinite(sc_nll)
     assert np.array_equal(np.isfinite(ex_nll), np.isfinite(sc_nll))
-    # the selection is provably the exact argmin while the screening error is below half the margin the
-    # screen used for that column; require a further factor 2 of head-room
-    err = np.where(fin, np.abs(ex_nll - sc_nll), 0.0).max(axis=1)
-    assert np.all(err <= 0.25 * tol), (err / tol).max()
+    # only the VARIATION of the screening error between alphas can misorder them (a common bias cancels): among the
+    # alphas near the minimum (within 20 margins) exact - screened must vary by less than a quarter of the margin
+    for c in range(Sc):
+        f = fin[c]
+        if not f.any():
+            continue
+        # (the alphas of the refined tiles already hold their exact value: compare the screened-only ones)
+        near = f & (ex_nll[c] <= np.min(ex_nll[c][f]) + 20.0 * tol[c]) & (ex_nll[c] != sc_nll[c])
+        if near.sum() >= 2:
+            diff = (ex_nll[c] - sc_nll[c])[near]
+            assert diff.max() - diff.min() <= 0.25 * tol[c], ((diff.max() - diff.min()) / tol[c], c)
     assert np.all(ncand >= 1) and np.all(ncand <= 201)
     ref = orc.cmf_cube(cube, ab, active)
     assert np.array_equal(ref["alpha_index"], sc["alpha_index"])
@@ -440,8 +447,9 @@ def test_full_flightline_properties():
         r2 = eng.results()
         chk = eng.screen_check()
         # the screened search at flightline size against the all-FP64 search, and the same with a useless margin and
-        # no certificate: with 598 columns of 20 000 lines the screening error (~0.16 of the default margin) is far
-        # above 1e-9 of it, so near-tied columns go wrong -- the margin and the certificate are what prevents that
+        # no certificate: with 598 columns of 20 000 lines the variation of the screening error between neighbouring
+        # alphas (~0.06 of the default margin) is far above 1e-9 of it, so near-tied columns go wrong -- the margin
+        # and the certificate are what prevents that
         eng.run(exact=True)
         ex_idx = eng.alpha_index()
         eng.set_screen_margin(1.0e-9, certify=False)
