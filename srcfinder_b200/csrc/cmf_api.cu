@@ -71,6 +71,7 @@ struct cmf_ctx {
     uint8_t *sel = nullptr, *inlier = nullptr;
     int16_t *cluster_img = nullptr, *alpha_img = nullptr;
     int32_t* rowidx = nullptr;    // row of every member pixel in the compacted xt of a background-mode pass
+    float* xt_mode = nullptr;     // the compacted copy (the full copy stays in xt for every mode of the run)
     // on-device partition (cmf_set_clustering) and the -f regulariser (cmf_set_regfull)
     bool auto_cluster = false, regfull = false;
     int pcadim = 6, km_max_iter = 100, y_pd = 0;
@@ -424,13 +425,22 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
             // the members of this mode, compacted to the first rows of every column of xt (in line order): the
             // statistics and the search then cost what the mode holds, not what the flightline holds
             launch_rank(d, ctx->sel, ctx->rowidx, st);
-            ctx->d.rowidx = ctx->rowidx;
-            launch_repack(ctx->d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, 0, d.L,
-                          ctx->sel, 0, st);
-            ctx->d.rowidx = nullptr;
+            float* const xt_full = ctx->xt;
+            // the member rows are gathered from the full column-major copy (one read of the members, one write) ...
+            const bool gathered = launch_compact(d, xt_full, ctx->sel, ctx->rowidx, ctx->nsplit, ctx->lps, ctx->xt_mode,
+                                                 ctx->colsum_part, ctx->colcnt_part, st);
+            if (gathered) {
+                ctx->xt = ctx->xt_mode;
+            } else {      // ... or, for a window that does not fit the gather's thread plan, repacked from the slab
+                ctx->d.rowidx = ctx->rowidx;
+                launch_repack(ctx->d, ctx->slab, ctx->xt, ctx->mask, ctx->colsum_part, ctx->colcnt_part, ctx->lps, 0,
+                              d.L, ctx->sel, 0, st);
+                ctx->d.rowidx = nullptr;
+            }
             ctx->d.nrows = ctx->n;                 // the member count of the mean kernel (first launch of the pass)
             ctx->launches += 3;
             fit_and_score(ctx, exact, ctx->sel, ctx->nuse, no_mark);
+            ctx->xt = xt_full;
             ctx->d.nrows = nullptr;
         }
         }
@@ -469,6 +479,7 @@ int ensure_mode_buffers(cmf_ctx* ctx) {
     A_(dalloc(ctx, &ctx->cluster_img, LS));
     A_(dalloc(ctx, &ctx->alpha_img, LS));
     A_(dalloc(ctx, &ctx->rowidx, LS));
+    if (!ctx->wide) A_(dalloc(ctx, &ctx->xt_mode, LS * ctx->d.DP));
     if (e != cudaSuccess) return fail(ctx, CMF_E_NOMEM, std::string("label buffers: ") + cudaGetErrorString(e));
     return CMF_OK;
 }
@@ -590,7 +601,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     free_buffers(ctx);
     ctx->have_labels = false;
     ctx->labels_d = nullptr; ctx->sel = nullptr; ctx->inlier = nullptr; ctx->cluster_img = nullptr;
-    ctx->alpha_img = nullptr; ctx->rowidx = nullptr;
+    ctx->alpha_img = nullptr; ctx->rowidx = nullptr; ctx->xt_mode = nullptr;
     ctx->auto_cluster = false; ctx->regfull = false; ctx->y_pd = 0;
     ctx->have_excl = false; ctx->excl_sel = nullptr;
     ctx->gram_full = nullptr; ctx->vtop = nullptr; ctx->ypca = nullptr; ctx->qpca = nullptr; ctx->pick = nullptr;

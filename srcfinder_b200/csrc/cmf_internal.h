@@ -132,6 +132,9 @@ void launch_members(const Dims& d, const int32_t* labels, const uint8_t* mask, i
 void launch_fill_f64(double* p, long long n, double v, cudaStream_t st);
 // rowidx[l*S + s] = number of selected pixels of column s above line l (exclusive scan down the lines)
 void launch_rank(const Dims& d, const uint8_t* sel, int32_t* rowidx, cudaStream_t st);
+// member rows of the full column-major copy -> compacted copy + the K0 partial sums / counts of the members
+bool launch_compact(const Dims& d, const float* xt_full, const uint8_t* sel, const int32_t* rowidx, int nsplit,
+                    int lines_per_split, float* xt_mode, double* colsum_part, int* colcnt_part, cudaStream_t st);
 // PCA projection (P, lam = eigenvectors / eigenvalues of the column covariance, launch_eigen target 1) + k-means
 void launch_pca_kmeans(const Dims& d, const float* xt, const uint8_t* mask, const double* mu, const int* n,
                        const double* P, const double* lam, int pcadim, int k, int max_iter, int* pick,

@@ -58,25 +58,41 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---- y[s][l][p] = sum_b (x[l][b] - mu[b]) v[b][p]  (FP64, b ascending), 0 for invalid pixels
+// CTA = (256 lines, column): the tile of xt rows is staged in shared memory with coalesced 16-byte loads (row pitch
+// DP + 1 floats: the row-wise reads of the threads fall on different banks); the wide-window layout (rows of up to
+// 432 floats) does not fit and takes the direct path.
 __global__ void __launch_bounds__(256)
     pca_project_kernel(const float* __restrict__ xt, const uint8_t* __restrict__ mask, const double* __restrict__ mu_g,
-                       const double* __restrict__ vtop_g, int L, int S, int D, int DP, int pd,
+                       const double* __restrict__ vtop_g, int L, int S, int D, int DP, int pd, int staged,
                        double* __restrict__ y_g) {
     extern __shared__ double sm[];
     double* v = sm;                 // [D][pd]
     double* mu = v + D * pd;        // [D]
+    float* tile = reinterpret_cast<float*>(mu + D);     // [256][DP + 1] when staged
     const int s = blockIdx.y, tid = threadIdx.x;
     for (int idx = tid; idx < D * pd; idx += blockDim.x)
         v[idx] = vtop_g[((long long)s * DP + idx / pd) * kMaxPcaDim + idx % pd];
     for (int b = tid; b < D; b += blockDim.x) mu[b] = mu_g[(long long)s * DP + b];
+    const int l0 = blockIdx.x * blockDim.x;
+    const int nl = min((int)blockDim.x, L - l0);
+    const int TP = DP + 1;
+    if (staged) {
+        const float4* src = reinterpret_cast<const float4*>(xt + ((long long)s * L + l0) * DP);
+        const int q4 = DP / 4;
+        for (int i = tid; i < nl * q4; i += blockDim.x) {
+            const float4 x = src[i];
+            float* dst = tile + (i / q4) * TP + 4 * (i % q4);
+            dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w;
+        }
+    }
     __syncthreads();
-    const int l = blockIdx.x * blockDim.x + tid;
+    const int l = l0 + tid;
     if (l >= L) return;
     double acc[kMaxPcaDim];
 #pragma unroll
     for (int p = 0; p < kMaxPcaDim; ++p) acc[p] = 0.0;
     if (mask[(long long)l * S + s]) {
-        const float* row = xt + ((long long)s * L + l) * DP;
+        const float* row = staged ? tile + tid * TP : xt + ((long long)s * L + l) * DP;
         for (int b = 0; b < D; ++b) {
             const double xc = (double)row[b] - mu[b];
 #pragma unroll
@@ -342,8 +358,12 @@ void launch_pca_kmeans(const Dims& d, const float* xt, const uint8_t* mask, cons
                        cudaStream_t st) {
     pca_pick_kernel<<<d.S, 128, 0, st>>>(lam, P, mu, n, d.D, d.DP, pcadim, pick, vtop);
     const dim3 grid((d.L + 255) / 256, d.S);
-    const size_t smem = (size_t)(d.D * pcadim + d.D) * sizeof(double);
-    pca_project_kernel<<<grid, 256, smem, st>>>(xt, mask, mu, vtop, d.L, d.S, d.D, d.DP, pcadim, y);
+    size_t smem = (size_t)(d.D * pcadim + d.D) * sizeof(double);
+    const size_t tile = (size_t)256 * (d.DP + 1) * sizeof(float);
+    const int staged = (smem + tile <= 160 * 1024) ? 1 : 0;
+    if (staged) smem += tile;
+    cudaFuncSetAttribute(pca_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pca_project_kernel<<<grid, 256, smem, st>>>(xt, mask, mu, vtop, d.L, d.S, d.D, d.DP, pcadim, staged, y);
     const size_t smem2 = (size_t)(kKmWarps * k * (pcadim + 1)) * sizeof(long long) + (size_t)k * pcadim * sizeof(double) +
                          (k <= kSmallK ? (size_t)k * (pcadim + 1) * kKmThreads * sizeof(int) : 0);
     if (pcadim <= 8) {

@@ -171,4 +171,63 @@ void launch_rank(const Dims& d, const uint8_t* sel, int32_t* rowidx, cudaStream_
     rank_kernel<<<(d.S + 3) / 4, 128, 0, st>>>(sel, d.L, d.S, rowidx);
 }
 
+
+// Member rows of the full column-major copy -> compacted copy of a background-mode pass, with the column sums and
+// counts of the members (the K0 partials of the pass).  CTA = (column, line split); thread <-> (row lane, 4 bands);
+// every thread adds its rows in line order and the row lanes are added in a fixed order -> deterministic.
+constexpr int kCompactRows = 16;
+
+__global__ void __launch_bounds__(512)
+    compact_kernel(const float* __restrict__ xt_full, const uint8_t* __restrict__ sel,
+                   const int32_t* __restrict__ rowidx, int L, int S, int DP, int lines_per_split,
+                   float* __restrict__ xt_mode, double* __restrict__ colsum_part, int* __restrict__ colcnt_part) {
+    extern __shared__ double csm[];                       // [kCompactRows][DP] partial sums
+    __shared__ int cnt_sh[kCompactRows];
+    const int s = blockIdx.x, split = blockIdx.y;
+    const int Q = DP / 4;                                 // float4 lanes per row
+    const int rr = threadIdx.x / Q, q = threadIdx.x % Q;
+    const int l_begin = split * lines_per_split, l_end = min(L, l_begin + lines_per_split);
+    const bool active = rr < kCompactRows;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int cnt = 0;
+    if (active) {
+        const float* src = xt_full + (long long)s * L * DP + 4 * q;
+        float* dst = xt_mode + (long long)s * L * DP + 4 * q;
+        for (int l = l_begin + rr; l < l_end; l += kCompactRows) {
+            const long long o = (long long)l * S + s;
+            if (sel[o]) {
+                const float4 x = *reinterpret_cast<const float4*>(src + (long long)l * DP);
+                *reinterpret_cast<float4*>(dst + (long long)rowidx[o] * DP) = x;
+                a0 += (double)x.x; a1 += (double)x.y; a2 += (double)x.z; a3 += (double)x.w;
+                ++cnt;
+            }
+        }
+        double* p = csm + rr * DP + 4 * q;
+        p[0] = a0; p[1] = a1; p[2] = a2; p[3] = a3;
+        if (q == 0) cnt_sh[rr] = cnt;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < DP; b += blockDim.x) {
+        double a = 0.0;
+        for (int r = 0; r < kCompactRows; ++r) a += csm[r * DP + b];
+        colsum_part[((long long)split * S + s) * DP + b] = a;
+    }
+    if (threadIdx.x == 0) {
+        int c = 0;
+        for (int r = 0; r < kCompactRows; ++r) c += cnt_sh[r];
+        colcnt_part[split * S + s] = c;
+    }
+}
+
+// returns false when the window is too wide for the thread plan (the caller then repacks from the slab)
+bool launch_compact(const Dims& d, const float* xt_full, const uint8_t* sel, const int32_t* rowidx, int nsplit,
+                    int lines_per_split, float* xt_mode, double* colsum_part, int* colcnt_part, cudaStream_t st) {
+    const int Q = d.DP / 4;
+    if (Q * kCompactRows > 512) return false;
+    dim3 grid(d.S, nsplit);
+    compact_kernel<<<grid, 512, (size_t)kCompactRows * d.DP * sizeof(double), st>>>(
+        xt_full, sel, rowidx, d.L, d.S, d.DP, lines_per_split, xt_mode, colsum_part, colcnt_part);
+    return true;
+}
+
 }  // namespace cmf
