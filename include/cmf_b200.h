@@ -141,7 +141,8 @@ int cmf_set_clustering(cmf_ctx* ctx, int kmodes, int pcadim, int reject_min, int
 
 /* -f (:161, :358): in a labelled / clustered looshrinkage run the shrinkage target of every mode fit is the
  * covariance of the whole column instead of diag(S) (looshrinkage's I_reg, :100, :131).  On the device this is a
- * Cholesky whitening ahead of the same eigen-solve.  No effect on unimodal runs (the reference tests bgmodes > 1). */
+ * whitening ahead of the same eigen-solve (Cholesky factor in shared memory up to 96 bands, the target's own spectral
+ * factor in global memory for wider windows).  No effect on unimodal runs (the reference tests bgmodes > 1). */
 int cmf_set_regfull(cmf_ctx* ctx, int enable);
 
 /* Opt-in, default off (= the reference's behaviour): keep pixels out of the BACKGROUND STATISTICS.  A pixel with
@@ -190,9 +191,9 @@ size_t cmf_output_bytes(const cmf_ctx* ctx, int what);
  * sample count the caller passes (:355-356).  nll_out[A] receives the leave-one-out negative log likelihood of every
  * alpha (inf where det(G) under/overflows, :111-113), mindex_out the argmin (-1 when every entry is inf, :121-127),
  * C_out double [D][D] the shrunk covariance (1 - alpha) S + alpha diag(S) (:130-134).  Every alpha is evaluated in
- * FP64 on the device (blocked kernels of csrc/k_wide.cu, any D up to 425+).  I_reg (the -f target, :100) must be
- * NULL / reg_rows 0 here: -f is served by the column path (cmf_set_regfull).  Independent of cmf_set_problem.
- * Synchronous. */
+ * FP64 on the device (blocked kernels of csrc/k_wide.cu, any D up to 425+).  I_reg (the -f target, :99, :131):
+ * double [reg_rows][D] or NULL / reg_rows 0; when given, the target is cov(I_reg) in the search and in C_out.
+ * Independent of cmf_set_problem.  Synchronous. */
 int cmf_looshrinkage(cmf_ctx* ctx, const double* I_zm, int32_t rows, int32_t D, const double* alphas, int32_t A,
                      int32_t n, const double* I_reg, int32_t reg_rows, double* nll_out, double* C_out,
                      int32_t* mindex_out);

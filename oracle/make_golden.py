@@ -148,6 +148,21 @@ def looshrinkage_cases():
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), I_zm=izm, alphas=alphas, n=n, nll=nll, C=C,
                             mindex=mindex)
         print("%-22s mindex %d  finite nll %d" % (name, mindex, np.isfinite(nll).sum()))
+    # with I_reg, as the column loop calls it for -f (:353-356): the samples of one mode, the whole column (less the
+    # mode's mean) as the regulariser, n = the column's pixel count
+    for name, L, seed, window in (("looshrinkage_reg_700x72", 700, 47, (351, 422)),
+                                  ("looshrinkage_reg_900x140", 900, 48, (200, 339))):
+        cube = synth.make_cube(L, 1, seed=seed)
+        x = np.float64(cube[:, window[0] - 1:window[1], 0])
+        member = x[:, -1] > np.median(x[:, -1])
+        mu = x[member].mean(axis=0)
+        izm = x[member] - mu
+        ireg = x - mu
+        nll = np.zeros(len(alphas))
+        C, mindex = ref.looshrinkage(izm, alphas, nll, L, I_reg=ireg)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), I_zm=izm, I_reg=ireg, alphas=alphas, n=L, nll=nll, C=C,
+                            mindex=mindex)
+        print("%-22s mindex %d  finite nll %d" % (name, mindex, np.isfinite(nll).sum()))
 
 
 def main():

@@ -344,11 +344,13 @@ _LOO_CTX = {}
 def looshrinkage(I_zm, alphas, nll, n, I_reg=[], device=0):
     """Drop-in for the reference's importable ``looshrinkage(I_zm, alphas, nll, n, I_reg=[])``
     (cmf/robust_mf.py:92-136): fills ``nll`` in place and returns ``(C, mindex)``.  Every alpha is evaluated in FP64
-    on the GPU (``cmf_looshrinkage``); ``I_reg`` (the ``-f`` target) is served by the column path
-    (``ColumnwiseMF.set_regfull``) and raises here."""
+    on the GPU (``cmf_looshrinkage``); with ``I_reg`` (the ``-f`` target, :99, :131) the target is ``cov(I_reg)``."""
     lib = _lib.load()
+    reg = None
     if len(I_reg) != 0:
-        raise CmfError("looshrinkage: I_reg is handled by ColumnwiseMF.set_regfull (the column path), not by this entry")
+        reg = np.ascontiguousarray(I_reg, dtype=np.float64)
+        if reg.ndim != 2 or reg.shape[1] != np.shape(I_zm)[1]:
+            raise CmfError("looshrinkage: I_reg must have the columns of I_zm")
     ctx = _LOO_CTX.get(int(device))
     if ctx is None:
         ctx = C.c_void_p()
@@ -364,7 +366,8 @@ def looshrinkage(I_zm, alphas, nll, n, I_reg=[], device=0):
     Cm = np.empty((D, D), dtype=np.float64)
     mi = C.c_int32(0)
     rc = lib.cmf_looshrinkage(ctx, C.c_void_p(x.ctypes.data), rows, D, C.c_void_p(al.ctypes.data), len(al), int(n),
-                              C.c_void_p(None), 0, C.c_void_p(nll.ctypes.data), C.c_void_p(Cm.ctypes.data),
+                              C.c_void_p(reg.ctypes.data if reg is not None else None),
+                              reg.shape[0] if reg is not None else 0, C.c_void_p(nll.ctypes.data), C.c_void_p(Cm.ctypes.data),
                               C.byref(mi))
     if rc != 0:
         raise CmfError("cmf_looshrinkage failed (%d): %s" % (rc, lib.cmf_last_error(ctx).decode()))

@@ -108,6 +108,7 @@ struct cmf_ctx {
     float *lo_part = nullptr, *hi_part = nullptr;
     int* qexp = nullptr;
     int8_t* img = nullptr;
+    WideTarget wtarget;           // -f on a wide window (cmf_set_regfull)
     double *wgram = nullptr, *wwork = nullptr, *wdinv = nullptr, *wdvec = nullptr, *wevec = nullptr, *Wtab = nullptr,
            *Zbuf = nullptr;
     double2* rot = nullptr;
@@ -253,12 +254,13 @@ void wide_fit_and_score(cmf_ctx* ctx, bool exact, const uint8_t* sel, const int*
     if (g8) launch_wide_gram8(d, ctx->img, ctx->wgram, st);
     else launch_wide_gram64(d, ctx->xt, ctx->ctr, ctx->wgram, st);
     mark(3);
-    launch_wide_eigen(d, ctx->wgram, ctx->n, ctx->mu, ctx->ctr, g8 ? ctx->qexp : nullptr, 0, ctx->wwork, ctx->wdinv,
-                      ctx->wdvec, ctx->wevec, ctx->rot, ctx->iters, ctx->sweeps, ctx->P, ctx->lam, ctx->slogT,
-                      ctx->status, st);
-    mark(4);
-    ctx->launches += 10;
     const bool loo = ctx->model == CMF_MODEL_LOOSHRINKAGE;
+    const bool full_target = modes_pass && ctx->regfull && loo;       // -f (:353-356)
+    launch_wide_eigen(d, ctx->wgram, ctx->n, ctx->mu, ctx->ctr, g8 ? ctx->qexp : nullptr, full_target ? 2 : 0,
+                      ctx->wwork, ctx->wdinv, ctx->wdvec, ctx->wevec, ctx->rot, ctx->iters, ctx->sweeps, ctx->P,
+                      ctx->lam, ctx->slogT, ctx->status, st, full_target ? &ctx->wtarget : nullptr);
+    mark(4);
+    ctx->launches += full_target ? 15 : 10;
     if (loo) {
         launch_wide_tables(d, ctx->APW, ctx->n, nloo, ctx->alphas_d, ctx->model, ctx->lam, ctx->slogT, ctx->logdet,
                            ctx->beta, ctx->rsum, ctx->Wtab, st);
@@ -375,18 +377,30 @@ int enqueue(cmf_ctx* ctx, bool timing, bool exact, const std::vector<cudaEvent_t
             launch_wide_stats(d, ctx->slab, ctx->mask, nullptr, 1, ctx->wsplit, ctx->wlps, ctx->colsum_part,
                               ctx->colcnt_part, ctx->lo_part, ctx->hi_part, ctx->mu, ctx->nuse, ctx->ctr, ctx->qexp, st);   // nuse (:302)
             ctx->launches += 3;
-            if (ctx->auto_cluster) {
-                // PCA basis of the whole column (:310-311): plain eigenvectors of its covariance
+            const bool full_target = ctx->regfull && ctx->model == CMF_MODEL_LOOSHRINKAGE;
+            if (ctx->auto_cluster || full_target) {
+                // scatter of the whole column: the PCA basis (:310) and the -f target (:353-356)
                 launch_wide_pack(d, ctx->slab, ctx->mask, nullptr, ctx->ctr, ctx->qexp, ctx->xt, g8 ? ctx->img : nullptr, st);
                 if (g8) launch_wide_gram8(d, ctx->img, ctx->wgram, st);
                 else launch_wide_gram64(d, ctx->xt, ctx->ctr, ctx->wgram, st);
+                ctx->launches += 2;
+            }
+            if (full_target) {
+                launch_wide_eigen(d, ctx->wgram, ctx->nuse, ctx->mu, ctx->ctr, g8 ? ctx->qexp : nullptr, 0, ctx->wwork,
+                                  ctx->wdinv, ctx->wdvec, ctx->wevec, ctx->rot, ctx->iters, ctx->sweeps, ctx->P, ctx->lam,
+                                  ctx->slogT, ctx->status, st);
+                launch_wide_target(d, ctx->P, ctx->lam, ctx->slogT, ctx->status, ctx->wtarget, st);
+                ctx->launches += 5;
+            }
+            if (ctx->auto_cluster) {
+                // PCA basis of the whole column (:310-311): plain eigenvectors of its covariance
                 launch_wide_eigen(d, ctx->wgram, ctx->nuse, ctx->mu, ctx->ctr, g8 ? ctx->qexp : nullptr, 1, ctx->wwork,
                                   ctx->wdinv, ctx->wdvec, ctx->wevec, ctx->rot, ctx->iters, ctx->sweeps, ctx->P, ctx->lam,
                                   ctx->slogT, ctx->status, st);
                 launch_pca_kmeans(d, ctx->xt, ctx->mask, ctx->mu, ctx->nuse, ctx->P, ctx->lam, ctx->pcadim, ctx->kmodes,
                                   ctx->km_max_iter, ctx->pick, ctx->vtop, ctx->ypca, ctx->qpca, ctx->lab8, ctx->labels_d,
                                   ctx->km_iters, st);
-                ctx->launches += 9;
+                ctx->launches += 7;
             }
             launch_modes(d, ctx->labels_d, ctx->mask, ctx->reject_min, ctx->entries, ctx->rejmask, ctx->nentries, ctx->flagmask, st);
             launch_fill_f64(ctx->mf, (long long)LSw, ctx->nodata, st);
@@ -604,6 +618,7 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     ctx->alpha_img = nullptr; ctx->rowidx = nullptr; ctx->xt_mode = nullptr;
     ctx->auto_cluster = false; ctx->regfull = false; ctx->y_pd = 0;
     ctx->have_excl = false; ctx->excl_sel = nullptr;
+    ctx->wtarget = WideTarget{};
     ctx->gram_full = nullptr; ctx->vtop = nullptr; ctx->ypca = nullptr; ctx->qpca = nullptr; ctx->pick = nullptr;
     ctx->km_iters = nullptr; ctx->lab8 = nullptr;
     Dims& d = ctx->d;
@@ -878,9 +893,15 @@ int cmf_set_regfull(cmf_ctx* ctx, int enable) {
     if (!ctx) return CMF_E_ARG;
     if (!ctx->have_problem) return fail(ctx, CMF_E_STATE, "cmf_set_regfull before cmf_set_problem");
     CK(cudaSetDevice(ctx->device));
-    if (enable && ctx->wide)
-        return fail(ctx, CMF_E_ARG, "-f (full-column regulariser) is not supported for active windows wider than 96 bands");
-    if (enable) {
+    if (enable && ctx->wide) {
+        // the target in spectral form, its transpose and one scratch matrix per column (k_wide.cu, "-f on a wide window")
+        const size_t SDD = (size_t)ctx->d.S * ctx->d.DP * ctx->d.DP;
+        WideTarget& t = ctx->wtarget;
+        if (!t.W && (dalloc(ctx, &t.W, SDD) != cudaSuccess || dalloc(ctx, &t.Wt, SDD) != cudaSuccess ||
+                     dalloc(ctx, &t.tmp, SDD) != cudaSuccess || dalloc(ctx, &t.slogT, (size_t)ctx->d.S) != cudaSuccess ||
+                     dalloc(ctx, &t.status, (size_t)ctx->d.S) != cudaSuccess))
+            return fail(ctx, CMF_E_NOMEM, "full-column target buffers");
+    } else if (enable) {
         int rc = ensure_full_gram(ctx);
         if (rc) return rc;
     }
@@ -1201,9 +1222,8 @@ int cmf_looshrinkage(cmf_ctx* ctx, const double* I_zm, int32_t rows, int32_t D, 
                      int32_t* mindex_out) {
     if (!ctx || !I_zm || !alphas || !nll_out || !C_out || !mindex_out) return CMF_E_ARG;
     if (rows < 1 || D < 1 || D > 1024 || A < 1 || A > 4096) return fail(ctx, CMF_E_ARG, "cmf_looshrinkage: bad shape");
-    if (I_reg != nullptr && reg_rows > 0)
-        return fail(ctx, CMF_E_ARG, "cmf_looshrinkage: I_reg (the -f target) is served by the column path "
-                                    "(cmf_set_regfull), not by the one-column entry");
+    const bool reg = I_reg != nullptr && reg_rows > 0;
+    if (reg && reg_rows < 2) return fail(ctx, CMF_E_ARG, "cmf_looshrinkage: I_reg needs at least two rows");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     Dims d{};
@@ -1215,6 +1235,7 @@ int cmf_looshrinkage(cmf_ctx* ctx, const double* I_zm, int32_t rows, int32_t D, 
     // one scratch block; doubles first
     size_t nd = (size_t)rows * DP /*x*/ + (size_t)rows * DP /*Z*/ + 3 * DD /*gram, work, P*/ + 8 * (size_t)DP + 5 * (size_t)d.AP +
                 (size_t)DP * APW /*W*/ + (size_t)A /*alphas*/ + (size_t)A /*nll*/ + (size_t)D * D /*C*/ + 3 * (size_t)DP /*w, wT*/ + 8;
+    if (reg) nd += (size_t)reg_rows * DP /*I_reg*/ + 4 * DD /*its gram, W, W^T, scratch*/ + (size_t)DP + 2;
     const size_t rot_cap = wide_rot_cap(d);
     const int iter_cap = wide_iter_cap(d);
     const size_t bytes = nd * sizeof(double) + rot_cap * sizeof(double2) + (size_t)iter_cap * sizeof(int2) + 16 * sizeof(int);
@@ -1230,12 +1251,23 @@ int cmf_looshrinkage(cmf_ctx* ctx, const double* I_zm, int32_t rows, int32_t D, 
     double *W = take((size_t)DP * APW), *al_d = take(A), *nll_d = take(A), *C_d = take((size_t)D * D), *w = take(DP),
            *wT = take(2 * (size_t)DP), *slogT = take(1), *c0 = take(3);
     (void)spare; (void)zero;
+    double *xr = nullptr, *gramr = nullptr, *meanr = nullptr;
+    WideTarget tgt;
+    if (reg) {
+        xr = take((size_t)reg_rows * DP); gramr = take(DD); tgt.W = take(DD); tgt.Wt = take(DD); tgt.tmp = take(DD);
+        meanr = take(DP); tgt.slogT = take(2);
+    }
     if (reinterpret_cast<uintptr_t>(p) & 15) ++p;                       // double2 alignment
     double2* rot = reinterpret_cast<double2*>(p);
     int2* iters = reinterpret_cast<int2*>(rot + rot_cap);
     int* ints = reinterpret_cast<int*>(iters + iter_cap);
     int *n_rows = ints, *n_loo = ints + 1, *status = ints + 2, *niter = ints + 3, *mindex = ints + 4;
-    const int hv[2] = {rows, n};
+    int* n_reg = ints + 5;
+    tgt.status = ints + 6;
+    const int hv[6] = {rows, n, 0, 0, 0, reg_rows};
+    if (reg && e == cudaSuccess)
+        e = cudaMemcpy2DAsync(xr, (size_t)DP * sizeof(double), I_reg, (size_t)D * sizeof(double), (size_t)D * sizeof(double),
+                              (size_t)reg_rows, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpy2DAsync(x, (size_t)DP * sizeof(double), I_zm, (size_t)D * sizeof(double),
                                                 (size_t)D * sizeof(double), (size_t)rows, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(al_d, alphas, (size_t)A * sizeof(double), cudaMemcpyHostToDevice, st);
@@ -1243,15 +1275,23 @@ int cmf_looshrinkage(cmf_ctx* ctx, const double* I_zm, int32_t rows, int32_t D, 
     if (e == cudaSuccess) {
         launch_wide_mean64(x, rows, D, DP, mean, st);                       // numpy.cov re-centres (:68)
         launch_wide_gram64_f64(rows, DP, 1, x, mean, gram, st);             // sum (x - mean)(x - mean)^T
-        // S = G / (m - 1), T = diag(S); the x100 stability scaling enters log det only (:94-99)
-        launch_wide_eigen(d, gram, n_rows, mean, mean, nullptr, 0, work, dinv, dvec, evec, rot, iters, niter, P, lam,
-                          slogT, status, st);
+        if (reg) {
+            // T = cov(I_reg) (:99): its spectral factor first, then S whitened with it
+            launch_wide_mean64(xr, reg_rows, D, DP, meanr, st);
+            launch_wide_gram64_f64(reg_rows, DP, 1, xr, meanr, gramr, st);
+            launch_wide_eigen(d, gramr, n_reg, meanr, meanr, nullptr, 0, work, dinv, dvec, evec, rot, iters, niter, P, lam,
+                              slogT, status, st);
+            launch_wide_target(d, P, lam, slogT, status, tgt, st);
+        }
+        // S = G / (m - 1), T = diag(S) unless given; the x100 stability scaling enters log det only (:94-99)
+        launch_wide_eigen(d, gram, n_rows, mean, mean, nullptr, reg ? 2 : 0, work, dinv, dvec, evec, rot, iters, niter, P,
+                          lam, slogT, status, st, reg ? &tgt : nullptr);
         launch_wide_tables(d, APW, n_rows, n_loo, al_d, 0, lam, slogT, logdet, beta, rsum, W, st);
         // r_k = x_k^T G^-1 x_k uses the samples as given, not re-centred (:114)
         launch_wide_loo_f64(rows, D, DP, d.AP, APW, x, mu0, P, W, beta, n_rows, Z, fpart, st);
         launch_finalize(d, fpart, 1, logdet, n_rows, al_d, P, lam, mu0, abscf, 0, 1, 1.0, nll_d, mindex, w, wT, c0, status,
                         nullptr, nullptr, n_loo, st);
-        launch_wide_cmat(gram, rows, D, DP, mindex, al_d, C_d, st);
+        launch_wide_cmat(gram, rows, D, DP, mindex, al_d, C_d, st, gramr, reg_rows);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(nll_out, nll_d, (size_t)A * sizeof(double), cudaMemcpyDeviceToHost, st);

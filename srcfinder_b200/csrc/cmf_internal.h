@@ -159,10 +159,18 @@ void launch_wide_gram8(const Dims& d, const int8_t* img, double* gram, cudaStrea
 size_t wide_rot_cap(const Dims& d);
 int wide_iter_cap(const Dims& d);
 bool wide_eigen_fits(const Dims& d);
+// the -f target of a wide window: W = T^-1/2 in spectral form (and its transpose), log det of the scaled target,
+// status of the target, one DP x DP scratch matrix per column
+struct WideTarget {
+    double *W = nullptr, *Wt = nullptr, *tmp = nullptr, *slogT = nullptr;
+    int* status = nullptr;
+};
+void launch_wide_target(const Dims& d, const double* P, const double* lam, const double* slogT, const int* status,
+                        const WideTarget& t, cudaStream_t st);
 void launch_wide_eigen(const Dims& d, const double* gram, const int* n, const double* mu, const double* ctr,
                        const int* qexp, int mode, double* work, double* dinv, double* dvec, double* evec,
                        double2* rot, int2* iters, int* niter, double* P, double* lam, double* slogT, int* status,
-                       cudaStream_t st);
+                       cudaStream_t st, const WideTarget* tgt = nullptr);
 void launch_wide_tables(const Dims& d, int APW, const int* n, const int* nloo, const double* alphas, int model,
                         const double* lam, const double* slogT, double* logdet, double* beta, double* rsum, double* W,
                         cudaStream_t st);
@@ -175,7 +183,7 @@ void launch_wide_loo_f64(int L, int D, int DP, int AP, int APW, const double* x,
 
 void launch_wide_mean64(const double* x, int rows, int D, int DP, double* mean, cudaStream_t st);
 void launch_wide_cmat(const double* gram, int m, int D, int DP, const int* mindex, const double* alphas, double* C,
-                      cudaStream_t st);
+                      cudaStream_t st, const double* gram_reg = nullptr, int m_reg = 0);
 
 size_t gram_part_elems(const Dims& d, int nchunk);
 int repack_nsplit(const Dims& d);

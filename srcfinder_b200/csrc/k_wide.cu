@@ -1214,6 +1214,87 @@ __global__ void __launch_bounds__(kRowsThreads, 2)
     if (tid < 64 && a0 + tid < AP) out[a0 + tid] = ((xch[tid] + xch[64 + tid]) + xch[128 + tid]) + xch[192 + tid];
 }
 
+// ---------------------------------------------------------------------------------------- -f on a wide window
+// The full-column covariance as the shrinkage target (cmf/robust_mf.py:99, :353-356): T = cov(I_reg) is whitened
+// with its own spectral factor W = T0^-1/2 U M^-1/2 (T0 = diag T, T0^-1/2 T T0^-1/2 = U M U^T from one solve of the
+// blocked eigen-solver per run, W^T T W = I), the mode's covariance becomes R = W^T S W, and with R = V Lambda V^T
+// the search sees P = W V and log det T = sum log T0 + sum log M exactly as with the diagonal target.
+// C = A B for the DP x DP row-major matrices of every column (FP64 DMMA, the 128 x 64 blocks of W5)
+__global__ void __launch_bounds__(kRowsThreads, 2)
+    wide_dgemm_kernel(const double* __restrict__ A_g, const double* __restrict__ B_g, int D, int DP,
+                      double* __restrict__ C_g) {
+    extern __shared__ double rows_sm[];
+    double* As = rows_sm;                    // [128][kRP]
+    double* Bs = As + 128 * kRP;             // [16][kWP]
+    const int s = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j0 = blockIdx.x * 64, r0 = blockIdx.y * 128;
+    const long long base = (long long)s * DP * DP;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    gemm_rows_block<double, false>(A_g + base + (long long)r0 * DP, DP, min(128, DP - r0), D, nullptr, B_g + base + j0, DP,
+                                   min(64, DP - j0), As, Bs, acc, tid);
+    const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) {
+            const int r = r0 + wm * 32 + ti * 8 + g, j = j0 + wn * 32 + tj * 8 + 2 * q;
+            if (r < DP && j < DP)
+                *reinterpret_cast<double2*>(C_g + base + (long long)r * DP + j) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
+        }
+}
+
+// W = P_f diag(M^-1/2) and its transpose, log det of the scaled target, status of the target (singular: some M <= 0)
+__global__ void __launch_bounds__(256)
+    wide_target_kernel(const double* __restrict__ P_g, const double* __restrict__ lam_g,
+                       const double* __restrict__ slogT_g, const int* __restrict__ status_g, int D, int DP,
+                       double* __restrict__ W_g, double* __restrict__ Wt_g, double* __restrict__ slogT_full,
+                       int* __restrict__ fstatus) {
+    extern __shared__ double isq[];          // [DP]
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const double* lam = lam_g + (long long)s * DP;
+    for (int j = tid; j < DP; j += blockDim.x) isq[j] = (j < D && lam[j] > 0.0) ? 1.0 / sqrt(lam[j]) : 0.0;
+    __syncthreads();
+    if (tid == 0) {
+        double a = slogT_g[s];
+        int bad = status_g[s] & (kStatusNoConverge | kStatusEmpty | kStatusDegenerate);
+        for (int j = 0; j < D; ++j) {
+            if (lam[j] > 0.0) a += log(lam[j]);
+            else bad |= kStatusSingular;
+        }
+        slogT_full[s] = a;
+        fstatus[s] = bad;
+    }
+    const long long base = (long long)s * DP * DP;
+    for (long long idx = tid; idx < (long long)DP * DP; idx += blockDim.x) {
+        const int b = (int)(idx / DP), j = (int)(idx % DP);
+        const double v = P_g[base + idx] * isq[j];
+        W_g[base + idx] = v;
+        Wt_g[base + (long long)j * DP + b] = v;
+    }
+}
+
+// the whitened covariance is symmetric up to rounding: the lower triangle is the value both halves use
+__global__ void __launch_bounds__(256) wide_mirror_kernel(double* __restrict__ work, int DP) {
+    double* A = work + (long long)blockIdx.x * DP * DP;
+    for (long long idx = threadIdx.x; idx < (long long)DP * DP; idx += blockDim.x) {
+        const int r = (int)(idx / DP), c = (int)(idx % DP);
+        if (c > r) A[idx] = A[(long long)c * DP + r];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    wide_target_finish_kernel(const double* __restrict__ slogT_full, const int* __restrict__ fstatus, int S,
+                              double* __restrict__ slogT, int* __restrict__ status) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    slogT[s] = slogT_full[s];
+    if ((status[s] & (kStatusEmpty | kStatusDegenerate)) == 0) status[s] |= fstatus[s];
+}
+
 // ---------------------------------------------------------------------------------------- launchers
 void launch_wide_stats(const Dims& d, const float* slab, uint8_t* mask, const uint8_t* sel, int write_mask,
                        int nsplit, int lps, double* colsum_part, int* colcnt_part, float* lo_part, float* hi_part,
@@ -1264,15 +1345,33 @@ static int wide_rot_rows(int DP) {
 
 bool wide_eigen_fits(const Dims& d) { return wide_rot_rows(d.DP) >= 8 && (size_t)(4 + kWtThreads / 32) * d.DP * 8 <= 200u * 1024u; }
 
-// mode: 0 = diag(S) target (correlation matrix), 1 = no scaling (plain eigenvectors of the covariance)
+static void launch_wide_dgemm(const Dims& d, const double* A, const double* B, double* C, cudaStream_t st) {
+    const size_t sm = (size_t)(128 * kRP + 16 * kWP) * sizeof(double);
+    dim3 grid((d.DP + 63) / 64, (d.DP + 127) / 128, d.S);
+    wide_dgemm_kernel<<<grid, kRowsThreads, sm, st>>>(A, B, d.D, d.DP, C);
+}
+
+void launch_wide_target(const Dims& d, const double* P, const double* lam, const double* slogT, const int* status,
+                        const WideTarget& t, cudaStream_t st) {
+    wide_target_kernel<<<d.S, 256, (size_t)d.DP * sizeof(double), st>>>(P, lam, slogT, status, d.D, d.DP, t.W, t.Wt,
+                                                                        t.slogT, t.status);
+}
+
+// mode: 0 = diag(S) target (correlation matrix), 1 = no scaling (plain eigenvectors of the covariance),
+//       2 = the full-column target held in `tgt` (-f)
 void launch_wide_eigen(const Dims& d, const double* gram, const int* n, const double* mu, const double* ctr,
                        const int* qexp, int mode, double* work, double* dinv, double* dvec, double* evec,
                        double2* rot, int2* iters, int* niter, double* P, double* lam, double* slogT, int* status,
-                       cudaStream_t st) {
+                       cudaStream_t st, const WideTarget* tgt) {
     const size_t rot_cap = wide_rot_cap(d);
     const int iter_cap = wide_iter_cap(d);
-    wide_cov_kernel<<<d.S, 256, (size_t)3 * d.DP * sizeof(double), st>>>(gram, n, d.D, d.DP, mu, ctr, qexp, mode, work,
-                                                                         dinv, slogT, status);
+    wide_cov_kernel<<<d.S, 256, (size_t)3 * d.DP * sizeof(double), st>>>(gram, n, d.D, d.DP, mu, ctr, qexp,
+                                                                         mode == 2 ? 1 : mode, work, dinv, slogT, status);
+    if (mode == 2) {
+        launch_wide_dgemm(d, work, tgt->W, tgt->tmp, st);            // S W
+        launch_wide_dgemm(d, tgt->Wt, tgt->tmp, work, st);           // W^T (S W)
+        wide_mirror_kernel<<<d.S, 256, 0, st>>>(work, d.DP);
+    }
     int nthr = 0;                                                       // 0: the blocked kernel
     if (const char* e = cmf_hook("CMF_WIDE_TRED")) nthr = atoi(e);      // tuning hook (tools build): 1024 / 512 = unblocked
     if (nthr == 0) {
@@ -1296,6 +1395,11 @@ void launch_wide_eigen(const Dims& d, const double* gram, const int* n, const do
     dim3 grid((d.DP + rows - 1) / rows, d.S);
     wide_rot_kernel<<<grid, kWrThreads, smem, st>>>(work, n, d.D, d.DP, rows, rot, (long long)rot_cap, iters, iter_cap,
                                                     niter, dinv, P);
+    if (mode == 2) {
+        launch_wide_dgemm(d, tgt->W, P, tgt->tmp, st);               // P = W V
+        cudaMemcpyAsync(P, tgt->tmp, (size_t)d.S * d.DP * d.DP * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        wide_target_finish_kernel<<<(d.S + 255) / 256, 256, 0, st>>>(tgt->slogT, tgt->status, d.S, slogT, status);
+    }
 }
 
 void launch_wide_tables(const Dims& d, int APW, const int* n, const int* nloo, const double* alphas, int model,
@@ -1347,7 +1451,8 @@ __global__ void __launch_bounds__(128) wide_mean64_kernel(const double* __restri
 // C = (1 - alpha) S + alpha T, S = cov = G / (m - 1), T = diag(diag(S))  (:130-134); alpha = 0 when mindex = -1
 __global__ void __launch_bounds__(256) wide_cmat_kernel(const double* __restrict__ gram, int m, int D, int DP,
                                                         const int* __restrict__ mindex, const double* __restrict__ alphas,
-                                                        double* __restrict__ C) {
+                                                        double* __restrict__ C, const double* __restrict__ gram_reg,
+                                                        int m_reg) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= D * D) return;
     const int r = idx / D, c = idx % D;
@@ -1355,7 +1460,9 @@ __global__ void __launch_bounds__(256) wide_cmat_kernel(const double* __restrict
     const double al = mi >= 0 ? alphas[mi] : 0.0;
     const double inv = 1.0 / (double)(m - 1);
     const double sv = gram[(long long)max(r, c) * DP + min(r, c)] * inv;
-    const double tv = (r == c) ? sv : 0.0;
+    // the target: diag(S), or cov(I_reg) when the caller gave one (:131-133)
+    const double tv = gram_reg ? gram_reg[(long long)max(r, c) * DP + min(r, c)] / (double)(m_reg - 1)
+                               : ((r == c) ? sv : 0.0);
     C[idx] = (1.0 - al) * sv + al * tv;
 }
 
@@ -1363,8 +1470,8 @@ void launch_wide_mean64(const double* x, int rows, int D, int DP, double* mean, 
     wide_mean64_kernel<<<(DP + 127) / 128, 128, 0, st>>>(x, rows, D, DP, mean);
 }
 void launch_wide_cmat(const double* gram, int m, int D, int DP, const int* mindex, const double* alphas, double* C,
-                      cudaStream_t st) {
-    wide_cmat_kernel<<<(D * D + 255) / 256, 256, 0, st>>>(gram, m, D, DP, mindex, alphas, C);
+                      cudaStream_t st, const double* gram_reg, int m_reg) {
+    wide_cmat_kernel<<<(D * D + 255) / 256, 256, 0, st>>>(gram, m, D, DP, mindex, alphas, C, gram_reg, m_reg);
 }
 
 }  // namespace cmf

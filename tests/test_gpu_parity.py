@@ -417,8 +417,7 @@ def test_error_paths():
     with pytest.raises(CmfError):
         ColumnwiseMF(16, 425, 4, [351, 430], np.zeros(80))            # window outside the cube
     wide = ColumnwiseMF(16, 425, 4, [5, 420], np.zeros(416))          # -R window: the wide-window kernel set
-    with pytest.raises(CmfError):
-        wide.set_regfull(True)                                        # -f: narrow windows only
+    wide.set_regfull(True)                                            # -f is served there too
     wide.close()
     eng = ColumnwiseMF(16, 425, 4, [351, 422], ab)
     with pytest.raises(CmfError):

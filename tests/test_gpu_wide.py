@@ -78,8 +78,7 @@ def test_wide_window_empirical_and_degenerate():
 
 def test_wide_window_background_modes():
     """-k / -r on the 416-band window (the reference allows it with -R): given labels against the oracle, and the
-    partition found on the device reproduces the labelled run; -f on a wide window fails loudly."""
-    from srcfinder_b200 import CmfError
+    partition found on the device reproduces the labelled run."""
     active = [5, 420]
     L, S = 1500, 2
     cube = synth.make_cube(L, S, seed=46, bad_pixels=True)
@@ -106,11 +105,34 @@ def test_wide_window_background_modes():
         eng.set_clustering(2, pcadim=6, reject_min=rmin)
         eng.run()
         auto = eng.results(); found = eng.labels()
-        with pytest.raises(CmfError):
-            eng.set_regfull(True)
     again = cmf_cube(cube, ab, active, reflectance=True, labels=found, reject_min=rmin)
     assert np.array_equal(auto["mf"], again["mf"], equal_nan=True)
     assert set(np.unique(found[auto["mask"]])) == {0, 1}
+
+
+@pytest.mark.parametrize("active,L", [([200, 330], 900), ([5, 420], 1300)])
+def test_wide_window_full_column_target(active, L):
+    """-f on a wide window (:353-356): every mode fit shrinks towards the covariance of the whole column.  Given
+    labels against the oracle; the clustered run equals the labelled run with the labels it found."""
+    S = 2
+    cube = synth.make_cube(L, S, seed=49, bad_pixels=True)
+    ab = _abscf(active)
+    mid = (active[0] + active[1]) // 2
+    bright = np.nan_to_num(cube[:, mid, :], nan=0.0, posinf=0.0)
+    labels = (bright > np.median(bright, axis=0, keepdims=True)).astype(np.int32)
+    ref = orc.cmf_cube(cube, ab, active, reflectance=True, labels=labels, regfull=True)
+    got = cmf_cube(cube, ab, active, reflectance=True, labels=labels, regfull=True)
+    plain = cmf_cube(cube, ab, active, reflectance=True, labels=labels)
+    assert np.array_equal(got["mask"], ref["mask"])
+    assert np.array_equal(got["alpha_index"], ref["alpha_index"])
+    assert not np.array_equal(got["mf"], plain["mf"])              # the target does change the fit
+    for c in range(S):
+        ok = ref["mf"][:, c] != -9999.0
+        err = np.max(np.abs(got["mf"][ok, c] - ref["mf"][ok, c])) / np.std(ref["mf"][ok, c])
+        assert err <= WIDE_SIGMA, "column %d: %.3g sigma" % (c, err)
+    auto = cmf_cube(cube, ab, active, reflectance=True, kmodes=2, regfull=True)
+    again = cmf_cube(cube, ab, active, reflectance=True, labels=auto["labels"], regfull=True)
+    assert np.array_equal(auto["mf"], again["mf"], equal_nan=True)
 
 
 def test_wide_window_determinism_and_run_host():
@@ -141,12 +163,13 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "looshrinkage_*.npz"))))
 def test_looshrinkage_drop_in(path):
-    """srcfinder_b200.looshrinkage(I_zm, alphas, nll, n) against the reference function's own output (fixture made
-    by oracle/make_golden.py looshrinkage): same (C, mindex), nll filled in place."""
+    """srcfinder_b200.looshrinkage(I_zm, alphas, nll, n[, I_reg]) against the reference function's own output
+    (fixtures made by oracle/make_golden.py looshrinkage): same (C, mindex), nll filled in place."""
     from srcfinder_b200 import looshrinkage
     z = np.load(path)
     nll = np.zeros(len(z["alphas"]))
-    C, mindex = looshrinkage(z["I_zm"], z["alphas"], nll, int(z["n"]))
+    reg = z["I_reg"] if "I_reg" in z.files else []                 # the -f target (:99, :131)
+    C, mindex = looshrinkage(z["I_zm"], z["alphas"], nll, int(z["n"]), I_reg=reg)
     assert mindex == int(z["mindex"])
     assert np.array_equal(np.isfinite(nll), np.isfinite(z["nll"]))
     fin = np.isfinite(z["nll"])
@@ -154,4 +177,4 @@ def test_looshrinkage_drop_in(path):
     assert np.max(np.abs(C - z["C"])) <= 1e-12 * np.max(np.abs(z["C"]))
     assert np.array_equal(C, C.T)
     with pytest.raises(Exception):
-        looshrinkage(z["I_zm"], z["alphas"], nll, int(z["n"]), I_reg=z["I_zm"])
+        looshrinkage(z["I_zm"], z["alphas"], nll, int(z["n"]), I_reg=z["I_zm"][:, :-1])
