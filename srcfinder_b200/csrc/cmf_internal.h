@@ -105,6 +105,9 @@ void launch_screen5(const Dims& d, const float* xt, const double* mu, const int*
                     int nchunk, double* fscreen, cudaStream_t st);
 #ifdef CMF_TUNING_HOOKS
 double screen5_selftest(int N, int K, int row_off, int swap_lbo_sbo);
+int screen5_timeline(long long* out);
+double screen5_mma_rate(int N, int reps);
+double fma_issue_rate(int packed, int warps);
 #endif
 void launch_select(const Dims& d, const double* fscreen, int nchunk, const double* logdet, const double* rsum,
                    const int* n, const int* nloo, double tol, double* nll, int* sel_index,

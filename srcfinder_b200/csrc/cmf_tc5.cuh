@@ -56,6 +56,20 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// the same with the descriptor given as its two 32-bit words: issue loops that step through the k-steps of an operand
+// add to the low word only (the start address field, 16-byte units), which keeps the arithmetic on 32-bit uniform
+// registers instead of 64-bit values the compiler hoists and spills
+__device__ __forceinline__ void mma_ts_tf32_w(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 bd;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 bd, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major, no swizzle: element (row, 16-byte
 // K chunk c) lives at start + (row % 8) * 16 + (row / 8) * SBO + c * LBO
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -90,6 +104,42 @@ __device__ __forceinline__ void tmem_st8(uint32_t addr, const uint32_t (&v)[8]) 
 __device__ __forceinline__ uint32_t tf32_round(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ uint32_t tf32_trunc(float x) { return __float_as_uint(x) & 0xffffe000u; }
 
+
+// Packed FP32 pairs (Blackwell FFMA2 / FMUL2 / FADD2): a three-register FFMA issues every second cycle per scheduler,
+// the packed forms do two lanes' worth of arithmetic in the same slot.  Pairs live in 64-bit registers {lo, hi}.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_pack_u(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 
 // One lane of a CONVERGED warp (elect.sync).  The MMA issuer warps run their loops with all 32 lanes and issue under
 // this predicate: with uniform control flow the descriptors stay in uniform registers, whereas a loop entered by

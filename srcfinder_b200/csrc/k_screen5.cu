@@ -14,9 +14,9 @@
 //     canonical K-major no-swizzle core-matrix layout, built once per column by screen5_tables_kernel,
 //   * R is split into two alpha halves with their own full/empty barriers so that the FP32 epilogue
 //     of one half overlaps the tensor work of the other half and of the next tile,
-//   * warp roles: warp 0 bulk-copy producer, warp 1 MMA issuer (one thread), warps 4-7 convert and
-//     square (thread = pixel), warps 8-15 epilogue (thread = pixel, 112 alphas each, accumulators in
-//     registers; setmaxnreg moves registers from the control warps to the epilogue warps).
+//   * warp roles: warps 0-7 epilogue (thread = pixel, 112 alphas each, accumulators in registers), warps 8-11
+//     convert and square (thread = pixel), warp 12 bulk-copy producer, warp 13 MMA issuer (one elected lane);
+//     setmaxnreg moves registers from the control warps to the epilogue warps.
 //
 // TMEM columns (DP = padded bands, N1 = DP rounded to 16, NA = padded alphas):
 //     [0, 2DP)            xh | xl          A of GEMM1
@@ -28,6 +28,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "cmf_common.cuh"
@@ -39,15 +40,40 @@ namespace cmf {
 namespace {
 
 constexpr int kT5Threads = 512;
+// Warp roles.  The schedulers favour the higher warp of the warps that are ready (measured: with the issuer in warp 1 it
+// waited several hundred cycles behind the epilogue warps of its scheduler before every GEMM), so the latency-critical
+// roles sit at the top: warps 0-7 epilogue (two alpha halves x four lane quarters), 8-11 convert / square, 12 bulk-copy
+// producer, 13 MMA issuer.
+constexpr int kT5WarpProducer = 12, kT5WarpIssuer = 13;
 // register budgets after setmaxnreg (4 control warps, 4 convert/square warps, 8 epilogue warps; the sum
 // 4 a + 4 b + 8 c may not exceed 2048): the epilogue keeps 112 per-alpha accumulators per thread
 #ifndef CMF_S5_REGS_CTL
-#define CMF_S5_REGS_CTL 40
-#define CMF_S5_REGS_CVT 104
-#define CMF_S5_REGS_EPI 184
+#define CMF_S5_REGS_CTL 32
+#define CMF_S5_REGS_CVT 64
+#define CMF_S5_REGS_EPI 208
+#endif
+#ifndef CMF_S5_ZP
+#define CMF_S5_ZP 3                 // hand-over parts of the squares (1..3)
 #endif
 #define CMF_STR2(x) #x
 #define CMF_STR(x) CMF_STR2(x)
+#ifdef CMF_TUNING_HOOKS
+// per-phase timeline of one CTA (tools build): SM clock at the hand-offs of tiles 6..9 (tools/s5_timeline.py)
+__device__ long long g_s5_tl[4][32];
+#define S5_TL(cond, tile, ev)                                                                             \
+    do {                                                                                                  \
+        if ((cond) && lane == 0 && s == 5 && chunk == 1 && blockIdx.z == 0 && (tile) >= 6 && (tile) < 10) \
+            g_s5_tl[(tile) - 6][ev] = clock64();                                                          \
+    } while (0)
+#define S5_CTA(cond, ev)                                                         \
+    do {                                                                         \
+        if ((cond) && blockIdx.x == 5 && blockIdx.y == 1 && blockIdx.z == 0)     \
+            g_s5_tl[3][ev] = clock64();                                          \
+    } while (0)
+#else
+#define S5_TL(cond, tile, ev) do {} while (0)
+#define S5_CTA(cond, ev) do {} while (0)
+#endif
 constexpr int kT5Stages = 3;       // 64-row half tiles in flight
 constexpr int kT5HalfRows = 64;
 
@@ -58,8 +84,9 @@ constexpr int kT5HalfRows = 64;
 // (|u| <= 2^-3) are formed on the fly; anything larger is the rare out-of-line slow path.
 // Everything that is not the 5-term fast path, out of line so that the hot loop stays small: 10 terms while
 // |u| <= 2^-3 (u^11 < 2^-33), log1p and a division up to u = 1/4, poison beyond.
+// dp: d2 = 1/beta - 1/2 of these 16 alphas
 __device__ __noinline__ void g_cold16(const float* __restrict__ rp, const float* __restrict__ beta,
-                                      const float4* __restrict__ dp, float* __restrict__ g) {
+                                      const float* __restrict__ dp, float* __restrict__ g) {
     float r[16], u[16], umax = 0.f;
 #pragma unroll
     for (int e = 0; e < 16; ++e) { r[e] = rp[e]; u[e] = beta[e] * r[e]; umax = fmaxf(umax, fabsf(u[e])); }
@@ -67,7 +94,7 @@ __device__ __noinline__ void g_cold16(const float* __restrict__ rp, const float*
     if (__ballot_sync(0xffffffffu, umax > 0x1p-3f) == 0u) {
         float pz[16], binv[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) { binv[e] = dp[e].x + 0.5f; pz[e] = binv[e] - 0.1f; }
+        for (int e = 0; e < 16; ++e) { binv[e] = dp[e] + 0.5f; pz[e] = binv[e] - 0.1f; }
 #pragma unroll 1
         for (int kk = 9; kk >= 2; --kk) {
             const float ik = 1.0f / (float)kk;
@@ -103,14 +130,16 @@ __host__ __device__ inline T5Plan t5_plan(int NT, int NT16) {
     p.ring_off = p.tab_bytes;
     p.mu_off = p.ring_off + (uint32_t)kT5Stages * kT5HalfRows * p.DP * 4;
     p.beta_off = p.mu_off + (uint32_t)p.DP * 8;
-    p.dtab_off = (p.beta_off + (uint32_t)p.NA * 4 + 15u) & ~15u;
-    p.bar_off = p.dtab_off + (uint32_t)p.NA * 16;
+    p.dtab_off = (p.beta_off + (uint32_t)p.NA * 4 + 15u) & ~15u;       // d2 = 1/beta - 1/2 per alpha
+    p.bar_off = p.dtab_off + (uint32_t)p.NA * 4;
     p.total = p.bar_off + 24 * 8;
     return p;
 }
 
-enum { B_TAB = 0, B_XFULL = 1, B_XEMPTY = 4, B_XREADY = 7, B_G1 = 8, B_ZREADY = 9, B_RFULL = 10, B_REMPTY = 12,
-       B_COUNT = 14 };
+// B_ZREADY: the squares are handed over in up to three parts (k-steps of GEMM2), so that GEMM2 starts on the first
+// third of zh|zl while the rest is still being squared
+enum { B_TAB = 0, B_XFULL = 1, B_XEMPTY = 4, B_XREADY = 7, B_G1 = 8, B_RFULL = 10, B_REMPTY = 12, B_ZREADY = 14,
+       B_COUNT = 17 };
 
 // ------------------------------------------------------------------ B operand tables
 // tab[s] = Ph | Pl | Wh | Wl, each [K chunk c][row][4]: P rows are eigen-directions j (K = band b),
@@ -168,6 +197,7 @@ __global__ void __launch_bounds__(kT5Threads, 1)
     // alphas over two CTAs so that tables and accumulators fit shared memory and TMEM), AP16 = padded alphas in all
     constexpr int DP = 8 * NT, N1 = (DP + 15) / 16 * 16;
     constexpr uint32_t C_XH = 0, C_XL = DP, C_Y = 2 * DP, C_ZL = 2 * DP + N1, C_R = 3 * DP + N1;
+    constexpr int ZP = (NT >= 6) ? CMF_S5_ZP : 1, ZC = (NT + ZP - 1) / ZP;    // hand-over parts of the squares, k-steps per part
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const T5Plan p = t5_plan(NT, NT16);
     const int NA = p.NA;
@@ -180,6 +210,7 @@ __global__ void __launch_bounds__(kT5Threads, 1)
     const int na_out = min(NA, AP16 - a_off);                    // alphas of the part that exist
     double* out = fscreen + ((long long)s * gridDim.y + chunk) * AP16 + a_off;
     if (n_g[s] < 2) return;                                      // nothing to search (K4 handles n < 2)
+    S5_CTA(tid == 0, 24);
     const int c_begin = chunk * lines_per_chunk;
     const int c_end = min(ncomp ? min(L, ncomp[s]) : L, c_begin + lines_per_chunk);   // compacted mode pass: ncomp[s] rows
     if (c_end <= c_begin) {                                      // empty tail chunk
@@ -191,9 +222,10 @@ __global__ void __launch_bounds__(kT5Threads, 1)
     const int nhalf = (nrows + kT5HalfRows - 1) / kT5HalfRows;
 
     float* ring = reinterpret_cast<float*>(smem_raw + p.ring_off);
-    float2* mu2 = reinterpret_cast<float2*>(smem_raw + p.mu_off);
+    float* muh = reinterpret_cast<float*>(smem_raw + p.mu_off);        // column mean, FP32 head and tail, [DP] each
+    float* mul = muh + DP;
     float* beta_s = reinterpret_cast<float*>(smem_raw + p.beta_off);
-    float4* dtab = reinterpret_cast<float4*>(smem_raw + p.dtab_off);
+    float* dtab = reinterpret_cast<float*>(smem_raw + p.dtab_off);     // d2 per alpha
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + p.bar_off);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
@@ -202,12 +234,12 @@ __global__ void __launch_bounds__(kT5Threads, 1)
         for (int i = 0; i < kT5Stages; ++i) { mbar_init(&bars[B_XFULL + i], 1); mbar_init(&bars[B_XEMPTY + i], 2); }
         mbar_init(&bars[B_XREADY], 128);
         mbar_init(&bars[B_G1], 1);
-        mbar_init(&bars[B_ZREADY], 128);
+        for (int i = 0; i < 3; ++i) mbar_init(&bars[B_ZREADY + i], 128);
         mbar_init(&bars[B_RFULL], 1); mbar_init(&bars[B_RFULL + 1], 1);
         mbar_init(&bars[B_REMPTY], 128); mbar_init(&bars[B_REMPTY + 1], 128);
         fence_mbar_init();
     }
-    if (warp == 1) {
+    if (warp == kT5WarpIssuer) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(512u)
                      : "memory");
@@ -216,25 +248,27 @@ __global__ void __launch_bounds__(kT5Threads, 1)
     for (int i = tid; i < DP; i += blockDim.x) {
         const double m = mu_g[(long long)s * DP + i];
         const float mh = (float)m;
-        mu2[i] = make_float2(mh, (float)(m - (double)mh));
+        muh[i] = mh;
+        mul[i] = (float)(m - (double)mh);
     }
     for (int i = tid; i < NA; i += blockDim.x) {
         const float b = (i < na_out) ? betaf_g[(long long)s * AP16 + a_off + i] : 0.f;
         const float binv = 1.0f / b;
         beta_s[i] = b;
-        // beta == 0 (alpha == 1, padding): u == 0 and every term vanishes; keep the constants finite
-        dtab[i] = (b > 0.f) ? make_float4(binv - 0.5f, binv - 1.0f / 3.0f, binv - 0.25f, binv - 0.2f)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        // d_k = 1/beta - 1/k, k = 2..5: d2 comes from the table, d3..d5 = d2 + (1/2 - 1/k) are formed in the epilogue.
+        // beta == 0 (alpha == 1, padding): u == 0 and every term vanishes whatever d2 is; keep it finite
+        dtab[i] = (b > 0.f) ? binv - 0.5f : 0.f;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    S5_CTA(tid == 0, 25);
 
     const int wg = warp >> 2;
-    if (wg == 0) {
+    if (wg == 3) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 " CMF_STR(CMF_S5_REGS_CTL) ";");
-        if (warp == 0 && lane == 0) {
+        if (warp == kT5WarpProducer && lane == 0) {
             // ---------------- producer: tables once, then 64-row half tiles through the ring
             mbar_expect_tx(&bars[B_TAB], p.tab_bytes);
             const unsigned char* src = reinterpret_cast<const unsigned char*>(tab_g) +
@@ -253,59 +287,87 @@ __global__ void __launch_bounds__(kT5Threads, 1)
                 bulk_g2s(ring + slot * kT5HalfRows * DP, col_base + (long long)h * kT5HalfRows * DP, bytes,
                          &bars[B_XFULL + slot]);
             }
-        } else if (warp == 1) {
-            // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues (see elect_one())
-            const uint32_t sbase = smem_u32(smem_raw);
+        } else if (warp == kT5WarpIssuer) {
+            // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues (see elect_one()).
+            // The bases go through a lane-0 shuffle so that the compiler knows them warp-uniform: descriptors and TMEM
+            // addresses are then formed on the uniform datapath, one add per operand with the k-steps unrolled
+            // (the rolled loop with per-thread bases spent ~12 instructions and ~65 cycles per MMA on R2UR and
+            // descriptor encoding, more than the tensor pipe needs for it).
+            const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem_raw), 0);
             const uint32_t lbo1 = N1 * 16, lbo2 = (uint32_t)NA * 16;
             const uint32_t id1 = idesc_tf32(N1), id2a = idesc_tf32(NA_a), id2b = idesc_tf32(NA_b > 0 ? NA_b : 16);
+            // descriptor of k-step ks = descriptor of k-step 0 + ks * (2 K chunks of LBO bytes, in 16-byte units), low word
+            const uint32_t dhi = (uint32_t)(smem_desc(0, 0, 128) >> 32);
+            const uint32_t st1 = (2 * lbo1) >> 4, st2 = (2 * lbo2) >> 4;
             mbar_wait_guard(&bars[B_TAB], 0);
+            S5_CTA(lane == 0, 26);
             for (int t = 0; t < ntiles; ++t) {
                 const uint32_t ph = (uint32_t)(t & 1);
+                // formed per tile (a handful of uniform adds) rather than kept live across the loop
+                uint32_t sb = sbase;
+                asm volatile("" : "+r"(sb));
+                sb = __shfl_sync(0xffffffffu, sb, 0);
+                uint32_t tm = tmem;
+                asm volatile("" : "+r"(tm));
+                tm = __shfl_sync(0xffffffffu, tm, 0);
+                const uint32_t d1h = (uint32_t)smem_desc(sb + p.ph_off, lbo1, 128), d1l = (uint32_t)smem_desc(sb + p.pl_off, lbo1, 128);
+                const uint32_t d2h = (uint32_t)smem_desc(sb + p.wh_off, lbo2, 128), d2l = (uint32_t)smem_desc(sb + p.wl_off, lbo2, 128);
+                const uint32_t d2hb = d2h + (uint32_t)NA_a, d2lb = d2l + (uint32_t)NA_a;
+                S5_TL(true, t, 8);
                 mbar_wait_guard(&bars[B_XREADY], ph);
+                S5_TL(true, t, 9);
                 tc_fence_after();
-#pragma unroll 1
-                for (int ks = 0; ks < NT; ++ks) {
-                    const uint64_t dh = smem_desc(sbase + p.ph_off + 2 * ks * lbo1, lbo1, 128);
-                    const uint64_t dl = smem_desc(sbase + p.pl_off + 2 * ks * lbo1, lbo1, 128);
-                    if (elect_one()) {
-                        mma_ts_tf32(tmem + C_Y, tmem + C_XH + 8 * ks, dh, id1, ks > 0);
-                        mma_ts_tf32(tmem + C_Y, tmem + C_XL + 8 * ks, dh, id1, 1);
-                        mma_ts_tf32(tmem + C_Y, tmem + C_XH + 8 * ks, dl, id1, 1);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < NT; ++ks) {
+                        mma_ts_tf32_w(tm + C_Y, tm + C_XH + 8 * ks, d1h + ks * st1, dhi, id1, ks > 0);
+                        mma_ts_tf32_w(tm + C_Y, tm + C_XL + 8 * ks, d1h + ks * st1, dhi, id1, 1);
+                        mma_ts_tf32_w(tm + C_Y, tm + C_XH + 8 * ks, d1l + ks * st1, dhi, id1, 1);
                     }
+                    tc_commit(&bars[B_G1]);
                 }
-                if (elect_one()) tc_commit(&bars[B_G1]);
-                mbar_wait_guard(&bars[B_ZREADY], ph);
+                __syncwarp();
+                S5_TL(true, t, 10);
                 if (t > 0) mbar_wait_guard(&bars[B_REMPTY], ph ^ 1u);
-                tc_fence_after();
-#pragma unroll 1
-                for (int ks = 0; ks < NT; ++ks) {
-                    const uint64_t dh = smem_desc(sbase + p.wh_off + 2 * ks * lbo2, lbo2, 128);
-                    const uint64_t dl = smem_desc(sbase + p.wl_off + 2 * ks * lbo2, lbo2, 128);
-                    if (elect_one()) {
-                        mma_ts_tf32(tmem + C_R, tmem + C_Y + 8 * ks, dh, id2a, ks > 0);
-                        mma_ts_tf32(tmem + C_R, tmem + C_Y + 8 * ks, dl, id2a, 1);
-                        mma_ts_tf32(tmem + C_R, tmem + C_ZL + 8 * ks, dh, id2a, 1);
+                S5_TL(true, t, 12);
+#pragma unroll
+                for (int zp = 0; zp < ZP; ++zp) {
+                    if (zp * ZC < NT) {
+                        mbar_wait_guard(&bars[B_ZREADY + zp], ph);
+                        tc_fence_after();
+                        if (zp == 0) S5_TL(true, t, 11);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = zp * ZC; ks < (zp + 1) * ZC && ks < NT; ++ks) {
+                                mma_ts_tf32_w(tm + C_R, tm + C_Y + 8 * ks, d2h + ks * st2, dhi, id2a, ks > 0);
+                                mma_ts_tf32_w(tm + C_R, tm + C_Y + 8 * ks, d2l + ks * st2, dhi, id2a, 1);
+                                mma_ts_tf32_w(tm + C_R, tm + C_ZL + 8 * ks, d2h + ks * st2, dhi, id2a, 1);
+                            }
+                            if ((zp + 1) * ZC >= NT) tc_commit(&bars[B_RFULL]);
+                        }
+                        __syncwarp();
                     }
                 }
-                if (elect_one()) tc_commit(&bars[B_RFULL]);
+                S5_TL(true, t, 13);
                 if (NA_b > 0) {
                     if (t > 0) { mbar_wait_guard(&bars[B_REMPTY + 1], ph ^ 1u); tc_fence_after(); }
-#pragma unroll 1
-                    for (int ks = 0; ks < NT; ++ks) {
-                        const uint64_t dh = smem_desc(sbase + p.wh_off + 2 * ks * lbo2 + NA_a * 16, lbo2, 128);
-                        const uint64_t dl = smem_desc(sbase + p.wl_off + 2 * ks * lbo2 + NA_a * 16, lbo2, 128);
-                        if (elect_one()) {
-                            mma_ts_tf32(tmem + C_R + NA_a, tmem + C_Y + 8 * ks, dh, id2b, ks > 0);
-                            mma_ts_tf32(tmem + C_R + NA_a, tmem + C_Y + 8 * ks, dl, id2b, 1);
-                            mma_ts_tf32(tmem + C_R + NA_a, tmem + C_ZL + 8 * ks, dh, id2b, 1);
+                    S5_TL(true, t, 14);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < NT; ++ks) {
+                            mma_ts_tf32_w(tm + C_R + NA_a, tm + C_Y + 8 * ks, d2hb + ks * st2, dhi, id2b, ks > 0);
+                            mma_ts_tf32_w(tm + C_R + NA_a, tm + C_Y + 8 * ks, d2lb + ks * st2, dhi, id2b, 1);
+                            mma_ts_tf32_w(tm + C_R + NA_a, tm + C_ZL + 8 * ks, d2hb + ks * st2, dhi, id2b, 1);
                         }
+                        tc_commit(&bars[B_RFULL + 1]);
                     }
-                    if (elect_one()) tc_commit(&bars[B_RFULL + 1]);
+                    __syncwarp();
+                    S5_TL(true, t, 15);
                 }
             }
         }
         __syncwarp();
-    } else if (wg == 1) {
+    } else if (wg == 2) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 " CMF_STR(CMF_S5_REGS_CVT) ";");
         // ---------------- convert (x -> xh|xl) and square (y -> zh|zl): thread = pixel = TMEM lane
         const int q = warp & 3, row = 32 * q + lane, myhalf = q >> 1, rin = row & (kT5HalfRows - 1);
@@ -313,13 +375,19 @@ __global__ void __launch_bounds__(kT5Threads, 1)
         // loops stay rolled: one warp per scheduler runs this code, so its footprint has to sit in the
         // instruction cache (the unrolled first version spent most of its time in instruction fetch)
         auto square8 = [&](uint32_t (&y)[8], int c) {
+            // packed pairs for the FP32 part; zl goes to TMEM unrounded (the tensor core reads the TF32 bits only)
             uint32_t lo[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float yv = __uint_as_float(y[e]);
-                const float z = yv * yv;
-                y[e] = tf32_round(z);
-                lo[e] = tf32_trunc(z - __uint_as_float(y[e]));
+            for (int e = 0; e < 8; e += 2) {
+                const uint64_t yy = f2_pack_u(y[e], y[e + 1]);
+                const uint64_t z = f2_mul(yy, yy);
+                float z0, z1, l0, l1;
+                f2_unpack(z, z0, z1);
+                y[e] = tf32_round(z0);
+                y[e + 1] = tf32_round(z1);
+                f2_unpack(f2_sub(z, f2_pack_u(y[e], y[e + 1])), l0, l1);
+                lo[e] = __float_as_uint(l0);
+                lo[e + 1] = __float_as_uint(l1);
             }
             tmem_st8(tl + C_Y + 8 * c, y);
             tmem_st8(tl + C_ZL + 8 * c, lo);
@@ -328,50 +396,81 @@ __global__ void __launch_bounds__(kT5Threads, 1)
         for (int t = 0; t <= ntiles; ++t) {
             if (t > 0) {
                 // ---- y -> zh | zl of tile t-1
+                S5_TL(q == 0, t - 1, 0);
                 mbar_wait_guard(&bars[B_G1], (uint32_t)((t - 1) & 1));
+                S5_TL(q == 0, t - 1, 1);
                 tc_fence_after();
                 uint32_t ya[8], yb[8];
                 tmem_ld8(tl + C_Y, ya);
+                auto hand_over = [&](int c) {                     // after k-step c: the part that ends here is complete
+                    if ((c + 1) % ZC == 0 || c + 1 == NT) {
+                        tc_wait_st();
+                        tc_fence_before();
+                        mbar_arrive(&bars[B_ZREADY + c / ZC]);
+                    }
+                };
 #pragma unroll 1
                 for (int c = 0; c < NT; c += 2) {
                     tc_wait_ld();
                     if (c + 1 < NT) tmem_ld8(tl + C_Y + 8 * (c + 1), yb);
                     square8(ya, c);
+                    hand_over(c);
                     if (c + 1 < NT) {
                         tc_wait_ld();
                         if (c + 2 < NT) tmem_ld8(tl + C_Y + 8 * (c + 2), ya);
                         square8(yb, c + 1);
+                        hand_over(c + 1);
                     }
                 }
-                tc_wait_st();
-                tc_fence_before();
-                mbar_arrive(&bars[B_ZREADY]);
+                S5_TL(q == 0, t - 1, 2);
             }
             if (t < ntiles) {
                 // ---- x -> xh | xl of tile t
                 const int h = 2 * t + myhalf, slot = h % kT5Stages, use = h / kT5Stages;
                 const bool have = h < nhalf;
+                S5_TL(q == 0, t, 3);
                 if (have) mbar_wait_guard(&bars[B_XFULL + slot], (uint32_t)(use & 1));
-                const bool row_ok = have && (128 * t + row < nrows);
-                const float4* src = reinterpret_cast<const float4*>(ring + (slot * kT5HalfRows + rin) * DP);
+                S5_TL(q == 0, t, 4);
+                const float* xrow = ring + (slot * kT5HalfRows + rin) * DP;
+                // a dropped pixel is NaN in every band of xt (repack), so band 0 tells; rows past the chunk end and
+                // dropped pixels become exact zeros through the masks of the TF32 split (NaN & 0 == 0)
+                const float x0 = xrow[0];                                   // stale but in-bounds when !have
+                const bool row_ok = have && (128 * t + row < nrows) && x0 == x0;
+                const ulonglong2* src = reinterpret_cast<const ulonglong2*>(xrow);
+                const ulonglong2* mh2 = reinterpret_cast<const ulonglong2*>(muh);
+                const ulonglong2* ml2 = reinterpret_cast<const ulonglong2*>(mul);
+                auto convert = [&](auto masked) {
+                    constexpr bool MASKED = decltype(masked)::value;
+                    const uint32_t mask = (!MASKED || row_ok) ? 0xffffe000u : 0u, keep = row_ok ? 0xffffffffu : 0u;
 #pragma unroll 1
-                for (int c = 0; c < NT; ++c) {
-                    float x[8];
-                    {
-                        const float4 a = src[2 * c], b = src[2 * c + 1];    // stale but in-bounds when !row_ok
-                        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-                    }
-                    uint32_t hi[8], lo[8];
+                    for (int c = 0; c < NT; ++c) {
+                        uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float2 m = mu2[8 * c + e];
-                        const float v = (row_ok && x[e] == x[e]) ? (x[e] - m.x) - m.y : 0.f;
-                        hi[e] = tf32_round(v);
-                        lo[e] = tf32_trunc(v - __uint_as_float(hi[e]));
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const ulonglong2 x = src[2 * c + h2], mh = mh2[2 * c + h2], ml = ml2[2 * c + h2];
+                            const uint64_t va = f2_sub(f2_sub(x.x, mh.x), ml.x), vb = f2_sub(f2_sub(x.y, mh.y), ml.y);
+                            float v0, v1, v2, v3, l0, l1, l2, l3;
+                            f2_unpack(va, v0, v1);
+                            f2_unpack(vb, v2, v3);
+                            hi[4 * h2 + 0] = (__float_as_uint(v0) + 0x1000u) & mask;
+                            hi[4 * h2 + 1] = (__float_as_uint(v1) + 0x1000u) & mask;
+                            hi[4 * h2 + 2] = (__float_as_uint(v2) + 0x1000u) & mask;
+                            hi[4 * h2 + 3] = (__float_as_uint(v3) + 0x1000u) & mask;
+                            // xl goes to TMEM unrounded: the tensor core reads the TF32 bits only
+                            f2_unpack(f2_sub(va, f2_pack_u(hi[4 * h2 + 0], hi[4 * h2 + 1])), l0, l1);
+                            f2_unpack(f2_sub(vb, f2_pack_u(hi[4 * h2 + 2], hi[4 * h2 + 3])), l2, l3);
+                            lo[4 * h2 + 0] = MASKED ? (__float_as_uint(l0) & keep) : __float_as_uint(l0);
+                            lo[4 * h2 + 1] = MASKED ? (__float_as_uint(l1) & keep) : __float_as_uint(l1);
+                            lo[4 * h2 + 2] = MASKED ? (__float_as_uint(l2) & keep) : __float_as_uint(l2);
+                            lo[4 * h2 + 3] = MASKED ? (__float_as_uint(l3) & keep) : __float_as_uint(l3);
+                        }
+                        tmem_st8(tl + C_XH + 8 * c, hi);
+                        tmem_st8(tl + C_XL + 8 * c, lo);
                     }
-                    tmem_st8(tl + C_XH + 8 * c, hi);
-                    tmem_st8(tl + C_XL + 8 * c, lo);
-                }
+                };
+                // the masks cost one operation per element: only warps that hold a dropped pixel or a row past the end pay
+                if (__all_sync(0xffffffffu, row_ok)) convert(std::false_type{});
+                else convert(std::true_type{});
                 tc_wait_st();
                 if (have) {
                     __syncwarp();
@@ -379,23 +478,26 @@ __global__ void __launch_bounds__(kT5Threads, 1)
                 }
                 tc_fence_before();
                 mbar_arrive(&bars[B_XREADY]);
+                S5_TL(q == 0, t, 5);
             }
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 " CMF_STR(CMF_S5_REGS_EPI) ";");
         // ---------------- epilogue: thread = pixel, one half of the alphas, per-alpha sums in registers
-        const int q = warp & 3, half = (warp - 8) >> 2;
+        const int q = warp & 3, half = warp >> 2;
         const int ntile = half ? nt_b : nt_a;
         const int cb = half ? NA_a : 0;
         const uint32_t tl = tmem + ((uint32_t)(32 * q) << 16) + C_R + (uint32_t)cb;
-        float acc[NH16][16];
+        uint64_t acc[NH16][8];                                    // per-alpha sums, two alphas per 64-bit register
 #pragma unroll
         for (int k = 0; k < NH16; ++k)
 #pragma unroll
-            for (int e = 0; e < 16; ++e) acc[k][e] = 0.f;
+            for (int e = 0; e < 8; ++e) acc[k][e] = 0ull;
         if (ntile > 0) {
             for (int t = 0; t < ntiles; ++t) {
+                S5_TL(q == 0, t, 16 + 4 * half);
                 mbar_wait_guard(&bars[B_RFULL + half], (uint32_t)(t & 1));
+                S5_TL(q == 0, t, 17 + 4 * half);
                 tc_fence_after();
                 uint32_t rbuf[2][16];
                 tmem_ld16(tl, rbuf[0]);
@@ -404,52 +506,73 @@ __global__ void __launch_bounds__(kT5Threads, 1)
                     if (k < ntile) {
                         tc_wait_ld();
                         if (k + 1 < NH16 && k + 1 < ntile) tmem_ld16(tl + 16 * (k + 1), rbuf[(k + 1) & 1]);
-                        float r[16], u[16], umax = 0.f;
-                        const float4* bp = reinterpret_cast<const float4*>(beta_s + cb + 16 * k);
+                        // packed FP32 pairs throughout: u = beta r, g = u^2 (d2 + d3 u + d4 u^2 + d5 u^3); beta and d2 come
+                        // from broadcast 16-byte reads (four alphas each), d3..d5 by addition; d2 is read after the
+                        // range check so that it is not live across it
+                        uint64_t u[8];
+                        float umax = 0.f;
+                        const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(beta_s + cb + 16 * k);
+                        const float* dp = dtab + cb + 16 * k;
 #pragma unroll
                         for (int v4 = 0; v4 < 4; ++v4) {
-                            const float4 b = bp[v4];
-                            const float bb[4] = {b.x, b.y, b.z, b.w};
+                            const ulonglong2 b = bp[v4];
+                            u[2 * v4] = f2_mul(b.x, f2_pack_u(rbuf[k & 1][4 * v4], rbuf[k & 1][4 * v4 + 1]));
+                            u[2 * v4 + 1] = f2_mul(b.y, f2_pack_u(rbuf[k & 1][4 * v4 + 2], rbuf[k & 1][4 * v4 + 3]));
+                        }
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                r[4 * v4 + e] = __uint_as_float(rbuf[k & 1][4 * v4 + e]);
-                                u[4 * v4 + e] = bb[e] * r[4 * v4 + e];
-                                umax = fmaxf(umax, fabsf(u[4 * v4 + e]));
-                            }
+                        for (int e = 0; e < 8; ++e) {
+                            float ua, ub;
+                            f2_unpack(u[e], ua, ub);
+                            umax = fmaxf(umax, fmaxf(fabsf(ua), fabsf(ub)));
                         }
                         if (!(umax == umax)) umax = 1.0f;                   // NaN -> slow path -> poison
                         const unsigned big = __ballot_sync(0xffffffffu, umax > 0x1p-6f);
-                        const float4* dp = dtab + cb + 16 * k;
                         if (big == 0u) {
+                            const uint64_t c3 = f2_pack(1.0f / 6.0f, 1.0f / 6.0f), c4 = f2_pack(0.25f, 0.25f),
+                                           c5 = f2_pack(0.3f, 0.3f);
+                            const ulonglong2* d2p = reinterpret_cast<const ulonglong2*>(dp);
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) {
-                                const float4 d = dp[e];                     // d2..d5 of this alpha (broadcast)
-                                const float pz = fmaf(fmaf(fmaf(d.w, u[e], d.z), u[e], d.y), u[e], d.x);
-                                acc[k][e] = fmaf(u[e] * u[e], pz, acc[k][e]);
+                            for (int v4 = 0; v4 < 4; ++v4) {
+                                const ulonglong2 dd = d2p[v4];
+#pragma unroll
+                                for (int h2 = 0; h2 < 2; ++h2) {
+                                    const int e = 2 * v4 + h2;
+                                    const uint64_t d2 = h2 ? dd.y : dd.x;
+                                    const uint64_t uu = f2_mul(u[e], u[e]);
+                                    const uint64_t t1 = f2_fma(f2_add(d2, c3), u[e], d2);                 // d2 + d3 u
+                                    const uint64_t t2 = f2_fma(f2_add(d2, c5), u[e], f2_add(d2, c4));     // d4 + d5 u
+                                    acc[k][e] = f2_fma(uu, f2_fma(t2, uu, t1), acc[k][e]);
+                                }
                             }
                         } else {
-                            float g[16], rc[16];                // copies keep r itself in registers
+                            float g[16], rc[16];
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) rc[e] = r[e];
+                            for (int e = 0; e < 16; ++e) rc[e] = __uint_as_float(rbuf[k & 1][e]);
                             g_cold16(rc, beta_s + cb + 16 * k, dp, g);
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) acc[k][e] += g[e];
+                            for (int e = 0; e < 8; ++e) acc[k][e] = f2_add(acc[k][e], f2_pack(g[2 * e], g[2 * e + 1]));
                         }
                     }
                 }
                 tc_fence_before();
                 mbar_arrive(&bars[B_REMPTY + half]);
+                S5_TL(q == 0, t, 18 + 4 * half);
             }
         }
+        S5_CTA(warp == 0 && lane == 0, 28);
         // every x tile has been consumed by now: the ring doubles as the reduction scratch [8 warps][NH16*16].
         // Butterfly with halving: after the five exchanges lane l holds the 32-lane total of value l.
-        double* red = reinterpret_cast<double*>(ring) + (warp - 8) * (NH16 * 16);
+        double* red = reinterpret_cast<double*>(ring) + warp * (NH16 * 16);
 #pragma unroll
         for (int g0 = 0; g0 < NH16 * 16; g0 += 32) {
             constexpr int kTot = NH16 * 16;
             double v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (g0 + i < kTot) ? (double)acc[(g0 + i) >> 4][(g0 + i) & 15] : 0.0;
+            for (int i = 0; i < 32; i += 2) {
+                float a0 = 0.f, a1 = 0.f;
+                if (g0 + i < kTot) f2_unpack(acc[(g0 + i) >> 4][((g0 + i) & 15) >> 1], a0, a1);
+                v[i] = (double)a0; v[i + 1] = (double)a1;
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const bool up = (lane & o) != 0;
@@ -462,10 +585,12 @@ __global__ void __launch_bounds__(kT5Threads, 1)
             if (g0 + lane < kTot) red[g0 + lane] = v[0];
         }
     }
+    S5_CTA(warp == 0 && lane == 0, 29);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 1) {
+    S5_CTA(tid == 0, 30);
+    if (warp == kT5WarpIssuer) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
     const double* red = reinterpret_cast<const double*>(ring);
@@ -476,6 +601,7 @@ __global__ void __launch_bounds__(kT5Threads, 1)
         for (int w = 0; w < 4; ++w) a += red[(4 * half + w) * (NH16 * 16) + j];
         out[i] = a;
     }
+    S5_CTA(tid == 0, 31);
 }
 
 #ifdef CMF_TUNING_HOOKS
@@ -541,6 +667,94 @@ __global__ void __launch_bounds__(128, 1)
     __syncthreads();
     tc_fence_after();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// Issue rate of the TS-form TF32 MMA in isolation (cmf_microbench kind 40 + N/16): one CTA, `reps` rounds of 27 MMAs
+// (9 k-steps x {A0.B0, A1.B0, A0.B1}, the pattern of GEMM1 / GEMM2) into one 128 x N accumulator; cycles per MMA.
+__global__ void __launch_bounds__(128, 1) tc5_rate_kernel(int N, int reps, int same_d, long long* out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 18 * N * 8; i += blockDim.x) reinterpret_cast<float*>(smem_raw)[i] = 0.f;
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    {
+        uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const uint32_t tl = tmem + ((uint32_t)(32 * warp) << 16);
+        for (int c = 0; c < 18; ++c) tmem_st8(tl + 8 * c, z);
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+        const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem_raw), 0);
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint32_t lbo = (uint32_t)N * 16;
+        const uint64_t d0 = smem_desc(sbase, lbo, 128), d1 = smem_desc(sbase + 9 * 2 * lbo, lbo, 128);
+        const uint64_t st = (2 * lbo) >> 4;
+        const uint32_t id = idesc_tf32(N);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 9; ++ks) {
+                    const uint32_t dd = tm + 256 + (same_d ? 0 : (ks & 1) * 0);
+                    mma_ts_tf32(dd, tm + 8 * ks, d0 + ks * st, id, (r | ks) > 0);
+                    mma_ts_tf32(dd, tm + 72 + 8 * ks, d0 + ks * st, id, 1);
+                    mma_ts_tf32(dd, tm + 8 * ks, d1 + ks * st, id, 1);
+                }
+            }
+            __syncwarp();
+        }
+        if (elect_one()) tc_commit(&bar);
+        __syncwarp();
+        mbar_wait_guard(&bar, 0);
+        const long long t1 = clock64();
+        if (tid == 0) out[0] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// Issue interval of FFMA and of the packed FFMA2 (cmf_microbench kinds 60..63): `warps` warps per scheduler, 16
+// independent accumulator chains per thread; cycles per warp instruction and scheduler.
+template <int PACKED>
+__global__ void __launch_bounds__(512, 1) fma_rate_kernel(int iters, float seed, long long* out, float* sink) {
+    float a[16];
+    uint64_t b[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a[i] = seed + i; b[i] = f2_pack(seed + i, seed - i); }
+    const float m = seed * 0.5f, c = seed * 0.25f;
+    const uint64_t m2 = f2_pack(m, m), c2 = f2_pack(c, c);
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (PACKED) b[i] = f2_fma(b[i], m2, c2);
+            else a[i] = fmaf(a[i], m, c);
+        }
+    }
+    const long long t1 = clock64();
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { float x, y; f2_unpack(b[i], x, y); r += a[i] + x + y; }
+    if (r == 123.456f) sink[0] = r;
+    if (threadIdx.x == 0) out[0] = t1 - t0;
 }
 
 #endif  // CMF_TUNING_HOOKS
@@ -610,6 +824,41 @@ void launch_screen5(const Dims& d, const float* xt, const double* mu, const int*
 }
 
 #ifdef CMF_TUNING_HOOKS
+// the timeline the last screening launch left behind: [4 tiles][32 events] SM clocks (0 = event not reached)
+int screen5_timeline(long long* out) {
+    return cudaMemcpyFromSymbol(out, g_s5_tl, sizeof(long long) * 4 * 32) == cudaSuccess ? 0 : -1;
+}
+
+// cycles per FFMA (packed = 0) or FFMA2 (packed = 1) warp instruction and scheduler with `warps` warps per scheduler
+double fma_issue_rate(int packed, int warps) {
+    long long* d = nullptr;
+    float* sink = nullptr;
+    long long h = 0;
+    cudaMalloc(&d, sizeof(long long));
+    cudaMalloc(&sink, sizeof(float));
+    const int iters = 2000;
+    if (packed) fma_rate_kernel<1><<<1, 128 * warps>>>(iters, 1.0f, d, sink);
+    else fma_rate_kernel<0><<<1, 128 * warps>>>(iters, 1.0f, d, sink);
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d); cudaFree(sink);
+    return e == cudaSuccess ? (double)h / (16.0 * iters * warps) : -1.0;
+}
+
+// cycles per TS-form TF32 MMA (M = 128, K = 8) with N columns, issued back to back by one CTA
+double screen5_mma_rate(int N, int reps) {
+    long long* d = nullptr;
+    long long h = 0;
+    cudaMalloc(&d, sizeof(long long));
+    const size_t smem = (size_t)18 * N * 32;
+    cudaFuncSetAttribute(tc5_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc5_rate_kernel<<<1, 128, smem>>>(N, reps, 1, d);
+    const cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? (double)h / (27.0 * reps) : -1.0;
+}
+
 // max |D - A.B^T| of one tcgen05 TS-form contraction against the host; < 0 on a CUDA error
 double screen5_selftest(int N, int K, int row_off, int swap_lbo_sbo) {
     const int NB = N + row_off;

@@ -448,7 +448,19 @@ extern "C" double cmf_microbench(int device, int kind, int iters) {
         else if (kind == 24) result = cmf::screen5_selftest(72, 72, 0, 0);
         else result = cmf::screen5_selftest(256, 8, 0, 0);
     }
+    else if (kind >= 40 && kind <= 56) {
+        // cycles per TS-form TF32 MMA with N = 16 (kind - 40) columns (kind 40: N = 256)
+        result = cmf::screen5_mma_rate(kind == 40 ? 256 : 16 * (kind - 40), iters);
+    }
+    else if (kind >= 60 && kind <= 63) {
+        // cycles per FFMA (60, 61) / FFMA2 (62, 63) warp instruction and scheduler, 1 or 4 warps per scheduler
+        result = cmf::fma_issue_rate(kind >= 62, (kind & 1) ? 4 : 1);
+    }
     if (cudaGetLastError() != cudaSuccess) result = -1.0;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return result;
 }
+
+// SM clocks at the hand-offs of four consecutive 128-pixel tiles of one CTA of the last loo_screen5_kernel launch
+// (tools/s5_timeline.py): out[4][32], 0 where an event was not reached
+extern "C" int cmf_tools_s5_timeline(long long* out) { return out ? cmf::screen5_timeline(out) : -1; }
