@@ -667,6 +667,8 @@ int cmf_set_problem(cmf_ctx* ctx, const cmf_problem* p) {
     ctx->can_screen = loo && d.NT2 <= 64 && (screen5_supported(d) || screen_smem_bytes(d) <= 227 * 1024);
     ctx->use_screen5 = ctx->can_screen && screen5_supported(d);
     if (const char* e = cmf_hook("CMF_SCREEN_IMPL")) if (strcmp(e, "legacy") == 0) ctx->use_screen5 = false;
+    if (ctx->use_screen5) ctx->nchunk_screen = screen5_pick_chunks(d, ctx->sm_count);
+    if (const char* e = cmf_hook("CMF_SCREEN_CHUNKS")) ctx->nchunk_screen = std::max(1, atoi(e));   // tuning hook (tools build)
     if (const char* e = cmf_hook("CMF_EIGEN")) ctx->eigen_method = (strcmp(e, "jacobi") == 0) ? 1 : 0;
     }
 

@@ -100,6 +100,7 @@ size_t screen_smem_bytes(const Dims& d);
 // tcgen05 / TMEM form of the screening pass (k_screen5.cu); falls back to launch_screen when unsupported
 bool screen5_supported(const Dims& d);
 size_t screen5_table_floats(const Dims& d);
+int screen5_pick_chunks(const Dims& d, int sm_count);
 void launch_screen5(const Dims& d, const float* xt, const double* mu, const int* n, const int* nloo,
                     const double* alphas, const double* P, const double* lam, float* tab, float* betaf,
                     int nchunk, double* fscreen, cudaStream_t st);

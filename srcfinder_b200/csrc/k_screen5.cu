@@ -788,6 +788,24 @@ size_t screen5_table_floats(const Dims& d) {
     return (size_t)parts * (t5_plan(d.NT, (d.NT16 + parts - 1) / parts).tab_bytes / 4);
 }
 
+// Line chunks per column for the screening pass: a CTA costs its 128-pixel tiles plus a fixed start / end (tables,
+// pipeline fill, final reduction: about 2.5 tiles, measured with tools/s5_timeline.py), CTAs run in waves of one per SM.
+int screen5_pick_chunks(const Dims& d, int sm_count) {
+    int best = 1;
+    double best_cost = 0.0;
+    for (int n = 1; n <= 16; ++n) {
+        int lpc = (d.L + n - 1) / n;
+        lpc = (lpc + 127) / 128 * 128;
+        const int n_eff = (d.L + lpc - 1) / lpc;
+        if (n_eff != n) continue;
+        const long long ctas = (long long)d.S * n;
+        const long long waves = (ctas + sm_count - 1) / sm_count;
+        const double cost = (double)waves * (lpc / 128 + 2.5);
+        if (n == 1 || cost < best_cost * 0.995) { best_cost = cost; best = n; }
+    }
+    return best;
+}
+
 int screen5_lines_per_chunk(const Dims& d, int nchunk) {
     int lpc = (d.L + nchunk - 1) / nchunk;
     return (lpc + 127) / 128 * 128;
