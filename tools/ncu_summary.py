@@ -37,7 +37,10 @@ _SCALE = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3,
 def main():
     rep, out_md = sys.argv[1], sys.argv[2]
     traffic_path = sys.argv[3] if len(sys.argv) > 3 else None
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):                     # the raw page exported on the GPU box (`ncu -i ... --page raw --csv`)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
