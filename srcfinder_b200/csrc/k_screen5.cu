@@ -80,16 +80,15 @@ constexpr int kT5HalfRows = 64;
 // The epilogue sums g = h + u per alpha, where h = log(1-u) + r u/(1-u) and u = beta r (log q + r/q = r + h):
 //     g = sum_{k>=2} u^k (1/beta - 1/k)
 // sum_k u_k = beta sum_k r_k is known in closed form (rsum), so K3b subtracts it in FP64.  d_k = 1/beta - 1/k
-// are per-alpha constants: k = 2..5 come from a shared-memory table (terms to u^5: |u| <= 2^-6), k <= 10
+// are per-alpha constants: d2 comes from a shared-memory table, the others from it (terms to u^5: |u| <= 2^-6), k <= 10
 // (|u| <= 2^-3) are formed on the fly; anything larger is the rare out-of-line slow path.
 // Everything that is not the 5-term fast path, out of line so that the hot loop stays small: 10 terms while
 // |u| <= 2^-3 (u^11 < 2^-33), log1p and a division up to u = 1/4, poison beyond.
-// dp: d2 = 1/beta - 1/2 of these 16 alphas
-__device__ __noinline__ void g_cold16(const float* __restrict__ rp, const float* __restrict__ beta,
-                                      const float* __restrict__ dp, float* __restrict__ g) {
-    float r[16], u[16], umax = 0.f;
+// up: u = beta r of these 16 alphas (GEMM2 delivers it, beta is folded into W), dp: d2 = 1/beta - 1/2
+__device__ __noinline__ void g_cold16(const float* __restrict__ up, const float* __restrict__ dp, float* __restrict__ g) {
+    float u[16], umax = 0.f;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) { r[e] = rp[e]; u[e] = beta[e] * r[e]; umax = fmaxf(umax, fabsf(u[e])); }
+    for (int e = 0; e < 16; ++e) { u[e] = up[e]; umax = fmaxf(umax, fabsf(u[e])); }
     if (!(umax == umax)) umax = 1.0f;
     if (__ballot_sync(0xffffffffu, umax > 0x1p-3f) == 0u) {
         float pz[16], binv[16];
@@ -106,10 +105,11 @@ __device__ __noinline__ void g_cold16(const float* __restrict__ rp, const float*
     } else {
 #pragma unroll 1
         for (int e = 0; e < 16; ++e) {
-            const float uu = beta[e] * rp[e], au = fabsf(uu);
+            const float uu = up[e], au = fabsf(uu), binv = dp[e] + 0.5f;
             // beyond u = 1/4 the term amplifies the TF32 error of r by u/(1-u) and more: such a pixel is an
-            // extreme outlier (x'G^-1 x > n/4); poison the sum so that the column is searched in FP64
-            g[e] = (au <= 0.25f) ? (log1pf(-uu) + rp[e] * uu / (1.0f - uu)) + uu : __int_as_float(0x7fc00000);
+            // extreme outlier (x'G^-1 x > n/4); poison the sum so that the column is searched in FP64.
+            // r u / (1 - u) with r = u / beta
+            g[e] = (au <= 0.25f) ? (log1pf(-uu) + binv * uu * uu / (1.0f - uu)) + uu : __int_as_float(0x7fc00000);
         }
     }
 }
@@ -118,7 +118,7 @@ __device__ __noinline__ void g_cold16(const float* __restrict__ rp, const float*
 struct T5Plan {
     int DP, N1, NA, KC;
     uint32_t ph_off, pl_off, wh_off, wl_off, tab_bytes;      // B operand tables (one bulk copy)
-    uint32_t ring_off, mu_off, beta_off, dtab_off, bar_off, total;
+    uint32_t ring_off, mu_off, dtab_off, bar_off, total;
 };
 
 __host__ __device__ inline T5Plan t5_plan(int NT, int NT16) {
@@ -129,8 +129,7 @@ __host__ __device__ inline T5Plan t5_plan(int NT, int NT16) {
     p.tab_bytes = 2 * pbytes + 2 * wbytes;
     p.ring_off = p.tab_bytes;
     p.mu_off = p.ring_off + (uint32_t)kT5Stages * kT5HalfRows * p.DP * 4;
-    p.beta_off = p.mu_off + (uint32_t)p.DP * 8;
-    p.dtab_off = (p.beta_off + (uint32_t)p.NA * 4 + 15u) & ~15u;       // d2 = 1/beta - 1/2 per alpha
+    p.dtab_off = (p.mu_off + (uint32_t)p.DP * 8 + 15u) & ~15u;         // d2 = 1/beta - 1/2 per alpha
     p.bar_off = p.dtab_off + (uint32_t)p.NA * 4;
     p.total = p.bar_off + 24 * 8;
     return p;
@@ -143,7 +142,8 @@ enum { B_TAB = 0, B_XFULL = 1, B_XEMPTY = 4, B_XREADY = 7, B_G1 = 8, B_RFULL = 1
 
 // ------------------------------------------------------------------ B operand tables
 // tab[s] = Ph | Pl | Wh | Wl, each [K chunk c][row][4]: P rows are eigen-directions j (K = band b),
-// W rows are alphas i (K = eigen-direction j); hi = tf32(v), lo = tf32(v - hi).
+// W rows are alphas i (K = eigen-direction j), scaled by beta_i so that GEMM2 delivers u = beta r directly;
+// hi = tf32(v), lo = tf32(v - hi).
 __global__ void __launch_bounds__(256)
     screen5_tables_kernel(const int* __restrict__ n_g, const int* __restrict__ nloo_g,
                           const double* __restrict__ alphas, int A, int D, int NT, int NT16c, int nparts, int AP16,
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256)
         if (j < D && i < A) {
             const double al = alphas[i];
             const double be = (1.0 - al) / (dn - 1.0);
-            w = 1.0 / (dn * be * lam[j] + al);
+            w = be / (dn * be * lam[j] + al);                  // beta folded in: GEMM2 delivers u = beta r
         }
         const float hi = to_tf32((float)w);
         tab[p.wh_off / 4 + idx] = hi;
@@ -224,7 +224,6 @@ __global__ void __launch_bounds__(kT5Threads, 1)
     float* ring = reinterpret_cast<float*>(smem_raw + p.ring_off);
     float* muh = reinterpret_cast<float*>(smem_raw + p.mu_off);        // column mean, FP32 head and tail, [DP] each
     float* mul = muh + DP;
-    float* beta_s = reinterpret_cast<float*>(smem_raw + p.beta_off);
     float* dtab = reinterpret_cast<float*>(smem_raw + p.dtab_off);     // d2 per alpha
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + p.bar_off);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
@@ -254,7 +253,6 @@ __global__ void __launch_bounds__(kT5Threads, 1)
     for (int i = tid; i < NA; i += blockDim.x) {
         const float b = (i < na_out) ? betaf_g[(long long)s * AP16 + a_off + i] : 0.f;
         const float binv = 1.0f / b;
-        beta_s[i] = b;
         // d_k = 1/beta - 1/k, k = 2..5: d2 comes from the table, d3..d5 = d2 + (1/2 - 1/k) are formed in the epilogue.
         // beta == 0 (alpha == 1, padding): u == 0 and every term vanishes whatever d2 is; keep it finite
         dtab[i] = (b > 0.f) ? binv - 0.5f : 0.f;
@@ -506,30 +504,24 @@ __global__ void __launch_bounds__(kT5Threads, 1)
                     if (k < ntile) {
                         tc_wait_ld();
                         if (k + 1 < NH16 && k + 1 < ntile) tmem_ld16(tl + 16 * (k + 1), rbuf[(k + 1) & 1]);
-                        // packed FP32 pairs throughout: u = beta r, g = u^2 (d2 + d3 u + d4 u^2 + d5 u^3); beta and d2 come
-                        // from broadcast 16-byte reads (four alphas each), d3..d5 by addition; d2 is read after the
-                        // range check so that it is not live across it
+                        // GEMM2 delivers u = beta r (beta is folded into W).  Packed FP32 pairs throughout:
+                        //   g = u^2 (d2 + d3 u + d4 u^2 + d5 u^3),  d_k = 1/beta - 1/k = d2 + (1/2 - 1/k)
+                        //     = u^2 (d2 (1 + u)(1 + u^2) + u (1/6 + u/4))          [+ 0.3 u^5: < 1e-8 of g for |u| <= 2^-6]
+                        // one broadcast 16-byte read of d2 per four alphas, after the range check
                         uint64_t u[8];
                         float umax = 0.f;
-                        const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(beta_s + cb + 16 * k);
                         const float* dp = dtab + cb + 16 * k;
 #pragma unroll
-                        for (int v4 = 0; v4 < 4; ++v4) {
-                            const ulonglong2 b = bp[v4];
-                            u[2 * v4] = f2_mul(b.x, f2_pack_u(rbuf[k & 1][4 * v4], rbuf[k & 1][4 * v4 + 1]));
-                            u[2 * v4 + 1] = f2_mul(b.y, f2_pack_u(rbuf[k & 1][4 * v4 + 2], rbuf[k & 1][4 * v4 + 3]));
-                        }
-#pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            float ua, ub;
-                            f2_unpack(u[e], ua, ub);
-                            umax = fmaxf(umax, fmaxf(fabsf(ua), fabsf(ub)));
+                            u[e] = f2_pack_u(rbuf[k & 1][2 * e], rbuf[k & 1][2 * e + 1]);
+                            umax = fmaxf(umax, fmaxf(fabsf(__uint_as_float(rbuf[k & 1][2 * e])),
+                                                     fabsf(__uint_as_float(rbuf[k & 1][2 * e + 1]))));
                         }
                         if (!(umax == umax)) umax = 1.0f;                   // NaN -> slow path -> poison
                         const unsigned big = __ballot_sync(0xffffffffu, umax > 0x1p-6f);
                         if (big == 0u) {
-                            const uint64_t c3 = f2_pack(1.0f / 6.0f, 1.0f / 6.0f), c4 = f2_pack(0.25f, 0.25f),
-                                           c5 = f2_pack(0.3f, 0.3f);
+                            const uint64_t one = f2_pack(1.0f, 1.0f), c3 = f2_pack(1.0f / 6.0f, 1.0f / 6.0f),
+                                           c4 = f2_pack(0.25f, 0.25f);
                             const ulonglong2* d2p = reinterpret_cast<const ulonglong2*>(dp);
 #pragma unroll
                             for (int v4 = 0; v4 < 4; ++v4) {
@@ -539,16 +531,17 @@ __global__ void __launch_bounds__(kT5Threads, 1)
                                     const int e = 2 * v4 + h2;
                                     const uint64_t d2 = h2 ? dd.y : dd.x;
                                     const uint64_t uu = f2_mul(u[e], u[e]);
-                                    const uint64_t t1 = f2_fma(f2_add(d2, c3), u[e], d2);                 // d2 + d3 u
-                                    const uint64_t t2 = f2_fma(f2_add(d2, c5), u[e], f2_add(d2, c4));     // d4 + d5 u
-                                    acc[k][e] = f2_fma(uu, f2_fma(t2, uu, t1), acc[k][e]);
+                                    const uint64_t a1 = f2_add(u[e], one);
+                                    const uint64_t s4 = f2_fma(uu, a1, a1);                          // (1 + u)(1 + u^2)
+                                    const uint64_t hu = f2_mul(f2_fma(c4, u[e], c3), u[e]);          // u (1/6 + u/4)
+                                    acc[k][e] = f2_fma(uu, f2_fma(d2, s4, hu), acc[k][e]);
                                 }
                             }
                         } else {
-                            float g[16], rc[16];
+                            float g[16], uc[16];
 #pragma unroll
-                            for (int e = 0; e < 16; ++e) rc[e] = __uint_as_float(rbuf[k & 1][e]);
-                            g_cold16(rc, beta_s + cb + 16 * k, dp, g);
+                            for (int e = 0; e < 16; ++e) uc[e] = __uint_as_float(rbuf[k & 1][e]);
+                            g_cold16(uc, dp, g);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) acc[k][e] = f2_add(acc[k][e], f2_pack(g[2 * e], g[2 * e + 1]));
                         }
