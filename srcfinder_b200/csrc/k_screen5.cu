@@ -49,8 +49,8 @@ constexpr int kT5WarpProducer = 12, kT5WarpIssuer = 13;
 // 4 a + 4 b + 8 c may not exceed 2048): the epilogue keeps 112 per-alpha accumulators per thread
 #ifndef CMF_S5_REGS_CTL
 #define CMF_S5_REGS_CTL 32
-#define CMF_S5_REGS_CVT 64
-#define CMF_S5_REGS_EPI 208
+#define CMF_S5_REGS_CVT 80
+#define CMF_S5_REGS_EPI 200
 #endif
 #ifndef CMF_S5_ZP
 #define CMF_S5_ZP 3                 // hand-over parts of the squares (1..3)
@@ -398,26 +398,25 @@ __global__ void __launch_bounds__(kT5Threads, 1)
                 mbar_wait_guard(&bars[B_G1], (uint32_t)((t - 1) & 1));
                 S5_TL(q == 0, t - 1, 1);
                 tc_fence_after();
-                uint32_t ya[8], yb[8];
-                tmem_ld8(tl + C_Y, ya);
-                auto hand_over = [&](int c) {                     // after k-step c: the part that ends here is complete
-                    if ((c + 1) % ZC == 0 || c + 1 == NT) {
+                // one hand-over part (ZC k-steps) per stage, double-buffered: the loads of the next part are in flight
+                // while this part is squared, so the TMEM load latency shows once per tile, not once per k-step
+                uint32_t yb[2][ZC][8];
+#pragma unroll
+                for (int i = 0; i < ZC; ++i)
+                    if (i < NT) tmem_ld8(tl + C_Y + 8 * i, yb[0][i]);
+#pragma unroll
+                for (int zp = 0; zp < ZP; ++zp) {
+                    if (zp * ZC < NT) {
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < ZC; ++i)
+                            if ((zp + 1) * ZC + i < NT) tmem_ld8(tl + C_Y + 8 * ((zp + 1) * ZC + i), yb[(zp + 1) & 1][i]);
+#pragma unroll
+                        for (int i = 0; i < ZC; ++i)
+                            if (zp * ZC + i < NT) square8(yb[zp & 1][i], zp * ZC + i);
                         tc_wait_st();
                         tc_fence_before();
-                        mbar_arrive(&bars[B_ZREADY + c / ZC]);
-                    }
-                };
-#pragma unroll 1
-                for (int c = 0; c < NT; c += 2) {
-                    tc_wait_ld();
-                    if (c + 1 < NT) tmem_ld8(tl + C_Y + 8 * (c + 1), yb);
-                    square8(ya, c);
-                    hand_over(c);
-                    if (c + 1 < NT) {
-                        tc_wait_ld();
-                        if (c + 2 < NT) tmem_ld8(tl + C_Y + 8 * (c + 2), ya);
-                        square8(yb, c + 1);
-                        hand_over(c + 1);
+                        mbar_arrive(&bars[B_ZREADY + zp]);
                     }
                 }
                 S5_TL(q == 0, t - 1, 2);
