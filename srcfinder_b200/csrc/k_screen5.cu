@@ -48,9 +48,9 @@ constexpr int kT5WarpProducer = 12, kT5WarpIssuer = 13;
 // register budgets after setmaxnreg (4 control warps, 4 convert/square warps, 8 epilogue warps; the sum
 // 4 a + 4 b + 8 c may not exceed 2048): the epilogue keeps 112 per-alpha accumulators per thread
 #ifndef CMF_S5_REGS_CTL
-#define CMF_S5_REGS_CTL 32
-#define CMF_S5_REGS_CVT 80
-#define CMF_S5_REGS_EPI 200
+#define CMF_S5_REGS_CTL 24
+#define CMF_S5_REGS_CVT 72
+#define CMF_S5_REGS_EPI 208
 #endif
 #ifndef CMF_S5_ZP
 #define CMF_S5_ZP 3                 // hand-over parts of the squares (1..3)
