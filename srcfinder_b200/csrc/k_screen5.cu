@@ -3,8 +3,8 @@
 //
 // Same arithmetic as k_screen.cu (which stays as the path for windows that do not fit TMEM):
 //     GEMM1  Y = Xc . P                 3 x TF32 (xh.Ph + xl.Ph + xh.Pl), FP32 accumulate in TMEM
-//     GEMM2  R = (Y*Y) . W              3 x TF32 (zh.Wh + zh.Wl + zl.Wh), FP32 accumulate in TMEM
-//     h(r)   = log(1-u) + r u/(1-u), u = beta r, FP32 series, summed per alpha
+//     GEMM2  U = (Y*Y) . (beta W)       3 x TF32 (zh.Wh + zh.Wl + zl.Wh), FP32 accumulate in TMEM; u = beta r
+//     h(r)   = log(1-u) + r u/(1-u), FP32 series in u (packed FP32 pairs), summed per alpha
 // but organised for the Blackwell tensor pipe instead of per-warp mma.sync fragments:
 //   * one CTA per (column, line chunk), 128-pixel tiles: the pixel is the TMEM lane (M = 128),
 //   * the A operand never touches shared memory: the converting threads write xh|xl straight into
@@ -13,7 +13,10 @@
 //   * the B operands (P and W, hi and lo TF32 parts) sit in shared memory for the whole CTA in the
 //     canonical K-major no-swizzle core-matrix layout, built once per column by screen5_tables_kernel,
 //   * R is split into two alpha halves with their own full/empty barriers so that the FP32 epilogue
-//     of one half overlaps the tensor work of the other half and of the next tile,
+//     of one half overlaps the tensor work of the other half and of the next tile; the squares reach GEMM2 in
+//     three parts (k-steps), so the tensor pipe does not wait for the whole squaring pass,
+//   * the MMA issue path is uniform: bases through a lane-0 shuffle, descriptor arithmetic on the 32-bit start
+//     address word, k-steps unrolled (about two uniform instructions per tcgen05.mma),
 //   * warp roles: warps 0-7 epilogue (thread = pixel, 112 alphas each, accumulators in registers), warps 8-11
 //     convert and square (thread = pixel), warp 12 bulk-copy producer, warp 13 MMA issuer (one elected lane);
 //     setmaxnreg moves registers from the control warps to the epilogue warps.
