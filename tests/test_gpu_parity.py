@@ -425,6 +425,29 @@ def test_error_paths():
     eng.close()
 
 
+@pytest.mark.parametrize("active", [[309, 391], [330, 417], [351, 397]])
+def test_screened_search_equals_exact_search_other_windows(active):
+    """The tcgen05 screen on the window shapes the bench does not exercise -- the CO2 window (83 bands: alphas split
+    over two CTAs, loo_screen5_kernel<11, 4>), an 88-band window (the widest that fits) and a 47-band one (6 k-steps,
+    two per hand-over part): same alpha as the all-FP64 search in every column of a 5 000-line cube, certificate
+    measured and below its threshold."""
+    import torch
+    L, S = 5000, 96
+    ab = _abscf(active)
+    slab = synth.make_slab_torch(L, S, active[0], active[1], "cuda", seed=5)
+    torch.cuda.synchronize()
+    with ColumnwiseMF(L, 425, S, active, ab) as eng:
+        assert eng.screen_kernel() == "loo_screen5_kernel"
+        eng.bind_device(slab.data_ptr())
+        eng.run()
+        idx = eng.alpha_index(); chk = eng.screen_check(); mf = eng.results()["mf"]
+        eng.run(exact=True)
+        ex_idx = eng.alpha_index(); ex_mf = eng.results()["mf"]
+    assert np.array_equal(idx, ex_idx)
+    assert np.array_equal(mf, ex_mf)
+    assert 0.0 < chk.max() < 0.25
+
+
 def test_full_flightline_properties():
     """BASELINE config C2 (598 x 425 x 20000, active slab resident in HBM): size-independent properties.
        * w . t = 1e5 for every column (the filter is normalised to the target)
