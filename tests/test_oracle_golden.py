@@ -72,3 +72,25 @@ def test_known_answer_scaled_target():
     probe = mu + s * (ab * mu)
     assert (probe - mu).dot(w) == pytest.approx(s * 1e5, rel=1e-9)
     assert abs(res["colavg"][0]) < 1e-6 * res["colstd"][0]
+
+
+import glob
+import os
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(_GOLDEN, "looshrinkage_*.npz"))))
+def test_loo_shrinkage_restatement_matches_reference_function(path):
+    """oracle.loo_shrinkage against the reference's importable looshrinkage() called directly (fixtures of
+    oracle/make_golden.py looshrinkage), with and without the -f regulariser I_reg (:99, :131): same index, same
+    finite set, same nll and C to rounding (same LAPACK calls in the same order)."""
+    z = np.load(path)
+    nll = np.zeros(len(z["alphas"]))
+    reg = z["I_reg"] if "I_reg" in z.files else None
+    c_mat, mindex = orc.loo_shrinkage(z["I_zm"], z["alphas"], nll, int(z["n"]), x_reg=reg)
+    assert mindex == int(z["mindex"])
+    assert np.array_equal(np.isfinite(nll), np.isfinite(z["nll"]))
+    fin = np.isfinite(z["nll"])
+    assert np.allclose(nll[fin], z["nll"][fin], rtol=1e-12, atol=0.0)
+    assert np.allclose(c_mat, z["C"], rtol=1e-13, atol=0.0)
