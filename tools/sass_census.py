@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "srcfinder_b200", "libcmf_b200.so")
 OPS = ["UTCHMMA", "UTCIMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "DMMA", "HMMA", "LDGSTS", "DFMA",
-       "FFMA", "LDG", "STG"]
+       "FFMA", "FFMA2", "LDG", "STG"]
 
 
 def main():
